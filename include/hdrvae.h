@@ -1,0 +1,212 @@
+/*
+ * hdrvae.h — C ABI of libhdrvae.so: the B200 (sm_100a) Flux-VAE HDR decode path.
+ *
+ * The reference (netocg/vae-decode-hdr) has no native code and no FFI: the whole
+ * path is PyTorch eager driven from hdr_vae_decode.py.  Each entry point below
+ * names the reference interface it replaces (file:line in /root/reference).  The
+ * reference-side binding a maintainer would add is the ctypes stub shown in
+ * INTEGRATION.md (vae_decode_hdr_b200/_native.py is that stub).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, <0 on error and
+ *     records a message retrievable with hdrvae_last_error() (thread local).
+ *     The Python host raises RuntimeError; there is NO CPU fallback.
+ *   - device pointers are raw CUDA pointers owned by the caller (PyTorch
+ *     allocations).  The library owns only what lives inside an hdrvae_ctx.
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*);
+ *     no hidden host threads.  Functions that fill a host-side hdrvae_stats
+ *     synchronise that stream once at the end; pass stats == NULL to stay async.
+ *   - activations inside the library are NHWC bf16; the boundary tensors keep the
+ *     reference layouts: latent float32 NCHW in, IMAGE float32 BHWC out
+ *     (hdr_vae_decode.py:78 and :195,:354).
+ */
+#ifndef HDRVAE_H_
+#define HDRVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDRVAE_ABI_VERSION 1
+
+typedef struct hdrvae_ctx hdrvae_ctx;
+
+/* hdr_mode enum as it is in code, same order (hdr_vae_decode.py:48). */
+enum {
+  HDRVAE_MODE_CONSERVATIVE = 0,          /* smart_hdr_expansion        :941-980  */
+  HDRVAE_MODE_EXPOSURE = 1,              /* exposure_based_hdr         :982-1007 */
+  HDRVAE_MODE_ADAPTIVE_RECOVERY = 2,     /* adaptive branch            :1114-1147 */
+  HDRVAE_MODE_MATHEMATICAL_RECOVERY = 3  /* mathematical branch        :1149-1159 */
+};
+
+/* Normalisation detected by analyze_conv_out (hdr_vae_decode.py:890-897). */
+enum { HDRVAE_NORM_NONE = 0, HDRVAE_NORM_SIGMOID = 1, HDRVAE_NORM_TANH = 2 };
+
+/* element types for hdrvae_weight_desc / activations handed across the ABI */
+enum { HDRVAE_F32 = 0, HDRVAE_BF16 = 1, HDRVAE_F16 = 2 };
+
+/* decoder arithmetic: bf16 operands / fp32 accumulate on tcgen05 (kind::f16) */
+enum { HDRVAE_PRECISION_BF16 = 0 };
+
+/* conv implementation selector (debug/validation): the tcgen05 implicit-GEMM
+ * kernel is the product path; the CUDA-core direct kernel exists to validate it
+ * on the GPU and is never selected implicitly. */
+enum { HDRVAE_CONV_TCGEN05 = 0, HDRVAE_CONV_DIRECT = 1 };
+
+/*
+ * Scalars the reference computes with ~25 full-tensor reductions + host syncs
+ * (hdr_vae_decode.py:862-879, 1063-1066, 100-102, 188-191); here they come out
+ * of the fused epilogue in one struct.  "pre" = input of decoder.conv_out
+ * ([B,128,H,W]), "post" = clamp((conv_out+1)/2,0,1), "conv" = conv_out only,
+ * "pre3" = 128->3 channel MAX-pool, "rec" = logit/atanh recovered map.
+ */
+typedef struct hdrvae_stats {
+  double pre_min, pre_max, pre_mean, pre_std;     /* :862-865 (std unbiased) */
+  double post_min, post_max, post_mean, post_std; /* :867-870 */
+  double conv_min, conv_max, conv_mean;           /* :877-879 */
+  double pre3_min, pre3_max;                      /* :1065-1066 */
+  double rec_min, rec_max;                        /* :1098 */
+  double aligned_max;                             /* :1116 (adaptive mode; else NaN) */
+  double out_min, out_max;                        /* :188-189 */
+  int64_t hdr_pixels;                             /* :190  sum(out > 1.0) */
+  int64_t negative_pixels;                        /* :191  sum(out < 0.0) */
+  int64_t highlight_count;                        /* :961  sum(pre3 > 1.0) */
+  int64_t intelligent_hdr_pixels;                 /* :100  sum(decoded > 1.0) before the multiplier */
+  double intelligent_max;                         /* :102 */
+  int32_t norm_function;                          /* HDRVAE_NORM_* :890-897 */
+  int32_t has_hdr;                                /* :1078 pre3_max > 1.001 */
+  int32_t accepted;                               /* :106  hdr_pixels>0 || max>1.1 (0 => reference would bypass) */
+  int32_t reserved;
+} hdrvae_stats;
+
+/* One tensor of vae.first_stage_model.decoder.state_dict() (hdr_vae_decode.py:842):
+ * name is the state-dict key ("up.1.block.0.nin_shortcut.weight", ...), data a
+ * host or device pointer to a contiguous tensor of `dtype`. */
+typedef struct hdrvae_weight_desc {
+  const char* name;
+  const void* data;
+  int32_t dtype;      /* HDRVAE_F32 / HDRVAE_BF16 / HDRVAE_F16 */
+  int32_t ndim;
+  int64_t shape[4];
+} hdrvae_weight_desc;
+
+/* Raw, all-reducible statistics block between epilogue phase A and phase B
+ * (multi-GPU batch sharding: MIN-, MAX- and SUM-reduce the three arrays across
+ * ranks). */
+#define HDRVAE_RAW_NMIN 4
+#define HDRVAE_RAW_NMAX 4
+#define HDRVAE_RAW_NSUM 8
+typedef struct hdrvae_raw_stats {
+  float vmin[HDRVAE_RAW_NMIN];   /* pre, post, conv, pre3 */
+  float vmax[HDRVAE_RAW_NMAX];   /* pre, post, conv, pre3 */
+  double vsum[HDRVAE_RAW_NSUM];  /* pre Σx, pre Σx², post Σx, post Σx², conv Σx, n_pre, n_post, highlight_count */
+} hdrvae_raw_stats;
+
+const char* hdrvae_last_error(void);
+int hdrvae_abi_version(void);
+
+/* ---- context ------------------------------------------------------------- */
+int hdrvae_create(hdrvae_ctx** out, int device);
+int hdrvae_destroy(hdrvae_ctx* ctx);
+/* HDRVAE_CONV_TCGEN05 (default) or HDRVAE_CONV_DIRECT (validation only; also env HDRVAE_CONV_IMPL=direct). */
+int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl);
+
+/* Diagnostics: per-op CUDA-event timing of everything the library launches between begin and end
+ * (the reference's only instrumentation is logging with host syncs, hdr_vae_decode.py:81-84,188-193). */
+long long hdrvae_launch_count(void);   /* kernels launched by the library so far (process-wide) */
+int hdrvae_profile_begin(void);
+int hdrvae_profile_end(const char* path_or_null);
+
+/* Replaces the reference's reads of vae.first_stage_model.decoder.* modules
+ * (hdr_vae_decode.py:448,505-516,842,855,876): one-time repack of the state
+ * dict into K-major bf16 GEMM operands (3x3 taps, upsample phase weights,
+ * fused q/k/v) owned by the context. */
+int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n, int precision);
+
+/* Bytes of caller-provided device workspace hdrvae_decode needs for a latent
+ * batch [B,16,h,w]. */
+int hdrvae_workspace_bytes(hdrvae_ctx* ctx, int B, int h, int w, size_t* bytes);
+
+/* ---- the hot path ---------------------------------------------------------
+ * Replaces HDRVAEDecode.simple_hdr_decode's happy path (hdr_vae_decode.py:62-195):
+ * analyze_conv_out (:837) + intelligent_hdr_decode (:1009) + multiplier (:180) +
+ * _format_tensor passthrough (:209-212,:354), with ONE decoder pass.
+ *   latent_nchw : device float32 [B,16,h,w]            (:78)
+ *   out_bhwc    : device float32 [B,8h,8w,3] contiguous (:195)
+ *   expansion_factor : smart_hdr_expansion factor (1.0 for "conservative" as the
+ *                 reference calls it, 3.0 for the README "moderate" alias)
+ *   ev_multiplier    : conservative_ev_multiplier (:180-182)
+ */
+int hdrvae_decode(hdrvae_ctx* ctx, const float* latent_nchw, int B, int h, int w, int mode,
+                  float expansion_factor, float ev_multiplier, float* out_bhwc,
+                  hdrvae_stats* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same path split around the batch-global scalars for multi-GPU batch sharding
+ * (SURVEY.md §8e): begin = decoder + epilogue phase A, leaves a device-resident
+ * hdrvae_raw_stats at *raw_stats_dev (inside the workspace) that the host
+ * all-reduces; finish = scalar finalisation + phase B. */
+int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent_nchw, int B, int h, int w,
+                        void* workspace, size_t workspace_bytes, void** raw_stats_dev, void* stream);
+int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float expansion_factor,
+                         float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Decoder only: latent -> SiLU(norm_out(h)), the tensor the reference's forward
+ * hook captures (hdr_vae_decode.py:850-855), as device bf16 NHWC [B,8h,8w,128]. */
+int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent_nchw, int B, int h, int w,
+                           void* features_nhwc_bf16, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Fused HDR epilogue on caller-supplied activations (the 1e-5 parity entry):
+ * replaces analyze_conv_out's statistics + conv_out (:862-879), the MAX-pool
+ * (:1042-1056), srgb_to_linear (:1163), the recovery block (:1076-1102), the mode
+ * formulas (:1106-1159) and the multiplier (:180-182).
+ *   pre_nhwc : device [B,H,W,128], dtype HDRVAE_F32 or HDRVAE_BF16
+ *   conv_w   : device float32 [3,128,3,3] (OIHW, as in the state dict), conv_b [3]
+ *   dbg_post3 / dbg_pre3 / dbg_argmax3 : optional device outputs [B,H,W,3]
+ *               (float32, float32, int32): clamp((conv+1)/2), MAX-pool, first-max index
+ *   scratch  : device, >= hdrvae_epilogue_scratch_bytes(B,H,W)
+ */
+int hdrvae_epilogue_scratch_bytes(int B, int H, int W, size_t* bytes);
+int hdrvae_epilogue(hdrvae_ctx* ctx, const void* pre_nhwc, int dtype, int B, int H, int W,
+                    const float* conv_w, const float* conv_b, int mode, float expansion_factor,
+                    float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, float* dbg_post3,
+                    float* dbg_pre3, int32_t* dbg_argmax3, void* scratch, size_t scratch_bytes,
+                    void* stream);
+
+/* ---- kernel-level entry points (unit parity tests and micro-benchmarks) ----
+ * Generic NHWC bf16 convolution on the tcgen05 implicit-GEMM kernel (or the
+ * CUDA-core validation kernel): replaces one nn.Conv2d of ComfyUI's Decoder as
+ * driven by vae.decode (:859,:1022).
+ *   x [B,H,W,Cin] bf16, w OIHW float32 [Cout,Cin,k,k] (k = 1 or 3, pad k/2),
+ *   bias float32 [Cout] or NULL, residual bf16 [B,OH,OW,Cout] or NULL,
+ *   upsample2x != 0: nearest-2x upsample folded into the load (OH=2H, OW=2W),
+ *   y [B,OH,OW,Cout] bf16 (out_f32 != 0: float32).  */
+int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int B, int H, int W, int Cin, const float* w,
+                  const float* bias, int Cout, int ksize, int upsample2x, const void* residual,
+                  void* y, int out_f32, int impl, void* stream);
+
+/* GroupNorm(32 groups, eps 1e-6, affine) [+ SiLU] on NHWC bf16: replaces
+ * norm1/norm2/norm_out + swish of ComfyUI's Decoder.  gamma/beta float32 [C]. */
+int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int B, int HW, int C, const float* gamma,
+                          const float* beta, int apply_silu, void* y, void* stream);
+
+/* Single-head attention over T tokens, d = 512 (mid.attn_1 core):
+ * q,k,v,o device bf16 [B,T,512]; softmax(q k^T / sqrt(512)) v. */
+int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int B, int T,
+                     void* o, void* stream);
+
+/* fp32 -> fp16 round-to-nearest-even pack for LinearEXRExport
+ * (linear_exr_export.py:155,165: ndarray.astype(np.float16); overflow -> inf).
+ * layout 0: same order as the input; layout 1: EXR scanline order
+ * (per image row: B plane, G plane, R plane). image [B,H,W,3] float32 device. */
+int hdrvae_pack_half(const float* image_bhwc, int B, int H, int W, int layout, uint16_t* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDRVAE_H_ */

@@ -1,0 +1,13 @@
+"""vae_decode_hdr_b200 — B200-native (sm_100a) drop-in for the HDRVAEDecode node of
+netocg/vae-decode-hdr.  Registered exactly like the reference package (__init__.py:43-53)."""
+from .hdr_vae_decode import HDRVAEDecode
+
+NODE_CLASS_MAPPINGS = {
+    "HDRVAEDecode": HDRVAEDecode,
+}
+
+NODE_DISPLAY_NAME_MAPPINGS = {
+    "HDRVAEDecode": "HDR VAE Decode",
+}
+
+__all__ = ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS", "HDRVAEDecode"]

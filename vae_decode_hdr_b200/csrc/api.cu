@@ -1,0 +1,691 @@
+// C ABI of libhdrvae.so (include/hdrvae.h): context, weight repack, the decoder layer program and
+// the entry points.  The layer program restates the Flux.1 AE decoder graph that the reference
+// drives through vae.decode (hdr_vae_decode.py:859,:1022; graph in SURVEY.md §8 a3).
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hdrvae.h"
+#include "common.cuh"
+
+namespace hdrvae {
+
+// ---- error channel ----------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+long long g_launch_count = 0;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+// ---- kernels implemented in the other translation units -------------------------------------------
+int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream);
+int launch_gemm_direct(const GemmParams& p, cudaStream_t s);
+void choose_tile(int H, int W, GemmParams* p);
+int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStream_t s);
+int launch_pack_weight(const float* w, __nv_bfloat16* out, int cout, int cin, int ks, int ntaps, int cin_pad,
+                       const int* tap_mask, float scale, cudaStream_t s);
+int launch_latent_to_nhwc(const float* z, __nv_bfloat16* out, int B, int C, int HW, int cpad, cudaStream_t s);
+int launch_softmax_rows(const float* s, __nv_bfloat16* p, int n_rows, int n_valid, int n_pad, long long s_ld,
+                        long long p_ld, cudaStream_t st);
+int launch_transpose_pad(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int out_ld, cudaStream_t s);
+int launch_pack_half(const float* img, uint16_t* out, int B, int H, int W, int layout, cudaStream_t s);
+size_t gn_scratch_bytes(int B, int C);
+int launch_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, const float* gamma,
+                     const float* beta, bool silu, void* scratch, cudaStream_t s);
+size_t epilogue_scratch_bytes(int B, int H, int W);
+void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W);
+float* epilogue_post3_ptr(void* scratch, int B, int H, int W);
+float* epilogue_pre3_ptr(void* scratch, int B, int H, int W);
+int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, const float* conv_w, const float* conv_b,
+                            int* argmax3, void* scratch, cudaStream_t s);
+int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
+                            void* scratch, cudaStream_t s);
+
+// ---- per-op device timing (diagnostics; enabled by hdrvae_profile_begin) -----------------------------
+struct ProfEntry { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof;
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t st) : s(st), on(g_prof_on) {
+    if (!on) return;
+    ProfEntry e; e.name = name; e.flops = flops; e.bytes = bytes;
+    cudaEventCreate(&e.e0); cudaEventCreate(&e.e1);
+    cudaEventRecord(e.e0, s);
+    g_prof.push_back(e);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_prof.back().e1, s); }
+};
+
+// ---- packed operands --------------------------------------------------------------------------
+struct PackedConv {
+  __nv_bfloat16* w[4] = {nullptr, nullptr, nullptr, nullptr};  // [Cout][ntaps*cin_pad]; 4 phase matrices when upsample
+  float* bias = nullptr;
+  int cin = 0, cin_pad = 0, cout = 0, ks = 0;
+  bool upsample = false;
+};
+struct NormW {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+  int C = 0;
+};
+struct ResW {
+  NormW n1, n2;
+  PackedConv c1, c2, nin;
+  bool has_nin = false;
+};
+
+}  // namespace hdrvae
+
+using namespace hdrvae;
+
+struct hdrvae_ctx {
+  int device = 0;
+  int num_sms = 148;
+  bool loaded = false;
+  int conv_impl = HDRVAE_CONV_TCGEN05;
+  std::vector<void*> owned;                       // every device allocation of the context
+  std::map<std::string, float*> raw;              // fp32 device copies of the state dict
+  std::map<std::string, std::vector<int64_t>> shapes;
+  PackedConv conv_in, qk, vproj, proj_out;
+  NormW attn_norm, norm_out;
+  ResW mid1, mid2, up[4][3];
+  PackedConv upsample[4];
+  float* conv_out_w = nullptr;                    // fp32 OIHW [3][128][3][3]
+  float* conv_out_b = nullptr;
+};
+
+namespace hdrvae {
+
+static int dev_alloc(hdrvae_ctx* ctx, size_t bytes, void** out) {
+  HDRVAE_CUDA_OK(cudaMalloc(out, bytes ? bytes : 16));
+  ctx->owned.push_back(*out);
+  return 0;
+}
+
+// 3x3 taps in (ky,kx) row-major order; dy = ky-1, dx = kx-1
+static void fill_taps_3x3(GemmParams* p) {
+  p->ntaps = 9;
+  for (int t = 0; t < 9; ++t) { p->tap_dy[t] = t / 3 - 1; p->tap_dx[t] = t % 3 - 1; }
+}
+// Upsample phase (py,px): 2x2 taps on the source grid.  Rows: py=0 -> {dy=-1: ky 0 | dy=0: ky 1,2},
+// py=1 -> {dy=0: ky 0,1 | dy=+1: ky 2}; columns alike.
+static void phase_taps(int py, int px, int* dy, int* dx, int* mask) {
+  const int rdy[2][2] = {{-1, 0}, {0, 1}};
+  const int rmask[2][2] = {{0b001, 0b110}, {0b011, 0b100}};   // bit ky (or kx)
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int t = a * 2 + b;
+      dy[t] = rdy[py][a];
+      dx[t] = rdy[px][b];
+      int m = 0;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          if ((rmask[py][a] >> ky & 1) && (rmask[px][b] >> kx & 1)) m |= 1 << (ky * 3 + kx);
+      mask[t] = m;
+    }
+}
+
+static int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int cin, int ks, bool upsample,
+                     float scale, PackedConv* pc, cudaStream_t s) {
+  pc->cin = cin; pc->cout = cout; pc->ks = ks; pc->upsample = upsample;
+  pc->cin_pad = (cin + 63) / 64 * 64;
+  if (bias != nullptr) {
+    HDRVAE_TRY(dev_alloc(ctx, cout * sizeof(float), (void**)&pc->bias));
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(pc->bias, bias, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (!upsample) {
+    const int ntaps = ks * ks;
+    int mask[9];
+    for (int t = 0; t < ntaps; ++t) mask[t] = 1 << t;
+    HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * ntaps * pc->cin_pad * 2, (void**)&pc->w[0]));
+    HDRVAE_TRY(launch_pack_weight(w, pc->w[0], cout, cin, ks, ntaps, pc->cin_pad, mask, scale, s));
+  } else {
+    HDRVAE_REQUIRE(ks == 3, "upsample folding needs a 3x3 kernel");
+    for (int ph = 0; ph < 4; ++ph) {
+      int dy[4], dx[4], mask[4];
+      phase_taps(ph >> 1, ph & 1, dy, dx, mask);
+      HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * 4 * pc->cin_pad * 2, (void**)&pc->w[ph]));
+      HDRVAE_TRY(launch_pack_weight(w, pc->w[ph], cout, cin, 3, 4, pc->cin_pad, mask, scale, s));
+    }
+  }
+  return 0;
+}
+
+// x [B,H,W,cin_pad] bf16 -> y [B,OH,OW,cout]; residual has y's layout.
+static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const __nv_bfloat16* x, int B, int H, int W, void* y,
+                    bool out_f32, const __nv_bfloat16* residual, int impl, cudaStream_t s) {
+  char pname[96];
+  snprintf(pname, sizeof pname, "conv%dx%d%s %d->%d @%dx%dx%d", pc.ks, pc.ks, pc.upsample ? "up" : "", pc.cin, pc.cout, B, H, W);
+  const double out_px = (double)B * H * W * (pc.upsample ? 4 : 1);
+  ProfScope prof(pname, 2.0 * out_px * pc.cout * pc.cin * pc.ks * pc.ks,
+                 (double)B * H * W * pc.cin_pad * 2 + out_px * pc.cout * 2 * (residual ? 2 : 1), s);
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.a = x;
+  p.a_px_stride = pc.cin_pad; p.a_row_stride = (long long)W * pc.cin_pad; p.a_img_stride = (long long)H * W * pc.cin_pad;
+  p.n_img = B; p.H = H; p.W = W;
+  p.k_per_tap = pc.cin_pad;
+  p.n_cols = pc.cout;
+  p.out = y; p.out_f32 = out_f32 ? 1 : 0;
+  p.bias = pc.bias; p.bias_per_row = 0; p.residual = residual; p.alpha = 1.0f;
+  choose_tile(H, W, &p);
+  const int phases = pc.upsample ? 4 : 1;
+  const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
+  p.out_px_stride = pc.cout; p.out_row_stride = (long long)OW * pc.cout; p.out_img_stride = (long long)OH * OW * pc.cout;
+  for (int ph = 0; ph < phases; ++ph) {
+    if (pc.upsample) {
+      int mask[4];
+      p.ntaps = 4;
+      phase_taps(ph >> 1, ph & 1, p.tap_dy, p.tap_dx, mask);
+      p.sy = p.sx = 2; p.py = ph >> 1; p.px = ph & 1;
+    } else {
+      if (pc.ks == 3) fill_taps_3x3(&p);
+      else { p.ntaps = 1; p.tap_dy[0] = p.tap_dx[0] = 0; }
+      p.sy = p.sx = 1; p.py = p.px = 0;
+    }
+    p.b = pc.w[ph];
+    p.b_row_stride = (long long)p.ntaps * pc.cin_pad;
+    p.b_rows = pc.cout;
+    if (impl == HDRVAE_CONV_DIRECT) HDRVAE_TRY(launch_gemm_direct(p, s));
+    else HDRVAE_TRY(launch_gemm_tc(p, ctx->num_sms, s));
+  }
+  return 0;
+}
+
+// Plain K-major GEMM: out[M][n_cols] = alpha * A[M][K] * Bm[n_cols][K]^T (+ bias) on the same kernel.
+static int run_gemm(hdrvae_ctx* ctx, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* Bm,
+                    long long ldb, int b_rows, int n_cols, void* out, long long ldo, bool out_f32, const float* bias,
+                    bool bias_per_row, float alpha, int impl, cudaStream_t s) {
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.a = A; p.a_px_stride = lda; p.a_row_stride = (long long)M * lda; p.a_img_stride = (long long)M * lda;
+  p.n_img = 1; p.H = 1; p.W = M;
+  p.k_per_tap = K; p.ntaps = 1;
+  p.b = Bm; p.b_row_stride = ldb; p.b_rows = b_rows; p.n_cols = n_cols;
+  p.out = out; p.out_f32 = out_f32 ? 1 : 0;
+  p.out_px_stride = ldo; p.out_row_stride = 0; p.out_img_stride = 0;
+  p.sy = p.sx = 1;
+  p.bias = bias; p.bias_per_row = bias_per_row ? 1 : 0; p.alpha = alpha;
+  p.tw_log2 = 7; p.TW = 128; p.TH = 1; p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
+  if (impl == HDRVAE_CONV_DIRECT) return launch_gemm_direct(p, s);
+  return launch_gemm_tc(p, ctx->num_sms, s);
+}
+
+// ---- workspace plan -----------------------------------------------------------------------------
+struct Plan {
+  int B, h, w, T, Tp, s_rows;
+  size_t off_lat, off_act[3], off_gn, off_qk, off_vt, off_o, off_s, off_p, off_epi, total;
+  size_t act_bytes;
+};
+static constexpr long long kScoreBudgetElems = 256ll << 20;   // fp32 score chunk <= 1 GiB
+
+static Plan make_plan(int B, int h, int w, bool attn_only = false) {
+  Plan pl;
+  pl.B = B; pl.h = h; pl.w = w;
+  pl.T = h * w;
+  pl.Tp = (pl.T + 63) / 64 * 64;
+  long long rows = kScoreBudgetElems / pl.Tp;
+  rows = rows / 128 * 128;
+  if (rows < 128) rows = 128;
+  const long long t128 = (pl.T + 127) / 128 * 128;
+  if (rows > t128) rows = t128;
+  pl.s_rows = (int)rows;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  pl.off_lat = take(attn_only ? 0 : (size_t)B * pl.T * 64 * 2);
+  pl.act_bytes = attn_only ? 0 : (size_t)B * pl.T * 64 * 256 * 2;   // [B, 8h, 8w, 256] bf16 = widest activation
+  for (int i = 0; i < 3; ++i) pl.off_act[i] = take(pl.act_bytes);
+  pl.off_gn = take(gn_scratch_bytes(B, 512));
+  pl.off_qk = take((size_t)B * pl.Tp * 1024 * 2);
+  pl.off_vt = take((size_t)B * 512 * pl.Tp * 2);
+  pl.off_o = take((size_t)B * pl.T * 512 * 2);
+  pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
+  pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
+  pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
+  pl.total = off;
+  return pl;
+}
+
+// ---- decoder layer program ------------------------------------------------------------------------
+struct Bufs {
+  __nv_bfloat16* x;   // residual stream
+  __nv_bfloat16* t;   // normalised / activated operand
+  __nv_bfloat16* hbuf;   // block-internal
+};
+
+static int run_gn(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, const NormW& nw, bool silu, void* scratch,
+                  cudaStream_t s) {
+  char pname[64];
+  snprintf(pname, sizeof pname, "groupnorm%s C=%d @%dx%d", silu ? "+silu" : "", nw.C, B, HW);
+  ProfScope prof(pname, 0.0, (double)B * HW * nw.C * 6.0, s);
+  return launch_groupnorm(x, y, B, HW, nw.C, nw.gamma, nw.beta, silu, scratch, s);
+}
+
+static int run_res(hdrvae_ctx* ctx, const ResW& rw, Bufs* bf, int B, int H, int W, void* gn_scratch, cudaStream_t s) {
+  const int impl = ctx->conv_impl;
+  HDRVAE_TRY(run_gn(bf->x, bf->t, B, H * W, rw.n1, true, gn_scratch, s));
+  HDRVAE_TRY(run_conv(ctx, rw.c1, bf->t, B, H, W, bf->hbuf, false, nullptr, impl, s));
+  HDRVAE_TRY(run_gn(bf->hbuf, bf->t, B, H * W, rw.n2, true, gn_scratch, s));
+  if (rw.has_nin) {
+    // shortcut into hbuf (free after norm2), then conv2 accumulates onto it in place
+    HDRVAE_TRY(run_conv(ctx, rw.nin, bf->x, B, H, W, bf->hbuf, false, nullptr, impl, s));
+    HDRVAE_TRY(run_conv(ctx, rw.c2, bf->t, B, H, W, bf->hbuf, false, bf->hbuf, impl, s));
+    std::swap(bf->x, bf->hbuf);
+  } else {
+    HDRVAE_TRY(run_conv(ctx, rw.c2, bf->t, B, H, W, bf->x, false, bf->x, impl, s));   // x += conv2(t), in place
+  }
+  return 0;
+}
+
+static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const __nv_bfloat16* qk /*[B][Tp][1024]*/,
+                              const __nv_bfloat16* vt /*[B][512][Tp]*/, __nv_bfloat16* o /*[B][T][512]*/,
+                              float qk_alpha, cudaStream_t s) {
+  const int impl = ctx->conv_impl;
+  float* S = reinterpret_cast<float*>(ws + pl.off_s);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_p);
+  for (int b = 0; b < pl.B; ++b) {
+    const __nv_bfloat16* q = qk + (size_t)b * pl.Tp * 1024;
+    const __nv_bfloat16* k = q + 512;
+    const __nv_bfloat16* v = vt + (size_t)b * 512 * pl.Tp;
+    for (int r0 = 0; r0 < pl.T; r0 += pl.s_rows) {
+      const int rows = std::min(pl.s_rows, pl.T - r0);
+      // S = alpha q k^T, fp32 (the decoder folds 1/sqrt(d) into the q weights: alpha = 1); padded key
+      // columns give 0 and are masked by the softmax
+      HDRVAE_TRY(run_gemm(ctx, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, pl.Tp, pl.Tp, S, pl.Tp, true, nullptr,
+                          false, qk_alpha, impl, s));
+      HDRVAE_TRY(launch_softmax_rows(S, P, rows, pl.T, pl.Tp, pl.Tp, pl.Tp, s));
+      HDRVAE_TRY(run_gemm(ctx, P, pl.Tp, rows, pl.Tp, v, pl.Tp, 512, 512, o + ((size_t)b * pl.T + r0) * 512, 512, false,
+                          nullptr, false, 1.0f, impl, s));
+    }
+  }
+  return 0;
+}
+
+static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uint8_t* ws, __nv_bfloat16** features,
+                       cudaStream_t s) {
+  HDRVAE_REQUIRE(ctx->loaded, "hdrvae: weights not loaded");
+  const int B = pl.B, impl = ctx->conv_impl;
+  int H = pl.h, W = pl.w;
+  __nv_bfloat16* lat = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_lat);
+  Bufs bf;
+  bf.x = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_act[0]);
+  bf.t = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_act[1]);
+  bf.hbuf = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_act[2]);
+  void* gns = ws + pl.off_gn;
+
+  HDRVAE_TRY(launch_latent_to_nhwc(latent, lat, B, 16, H * W, 64, s));
+  HDRVAE_TRY(run_conv(ctx, ctx->conv_in, lat, B, H, W, bf.x, false, nullptr, impl, s));
+  HDRVAE_TRY(run_res(ctx, ctx->mid1, &bf, B, H, W, gns, s));
+  {
+    // mid.attn_1: x += proj_out(softmax(q k^T / sqrt(c)) v), q,k,v = 1x1 convs of GroupNorm(x) (no SiLU)
+    __nv_bfloat16* qk = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qk);
+    __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_vt);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_o);
+    HDRVAE_TRY(run_gn(bf.x, bf.t, B, H * W, ctx->attn_norm, false, gns, s));
+    if (pl.Tp != pl.T) HDRVAE_CUDA_OK(cudaMemsetAsync(qk, 0, (size_t)B * pl.Tp * 1024 * 2, s));
+    ProfScope* pq = new ProfScope("attention q|k and v^T projections", 2.0 * B * (double)pl.T * 512 * 1536, 0.0, s);
+    for (int b = 0; b < B; ++b) {
+      const __nv_bfloat16* tb = bf.t + (size_t)b * pl.T * 512;
+      // [q*scale | k] = t Wqk^T + bqk : [T][1024]
+      HDRVAE_TRY(run_gemm(ctx, tb, 512, pl.T, 512, ctx->qk.w[0], 512, 1024, 1024, qk + (size_t)b * pl.Tp * 1024, 1024,
+                          false, ctx->qk.bias, false, 1.0f, impl, s));
+      // v^T = Wv t^T + bv : [512][Tp]  (operand roles swapped so PV sees a K-major B operand)
+      HDRVAE_TRY(run_gemm(ctx, ctx->vproj.w[0], 512, 512, 512, tb, 512, pl.T, pl.Tp, vt + (size_t)b * 512 * pl.Tp,
+                          pl.Tp, false, ctx->vproj.bias, true, 1.0f, impl, s));
+    }
+    delete pq;
+    {
+      ProfScope prof("attention core (QK^T, softmax, PV)", 4.0 * B * (double)pl.T * pl.T * 512, 12.0 * B * (double)pl.T * pl.Tp, s);
+      HDRVAE_TRY(run_attention_core(ctx, pl, ws, qk, vt, o, 1.0f, s));
+    }
+    HDRVAE_TRY(run_conv(ctx, ctx->proj_out, o, B, H, W, bf.x, false, bf.x, impl, s));
+  }
+  HDRVAE_TRY(run_res(ctx, ctx->mid2, &bf, B, H, W, gns, s));
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    for (int i = 0; i < 3; ++i) HDRVAE_TRY(run_res(ctx, ctx->up[lvl][i], &bf, B, H, W, gns, s));
+    if (lvl != 0) {
+      HDRVAE_TRY(run_conv(ctx, ctx->upsample[lvl], bf.x, B, H, W, bf.hbuf, false, nullptr, impl, s));
+      std::swap(bf.x, bf.hbuf);
+      H *= 2; W *= 2;
+    }
+  }
+  HDRVAE_TRY(run_gn(bf.x, bf.t, B, H * W, ctx->norm_out, true, gns, s));
+  *features = bf.t;
+  return 0;
+}
+
+static int check_ws(const Plan& pl, void* ws, size_t bytes) {
+  HDRVAE_REQUIRE(ws != nullptr && bytes >= pl.total, "hdrvae: workspace too small (%zu < %zu bytes)", bytes, pl.total);
+  HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "hdrvae: workspace must be 1024-byte aligned");
+  return 0;
+}
+
+}  // namespace hdrvae
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* hdrvae_last_error(void) { return g_last_error.c_str(); }
+int hdrvae_abi_version(void) { return HDRVAE_ABI_VERSION; }
+
+int hdrvae_create(hdrvae_ctx** out, int device) {
+  HDRVAE_REQUIRE(out != nullptr, "hdrvae_create: null out pointer");
+  int n = 0;
+  HDRVAE_CUDA_OK(cudaGetDeviceCount(&n));
+  HDRVAE_REQUIRE(device >= 0 && device < n, "hdrvae_create: no CUDA device %d (count %d); there is no CPU path", device, n);
+  HDRVAE_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  HDRVAE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  HDRVAE_REQUIRE(prop.major == 10, "hdrvae_create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major,
+                 prop.minor);
+  hdrvae_ctx* ctx = new hdrvae_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  const char* impl = getenv("HDRVAE_CONV_IMPL");
+  if (impl != nullptr && strcmp(impl, "direct") == 0) ctx->conv_impl = HDRVAE_CONV_DIRECT;
+  *out = ctx;
+  return 0;
+}
+
+int hdrvae_destroy(hdrvae_ctx* ctx) {
+  if (ctx == nullptr) return 0;
+  cudaSetDevice(ctx->device);
+  for (void* p : ctx->owned) cudaFree(p);
+  delete ctx;
+  return 0;
+}
+
+static_assert(sizeof(hdrvae_stats) == 200 && sizeof(hdrvae_raw_stats) == 96, "ABI struct layout changed");
+
+long long hdrvae_launch_count(void) { return g_launch_count; }
+
+int hdrvae_profile_begin(void) {
+  for (auto& e : g_prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+
+// Synchronises the device, writes "name\tms\tTFLOP/s\tGB/s" lines to `path` (or stderr) and stops profiling.
+int hdrvae_profile_end(const char* path) {
+  g_prof_on = false;
+  HDRVAE_CUDA_OK(cudaDeviceSynchronize());
+  FILE* f = path ? fopen(path, "w") : stderr;
+  HDRVAE_REQUIRE(f != nullptr, "hdrvae_profile_end: cannot open %s", path);
+  double total = 0.0;
+  for (auto& e : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.e0, e.e1);
+    total += ms;
+    fprintf(f, "%-52s\t%9.4f ms\t%8.1f TFLOP/s\t%8.1f GB/s\n", e.name.c_str(), ms, e.flops / ms / 1e9, e.bytes / ms / 1e6);
+    cudaEventDestroy(e.e0); cudaEventDestroy(e.e1);
+  }
+  fprintf(f, "%-52s\t%9.4f ms\n", "TOTAL (sum of scopes)", total);
+  if (path) fclose(f);
+  g_prof.clear();
+  return 0;
+}
+
+int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl) {
+  HDRVAE_REQUIRE(ctx != nullptr && (impl == HDRVAE_CONV_TCGEN05 || impl == HDRVAE_CONV_DIRECT), "bad conv impl");
+  ctx->conv_impl = impl;
+  return 0;
+}
+
+int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n, int precision) {
+  HDRVAE_REQUIRE(ctx != nullptr && descs != nullptr, "hdrvae_load_weights: null argument");
+  HDRVAE_REQUIRE(precision == HDRVAE_PRECISION_BF16, "hdrvae_load_weights: unsupported precision %d", precision);
+  HDRVAE_REQUIRE(!ctx->loaded, "hdrvae_load_weights: context already holds weights (create a new one)");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t s = nullptr;
+  std::vector<void*> staging;
+  for (int i = 0; i < n; ++i) {
+    const hdrvae_weight_desc& d = descs[i];
+    HDRVAE_REQUIRE(d.name && d.data && d.ndim >= 1 && d.ndim <= 4, "hdrvae_load_weights: bad descriptor %d", i);
+    long long cnt = 1;
+    std::vector<int64_t> shp;
+    for (int k = 0; k < d.ndim; ++k) { cnt *= d.shape[k]; shp.push_back(d.shape[k]); }
+    const size_t esz = d.dtype == HDRVAE_F32 ? 4 : 2;
+    void* stage = nullptr;
+    HDRVAE_CUDA_OK(cudaMalloc(&stage, cnt * esz));
+    staging.push_back(stage);
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(stage, d.data, cnt * esz, cudaMemcpyDefault, s));
+    float* f = nullptr;
+    HDRVAE_TRY(dev_alloc(ctx, cnt * sizeof(float), (void**)&f));
+    HDRVAE_TRY(launch_to_f32(stage, d.dtype, f, cnt, s));
+    ctx->raw[d.name] = f;
+    ctx->shapes[d.name] = shp;
+  }
+  auto W = [&](const std::string& k) -> float* { auto it = ctx->raw.find(k); return it == ctx->raw.end() ? nullptr : it->second; };
+  auto need_conv = [&](const std::string& k, int cout, int cin, int ks) -> int {
+    auto it = ctx->shapes.find(k + ".weight");
+    HDRVAE_REQUIRE(it != ctx->shapes.end() && W(k + ".bias") != nullptr, "state dict lacks %s.{weight,bias}", k.c_str());
+    const auto& sh = it->second;
+    HDRVAE_REQUIRE(sh.size() == 4 && sh[0] == cout && sh[1] == cin && sh[2] == ks && sh[3] == ks,
+                   "%s.weight has the wrong shape (want [%d,%d,%d,%d])", k.c_str(), cout, cin, ks, ks);
+    return 0;
+  };
+  auto conv = [&](const std::string& k, int cout, int cin, int ks, bool up, float scale, PackedConv* pc) -> int {
+    HDRVAE_TRY(need_conv(k, cout, cin, ks));
+    return pack_conv(ctx, W(k + ".weight"), W(k + ".bias"), cout, cin, ks, up, scale, pc, s);
+  };
+  auto norm = [&](const std::string& k, int C, NormW* nw) -> int {
+    HDRVAE_REQUIRE(W(k + ".weight") && W(k + ".bias") && ctx->shapes[k + ".weight"].size() == 1 &&
+                       ctx->shapes[k + ".weight"][0] == C, "state dict lacks %s (GroupNorm over %d channels)", k.c_str(), C);
+    nw->gamma = W(k + ".weight"); nw->beta = W(k + ".bias"); nw->C = C;
+    return 0;
+  };
+  auto res = [&](const std::string& k, int cin, int cout, ResW* rw) -> int {
+    HDRVAE_TRY(norm(k + ".norm1", cin, &rw->n1));
+    HDRVAE_TRY(conv(k + ".conv1", cout, cin, 3, false, 1.f, &rw->c1));
+    HDRVAE_TRY(norm(k + ".norm2", cout, &rw->n2));
+    HDRVAE_TRY(conv(k + ".conv2", cout, cout, 3, false, 1.f, &rw->c2));
+    rw->has_nin = cin != cout;
+    if (rw->has_nin) HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, 1.f, &rw->nin));
+    return 0;
+  };
+
+  HDRVAE_TRY(conv("conv_in", 512, 16, 3, false, 1.f, &ctx->conv_in));
+  HDRVAE_TRY(res("mid.block_1", 512, 512, &ctx->mid1));
+  HDRVAE_TRY(res("mid.block_2", 512, 512, &ctx->mid2));
+  HDRVAE_TRY(norm("mid.attn_1.norm", 512, &ctx->attn_norm));
+  {
+    // fused [q * 1/sqrt(512) ; k] projection: one [1024][512] K-major operand + concatenated bias
+    HDRVAE_TRY(need_conv("mid.attn_1.q", 512, 512, 1));
+    HDRVAE_TRY(need_conv("mid.attn_1.k", 512, 512, 1));
+    const float scale = 1.0f / sqrtf(512.0f);
+    PackedConv& qk = ctx->qk;
+    qk.cin = qk.cin_pad = 512; qk.cout = 1024; qk.ks = 1;
+    HDRVAE_TRY(dev_alloc(ctx, (size_t)1024 * 512 * 2, (void**)&qk.w[0]));
+    HDRVAE_TRY(dev_alloc(ctx, 1024 * sizeof(float), (void**)&qk.bias));
+    int mask1[1] = {1};
+    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.q.weight"), qk.w[0], 512, 512, 1, 1, 512, mask1, scale, s));
+    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.k.weight"), qk.w[0] + 512 * 512, 512, 512, 1, 1, 512, mask1, 1.f, s));
+    // bias: q part scaled
+    std::vector<float> hb(1024);
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(hb.data(), W("mid.attn_1.q.bias"), 512 * 4, cudaMemcpyDeviceToHost, s));
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(hb.data() + 512, W("mid.attn_1.k.bias"), 512 * 4, cudaMemcpyDeviceToHost, s));
+    HDRVAE_CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < 512; ++i) hb[i] *= scale;
+    HDRVAE_CUDA_OK(cudaMemcpy(qk.bias, hb.data(), 1024 * 4, cudaMemcpyHostToDevice));
+  }
+  HDRVAE_TRY(conv("mid.attn_1.v", 512, 512, 1, false, 1.f, &ctx->vproj));
+  HDRVAE_TRY(conv("mid.attn_1.proj_out", 512, 512, 1, false, 1.f, &ctx->proj_out));
+  const int ch[4] = {128, 256, 512, 512};
+  int cin = 512;
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    for (int i = 0; i < 3; ++i) {
+      HDRVAE_TRY(res("up." + std::to_string(lvl) + ".block." + std::to_string(i), cin, ch[lvl], &ctx->up[lvl][i]));
+      cin = ch[lvl];
+    }
+    if (lvl != 0) HDRVAE_TRY(conv("up." + std::to_string(lvl) + ".upsample.conv", cin, cin, 3, true, 1.f, &ctx->upsample[lvl]));
+  }
+  HDRVAE_TRY(norm("norm_out", 128, &ctx->norm_out));
+  HDRVAE_TRY(need_conv("conv_out", 3, 128, 3));
+  ctx->conv_out_w = W("conv_out.weight");
+  ctx->conv_out_b = W("conv_out.bias");
+  HDRVAE_CUDA_OK(cudaStreamSynchronize(s));
+  for (void* p : staging) cudaFree(p);
+  ctx->loaded = true;
+  return 0;
+}
+
+int hdrvae_workspace_bytes(hdrvae_ctx* ctx, int B, int h, int w, size_t* bytes) {
+  HDRVAE_REQUIRE(ctx != nullptr && bytes != nullptr, "hdrvae_workspace_bytes: null argument");
+  HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_workspace_bytes: empty latent batch [%d,16,%d,%d]", B, h, w);
+  *bytes = make_plan(B, h, w).total;
+  return 0;
+}
+
+int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, void* workspace, size_t ws_bytes,
+                        void** raw_stats_dev, void* stream) {
+  HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr, "hdrvae_decode: null argument");
+  HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode: empty latent batch [%d,16,%d,%d]", B, h, w);
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  const Plan pl = make_plan(B, h, w);
+  HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* feat = nullptr;
+  HDRVAE_TRY(run_decoder(ctx, latent, pl, ws, &feat, s));
+  {
+    ProfScope prof("epilogue phase A (conv_out, max-pool, stats)", 2.0 * B * 64.0 * h * w * 3 * 1152, B * 64.0 * h * w * (256 + 24), s);
+    HDRVAE_TRY(launch_epilogue_phase_a(feat, HDRVAE_BF16, B, 8 * h, 8 * w, ctx->conv_out_w, ctx->conv_out_b, nullptr,
+                                       ws + pl.off_epi, s));
+  }
+  if (raw_stats_dev != nullptr) *raw_stats_dev = epilogue_raw_stats_ptr(ws + pl.off_epi, B, 8 * h, 8 * w);
+  return 0;
+}
+
+int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float expansion_factor, float ev_multiplier,
+                         float* out_bhwc, hdrvae_stats* stats, void* workspace, size_t ws_bytes, void* stream) {
+  HDRVAE_REQUIRE(ctx != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  const Plan pl = make_plan(B, h, w);
+  HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  ProfScope prof("epilogue phase B (mode formula)", 0.0, B * 64.0 * h * w * 36, reinterpret_cast<cudaStream_t>(stream));
+  return launch_epilogue_phase_b(B, 8 * h, 8 * w, mode, expansion_factor, ev_multiplier, out_bhwc, stats,
+                                 ws + pl.off_epi, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hdrvae_decode(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, int mode, float expansion_factor,
+                  float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace, size_t ws_bytes,
+                  void* stream) {
+  HDRVAE_TRY(hdrvae_decode_begin(ctx, latent, B, h, w, workspace, ws_bytes, nullptr, stream));
+  return hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, out_bhwc, stats, workspace, ws_bytes,
+                              stream);
+}
+
+int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, void* features, void* workspace,
+                           size_t ws_bytes, void* stream) {
+  HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr && features != nullptr, "hdrvae_decode_features: null argument");
+  HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode_features: empty latent batch");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  const Plan pl = make_plan(B, h, w);
+  HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* feat = nullptr;
+  HDRVAE_TRY(run_decoder(ctx, latent, pl, reinterpret_cast<uint8_t*>(workspace), &feat, s));
+  HDRVAE_CUDA_OK(cudaMemcpyAsync(features, feat, (size_t)B * 64 * h * w * 128 * 2, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int hdrvae_epilogue_scratch_bytes(int B, int H, int W, size_t* bytes) {
+  HDRVAE_REQUIRE(bytes != nullptr && B >= 1 && H >= 1 && W >= 1, "hdrvae_epilogue_scratch_bytes: bad argument");
+  *bytes = epilogue_scratch_bytes(B, H, W);
+  return 0;
+}
+
+int hdrvae_epilogue(hdrvae_ctx* ctx, const void* pre, int dtype, int B, int H, int W, const float* conv_w,
+                    const float* conv_b, int mode, float expansion_factor, float ev_multiplier, float* out_bhwc,
+                    hdrvae_stats* stats, float* dbg_post3, float* dbg_pre3, int32_t* dbg_argmax3, void* scratch,
+                    size_t scratch_bytes, void* stream) {
+  HDRVAE_REQUIRE(ctx != nullptr && pre != nullptr && conv_w != nullptr && conv_b != nullptr && out_bhwc != nullptr,
+                 "hdrvae_epilogue: null argument");
+  HDRVAE_REQUIRE(B >= 1 && H >= 1 && W >= 1, "hdrvae_epilogue: empty image batch");
+  HDRVAE_REQUIRE(scratch != nullptr && scratch_bytes >= epilogue_scratch_bytes(B, H, W), "hdrvae_epilogue: scratch too small");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  HDRVAE_TRY(launch_epilogue_phase_a(pre, dtype, B, H, W, conv_w, conv_b, dbg_argmax3, scratch, s));
+  const size_t img = (size_t)B * H * W * 3 * sizeof(float);
+  if (dbg_post3) HDRVAE_CUDA_OK(cudaMemcpyAsync(dbg_post3, epilogue_post3_ptr(scratch, B, H, W), img, cudaMemcpyDeviceToDevice, s));
+  if (dbg_pre3) HDRVAE_CUDA_OK(cudaMemcpyAsync(dbg_pre3, epilogue_pre3_ptr(scratch, B, H, W), img, cudaMemcpyDeviceToDevice, s));
+  return launch_epilogue_phase_b(B, H, W, mode, expansion_factor, ev_multiplier, out_bhwc, stats, scratch, s);
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------------
+int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int B, int H, int W, int Cin, const float* w, const float* bias,
+                  int Cout, int ksize, int upsample2x, const void* residual, void* y, int out_f32, int impl,
+                  void* stream) {
+  HDRVAE_REQUIRE(ctx && x && w && y, "hdrvae_conv2d: null argument");
+  HDRVAE_REQUIRE(Cin % 64 == 0, "hdrvae_conv2d: Cin must be a multiple of 64 (pad the activation channels)");
+  HDRVAE_REQUIRE(Cout % 32 == 0 && (ksize == 1 || ksize == 3), "hdrvae_conv2d: Cout %% 32 == 0 and ksize in {1,3}");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  hdrvae_ctx tmp;                     // owns the temporary packed operands
+  tmp.device = ctx->device; tmp.num_sms = ctx->num_sms;
+  PackedConv pc;
+  int r = pack_conv(&tmp, w, bias, Cout, Cin, ksize, upsample2x != 0, 1.f, &pc, s);
+  if (r == 0) r = run_conv(&tmp, pc, reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, y, out_f32 != 0,
+                           reinterpret_cast<const __nv_bfloat16*>(residual), impl, s);
+  cudaStreamSynchronize(s);
+  for (void* p : tmp.owned) cudaFree(p);
+  if (r == 0) HDRVAE_CUDA_OK(cudaGetLastError());
+  return r;
+}
+
+int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int B, int HW, int C, const float* gamma, const float* beta,
+                          int apply_silu, void* y, void* stream) {
+  HDRVAE_REQUIRE(ctx && x && gamma && beta && y, "hdrvae_groupnorm_silu: null argument");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  HDRVAE_CUDA_OK(cudaMalloc(&scratch, gn_scratch_bytes(B, C)));
+  int r = launch_groupnorm(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, HW, C,
+                           gamma, beta, apply_silu != 0, scratch, s);
+  cudaStreamSynchronize(s);
+  cudaFree(scratch);
+  return r;
+}
+
+int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int B, int T, void* o, void* stream) {
+  HDRVAE_REQUIRE(ctx && q && k && v && o && B >= 1 && T >= 1, "hdrvae_attention: bad argument");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Plan pl = make_plan(B, 1, T, true);
+  uint8_t* ws = nullptr;
+  HDRVAE_CUDA_OK(cudaMalloc((void**)&ws, pl.total));
+  __nv_bfloat16* qk = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qk);
+  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_vt);
+  int r = 0;
+  const float scale = 1.0f / sqrtf(512.0f);
+  cudaMemsetAsync(qk, 0, (size_t)B * pl.Tp * 1024 * 2, s);
+  cudaMemsetAsync(vt, 0, (size_t)B * 512 * pl.Tp * 2, s);
+  for (int b = 0; b < B && r == 0; ++b) {
+    // interleave q (scaled in fp32 -> bf16) and k rows into the [Tp][1024] operand, transpose v
+    r = launch_transpose_pad(reinterpret_cast<const __nv_bfloat16*>(v) + (size_t)b * T * 512, vt + (size_t)b * 512 * pl.Tp, T, 512, pl.Tp, s);
+    if (r == 0) HDRVAE_CUDA_OK(cudaMemcpy2DAsync(qk + (size_t)b * pl.Tp * 1024, 2048, reinterpret_cast<const __nv_bfloat16*>(q) + (size_t)b * T * 512, 1024, 1024, T, cudaMemcpyDeviceToDevice, s));
+    if (r == 0) HDRVAE_CUDA_OK(cudaMemcpy2DAsync(qk + (size_t)b * pl.Tp * 1024 + 512, 2048, reinterpret_cast<const __nv_bfloat16*>(k) + (size_t)b * T * 512, 1024, 1024, T, cudaMemcpyDeviceToDevice, s));
+  }
+  if (r == 0) r = run_attention_core(ctx, pl, ws, qk, vt, reinterpret_cast<__nv_bfloat16*>(o), scale, s);
+  cudaStreamSynchronize(s);
+  cudaFree(ws);
+  return r;
+}
+
+int hdrvae_pack_half(const float* image, int B, int H, int W, int layout, uint16_t* out, void* stream) {
+  HDRVAE_REQUIRE(image && out && B >= 0 && H >= 0 && W >= 0 && (layout == 0 || layout == 1), "hdrvae_pack_half: bad argument");
+  return launch_pack_half(image, out, B, H, W, layout, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Shared host/device helpers for libhdrvae (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace hdrvae {
+
+void set_error(const char* fmt, ...);
+extern long long g_launch_count;   // kernels launched by this library (bench.py's gpu_launches)
+#define HDRVAE_LAUNCHED() (++::hdrvae::g_launch_count)
+
+#define HDRVAE_CUDA_OK(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::hdrvae::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+#define HDRVAE_REQUIRE(cond, ...)       \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::hdrvae::set_error(__VA_ARGS__); \
+      return -2;                        \
+    }                                   \
+  } while (0)
+
+#define HDRVAE_TRY(expr)      \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ----------------------------------------------------------------- GEMM / conv descriptor
+// out[n, y*sy+py, x*sx+px, col] = bias[col] + sum_{t<ntaps} sum_{c<K_per_tap}
+//        A[n, y+dy[t], x+dx[t], c] * Bw[col][t*K_per_tap + c]      (+ residual[...])
+// A is addressed as a 4-D NHWC tensor (plain matrices use H = N = 1, W = rows).
+struct GemmParams {
+  // A operand (activations): element strides, used by the direct kernel; the tcgen05 kernel
+  // reads A through a TMA tensor map built from the same numbers.
+  const __nv_bfloat16* a;
+  long long a_img_stride, a_row_stride, a_px_stride;
+  // B operand (weights / keys), [cols][ktot] K-major bf16
+  const __nv_bfloat16* b;
+  long long b_row_stride;
+  int b_rows;       // rows of B that exist in memory (0: same as n_cols); rows beyond are zero-filled by TMA
+  int n_img, H, W;  // source grid of the M dimension
+  int k_per_tap;    // multiple of 64
+  int ntaps;
+  int tap_dy[9], tap_dx[9];
+  int n_cols;       // valid output columns (Cout)
+  // tiling of the M dimension: TW x TH = 128 pixels
+  int tw_log2, TW, TH, tiles_x, tiles_y, n_tiles_n;
+  // output
+  void* out;
+  int out_f32;
+  long long out_img_stride, out_row_stride, out_px_stride;  // elements
+  int sy, sx, py, px;
+  const float* bias;
+  int bias_per_row;  // bias indexed by the M row (x coordinate) instead of the column
+  const __nv_bfloat16* residual;  // same addressing as out, or null
+  float alpha;       // accumulator scale applied before bias (1.0 for convs)
+};
+
+struct TensorMapPair {
+  CUtensorMap a, b;
+};
+
+}  // namespace hdrvae

@@ -1,0 +1,251 @@
+// Small kernels around the GEMM core: weight repack, latent layout change, CUDA-core
+// validation conv, attention row softmax, fp16 pack for the EXR exporter.
+#include "common.cuh"
+
+namespace hdrvae {
+
+// ------------------------------------------------------------------ dtype -> fp32 copy
+__global__ void to_f32_kernel(const void* __restrict__ src, int dtype, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v;
+    if (dtype == 0) v = reinterpret_cast<const float*>(src)[i];
+    else if (dtype == 1) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+    else v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+    dst[i] = v;
+  }
+}
+int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStream_t s) {
+  if (n == 0) return 0;
+  to_f32_kernel<<<ceil_div(n, 256) > 1184 ? 1184 : ceil_div(n, 256), 256, 0, s>>>(src, dtype, dst, n);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ weight repack
+// OIHW fp32 [Cout][Cin][ks][ks] -> K-major bf16 [Cout][ntaps][cin_pad]; output tap t is the SUM of
+// the source kernel positions set in tap_mask[t] (bit ky*ks+kx).  Plain 3x3: mask = 1<<t.
+// Upsample phase matrices: 2x2 taps, each the sum of the 3x3 positions that land on the same
+// source pixel after nearest-2x upsampling.  `scale` multiplies every weight (attention 1/sqrt(d)).
+struct PackArgs {
+  int cout, cin, ks, ntaps, cin_pad;
+  int tap_mask[9];
+  float scale;
+};
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, PackArgs a) {
+  const long long total = (long long)a.cout * a.ntaps * a.cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % a.cin_pad);
+    const int t = (int)((i / a.cin_pad) % a.ntaps);
+    const int co = (int)(i / ((long long)a.cin_pad * a.ntaps));
+    float acc = 0.f;
+    if (ci < a.cin) {
+      const int kk = a.ks * a.ks;
+      for (int s = 0; s < kk; ++s)
+        if (a.tap_mask[t] & (1 << s)) acc += w[((long long)co * a.cin + ci) * kk + s];
+    }
+    out[i] = __float2bfloat16_rn(acc * a.scale);
+  }
+}
+int launch_pack_weight(const float* w, __nv_bfloat16* out, int cout, int cin, int ks, int ntaps, int cin_pad,
+                       const int* tap_mask, float scale, cudaStream_t s) {
+  PackArgs a;
+  a.cout = cout; a.cin = cin; a.ks = ks; a.ntaps = ntaps; a.cin_pad = cin_pad; a.scale = scale;
+  for (int t = 0; t < 9; ++t) a.tap_mask[t] = t < ntaps ? tap_mask[t] : 0;
+  const long long total = (long long)cout * ntaps * cin_pad;
+  int grid = ceil_div(total, 256);
+  if (grid > 2368) grid = 2368;
+  pack_weight_kernel<<<grid, 256, 0, s>>>(w, out, a);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ latent NCHW fp32 -> NHWC bf16 (channels zero-padded)
+__global__ void latent_to_nhwc_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out, int B, int C,
+                                      int HW, int cpad) {
+  const long long total = (long long)B * HW * cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const long long p = i / cpad;
+    const int hw = (int)(p % HW);
+    const int b = (int)(p / HW);
+    out[i] = __float2bfloat16_rn(c < C ? z[((long long)b * C + c) * HW + hw] : 0.f);
+  }
+}
+int launch_latent_to_nhwc(const float* z, __nv_bfloat16* out, int B, int C, int HW, int cpad, cudaStream_t s) {
+  const long long total = (long long)B * HW * cpad;
+  int grid = ceil_div(total, 256);
+  if (grid > 2368) grid = 2368;
+  latent_to_nhwc_kernel<<<grid, 256, 0, s>>>(z, out, B, C, HW, cpad);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ CUDA-core validation conv (same GemmParams)
+// One thread per output element; used only to validate the tcgen05 kernel on the GPU
+// (HDRVAE_CONV_DIRECT), never on the product path.
+__global__ void gemm_direct_kernel(const GemmParams p) {
+  const long long total = (long long)p.n_img * p.H * p.W * p.n_cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % p.n_cols);
+    long long r = i / p.n_cols;
+    const int x = (int)(r % p.W); r /= p.W;
+    const int y = (int)(r % p.H);
+    const int img = (int)(r / p.H);
+    float acc = 0.f;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int ys = y + p.tap_dy[t], xs = x + p.tap_dx[t];
+      if (ys < 0 || ys >= p.H || xs < 0 || xs >= p.W) continue;
+      const __nv_bfloat16* ap = p.a + img * p.a_img_stride + ys * p.a_row_stride + xs * p.a_px_stride;
+      if (p.b_rows > 0 && col >= p.b_rows) continue;
+      const __nv_bfloat16* bp = p.b + col * p.b_row_stride + (long long)t * p.k_per_tap;
+      for (int c = 0; c < p.k_per_tap; c += 8) {
+        const uint4 av = *reinterpret_cast<const uint4*>(ap + c);
+        const uint4 bv = *reinterpret_cast<const uint4*>(bp + c);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(__low2float(a2[e]), __low2float(b2[e]), acc);
+          acc = fmaf(__high2float(a2[e]), __high2float(b2[e]), acc);
+        }
+      }
+    }
+    float v = acc * p.alpha;
+    if (p.bias != nullptr) v += p.bias_per_row ? p.bias[x] : p.bias[col];
+    const long long off = (long long)img * p.out_img_stride + (long long)(y * p.sy + p.py) * p.out_row_stride +
+                          (long long)(x * p.sx + p.px) * p.out_px_stride + col;
+    if (p.residual != nullptr) v += __bfloat162float(p.residual[off]);
+    if (p.out_f32) reinterpret_cast<float*>(p.out)[off] = v;
+    else reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+  }
+}
+int launch_gemm_direct(const GemmParams& p, cudaStream_t s) {
+  const long long total = (long long)p.n_img * p.H * p.W * p.n_cols;
+  int grid = ceil_div(total, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  gemm_direct_kernel<<<grid, 256, 0, s>>>(p);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ attention row softmax: fp32 scores -> bf16 probabilities
+// One CTA per query row; three passes over the row (max, sum, write); the row (<= 1 MB) stays in L2.
+// Columns [n_valid, n_pad) are padding keys: excluded from the softmax and written as 0.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
+                                                           int n_valid, int n_pad, long long s_ld, long long p_ld) {
+  const float* row = s + (long long)blockIdx.x * s_ld;
+  __nv_bfloat16* out = p + (long long)blockIdx.x * p_ld;
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int nv = n_valid >> 2;                      // full float4 groups
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row4[i];
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int i = nv * 4 + threadIdx.x; i < n_valid; i += 256) m = fmaxf(m, row[i]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row4[i];
+    sum += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+  }
+  for (int i = nv * 4 + threadIdx.x; i < n_valid; i += 256) sum += __expf(row[i] - m);
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bcast = 1.f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  uint2* out4 = reinterpret_cast<uint2*>(out);
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row4[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+    uint2 o2;
+    o2.x = *reinterpret_cast<uint32_t*>(&lo);
+    o2.y = *reinterpret_cast<uint32_t*>(&hi);
+    out4[i] = o2;
+  }
+  for (int i = nv * 4 + threadIdx.x; i < n_pad; i += 256)
+    out[i] = __float2bfloat16_rn(i < n_valid ? __expf(row[i] - m) * inv : 0.f);
+}
+int launch_softmax_rows(const float* s, __nv_bfloat16* p, int n_rows, int n_valid, int n_pad, long long s_ld,
+                        long long p_ld, cudaStream_t st) {
+  HDRVAE_REQUIRE(s_ld % 4 == 0 && p_ld % 4 == 0 && n_pad >= n_valid, "softmax: bad leading dimensions");
+  softmax_rows_kernel<<<n_rows, 256, 0, st>>>(s, p, n_valid, n_pad, s_ld, p_ld);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ [rows][cols] -> [cols][out_ld] transpose (test entry only)
+__global__ void transpose_pad_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
+                                     int cols, int out_ld) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(long long)c * out_ld + r] = tile[threadIdx.x][j];
+  }
+}
+int launch_transpose_pad(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int out_ld, cudaStream_t s) {
+  transpose_pad_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, s>>>(in, out, rows, cols, out_ld);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ fp32 -> fp16 pack (LinearEXRExport, linear_exr_export.py:155,165)
+// layout 0: same element order as the input (numpy astype(np.float16)); layout 1: EXR scanline order,
+// per image row the B plane, then G, then R (OpenEXR stores channels alphabetically).
+__global__ void pack_half_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int H, int W, int layout) {
+  const long long total = (long long)B * H * W * 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (layout == 0) {
+      out[i] = __float2half_rn(img[i]);
+    } else {
+      const int x = (int)(i % W);
+      long long r = i / W;
+      const int plane = (int)(r % 3); r /= 3;         // 0 = B, 1 = G, 2 = R
+      const long long row = r;                        // b*H + y
+      out[i] = __float2half_rn(img[(row * W + x) * 3 + (2 - plane)]);
+    }
+  }
+}
+int launch_pack_half(const float* img, uint16_t* out, int B, int H, int W, int layout, cudaStream_t s) {
+  const long long total = (long long)B * H * W * 3;
+  if (total == 0) return 0;
+  int grid = ceil_div(total, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  pack_half_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<__half*>(out), B, H, W, layout);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hdrvae
