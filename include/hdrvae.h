@@ -48,8 +48,12 @@ enum { HDRVAE_NORM_NONE = 0, HDRVAE_NORM_SIGMOID = 1, HDRVAE_NORM_TANH = 2 };
 /* element types for hdrvae_weight_desc / activations handed across the ABI */
 enum { HDRVAE_F32 = 0, HDRVAE_BF16 = 1, HDRVAE_F16 = 2 };
 
-/* decoder arithmetic: bf16 operands / fp32 accumulate on tcgen05 (kind::f16) */
-enum { HDRVAE_PRECISION_BF16 = 0 };
+/* 16-bit tensor-core operand type of the decoder (kind::f16, fp32 accumulate in TMEM).  In both modes the
+ * un-normalised residual / conv streams stay fp32 in HBM and the convs that read them run as kind::tf32.
+ *   F16  (default): fp16 operands (GroupNorm outputs, weights, attention operands are bounded) — meets the
+ *                   1e-2 end-to-end tolerance;
+ *   BF16          : bf16 operands, same speed, ~8x larger operand rounding (DESIGN.md "Precision"). */
+enum { HDRVAE_PRECISION_BF16 = 0, HDRVAE_PRECISION_F16 = 1 };
 
 /* conv implementation selector (debug/validation): the tcgen05 implicit-GEMM
  * kernel is the product path; the CUDA-core direct kernel exists to validate it
@@ -113,6 +117,8 @@ int hdrvae_create(hdrvae_ctx** out, int device);
 int hdrvae_destroy(hdrvae_ctx* ctx);
 /* HDRVAE_CONV_TCGEN05 (default) or HDRVAE_CONV_DIRECT (validation only; also env HDRVAE_CONV_IMPL=direct). */
 int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl);
+/* HDRVAE_F16 or HDRVAE_BF16: element type of hdrvae_decode_features' output (set by hdrvae_load_weights). */
+int hdrvae_operand_dtype(hdrvae_ctx* ctx);
 
 /* Diagnostics: per-op CUDA-event timing of everything the library launches between begin and end
  * (the reference's only instrumentation is logging with host syncs, hdr_vae_decode.py:81-84,188-193). */
@@ -155,16 +161,16 @@ int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float e
                          size_t workspace_bytes, void* stream);
 
 /* Decoder only: latent -> SiLU(norm_out(h)), the tensor the reference's forward
- * hook captures (hdr_vae_decode.py:850-855), as device bf16 NHWC [B,8h,8w,128]. */
+ * hook captures (hdr_vae_decode.py:850-855), as device NHWC [B,8h,8w,128] of hdrvae_operand_dtype(ctx) (fp16 by default). */
 int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent_nchw, int B, int h, int w,
-                           void* features_nhwc_bf16, void* workspace, size_t workspace_bytes,
+                           void* features_nhwc, void* workspace, size_t workspace_bytes,
                            void* stream);
 
 /* Fused HDR epilogue on caller-supplied activations (the 1e-5 parity entry):
  * replaces analyze_conv_out's statistics + conv_out (:862-879), the MAX-pool
  * (:1042-1056), srgb_to_linear (:1163), the recovery block (:1076-1102), the mode
  * formulas (:1106-1159) and the multiplier (:180-182).
- *   pre_nhwc : device [B,H,W,128], dtype HDRVAE_F32 or HDRVAE_BF16
+ *   pre_nhwc : device [B,H,W,128], dtype HDRVAE_F32, HDRVAE_F16 or HDRVAE_BF16
  *   conv_w   : device float32 [3,128,3,3] (OIHW, as in the state dict), conv_b [3]
  *   dbg_post3 / dbg_pre3 / dbg_argmax3 : optional device outputs [B,H,W,3]
  *               (float32, float32, int32): clamp((conv+1)/2), MAX-pool, first-max index
@@ -178,25 +184,31 @@ int hdrvae_epilogue(hdrvae_ctx* ctx, const void* pre_nhwc, int dtype, int B, int
                     void* stream);
 
 /* ---- kernel-level entry points (unit parity tests and micro-benchmarks) ----
- * Generic NHWC bf16 convolution on the tcgen05 implicit-GEMM kernel (or the
- * CUDA-core validation kernel): replaces one nn.Conv2d of ComfyUI's Decoder as
- * driven by vae.decode (:859,:1022).
- *   x [B,H,W,Cin] bf16, w OIHW float32 [Cout,Cin,k,k] (k = 1 or 3, pad k/2),
- *   bias float32 [Cout] or NULL, residual bf16 [B,OH,OW,Cout] or NULL,
- *   upsample2x != 0: nearest-2x upsample folded into the load (OH=2H, OW=2W),
- *   y [B,OH,OW,Cout] bf16 (out_f32 != 0: float32).  */
-int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int B, int H, int W, int Cin, const float* w,
-                  const float* bias, int Cout, int ksize, int upsample2x, const void* residual,
-                  void* y, int out_f32, int impl, void* stream);
+ * Generic NHWC convolution on the tcgen05 implicit-GEMM kernel (or the CUDA-core validation kernel):
+ * replaces one nn.Conv2d of ComfyUI's Decoder as driven by vae.decode (:859,:1022).
+ *   x [B,H,W,Cin] of x_dtype: HDRVAE_F16 / HDRVAE_BF16 (kind::f16) or HDRVAE_F32 (read as tf32, kind::tf32);
+ *   w OIHW float32 [Cout,Cin,k,k] (k = 1 or 3, pad k/2), bias float32 [Cout] or NULL (device pointers);
+ *   residual [B,OH,OW,Cout] of res_dtype or NULL; upsample2x != 0: nearest-2x upsample folded into the load
+ *   (OH=2H, OW=2W); y [B,OH,OW,Cout] of y_dtype; round_tf32: round a float32 y to tf32 (RN);
+ *   gn_partials: optional device float32 [B][chunks][32][2] receiving the GroupNorm (sum, sum of squares)
+ *   partials of y, chunks = hdrvae_conv2d_stats_chunks(H, W, upsample2x) (also stored to *gn_chunks). */
+int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, int H, int W, int Cin, const float* w,
+                  const float* bias, int Cout, int ksize, int upsample2x, const void* residual, int res_dtype,
+                  void* y, int y_dtype, int round_tf32, float* gn_partials, int* gn_chunks, int impl,
+                  void* stream);
+int hdrvae_conv2d_stats_chunks(int H, int W, int upsample2x);
 
-/* GroupNorm(32 groups, eps 1e-6, affine) [+ SiLU] on NHWC bf16: replaces
- * norm1/norm2/norm_out + swish of ComfyUI's Decoder.  gamma/beta float32 [C]. */
-int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int B, int HW, int C, const float* gamma,
-                          const float* beta, int apply_silu, void* y, void* stream);
+/* GroupNorm(32 groups, eps 1e-6, affine) [+ SiLU] on NHWC: replaces norm1/norm2/norm_out + swish of
+ * ComfyUI's Decoder.  x of x_dtype (float32 stream or 16-bit), y of y_dtype (HDRVAE_F16/BF16), gamma/beta
+ * float32 [C].  gn_partials/gn_chunks: statistics partials emitted by hdrvae_conv2d for x (skips the
+ * statistics pass), or NULL/0. */
+int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, int HW, int C, const float* gamma,
+                          const float* beta, int apply_silu, void* y, int y_dtype, const float* gn_partials,
+                          int gn_chunks, void* stream);
 
 /* Single-head attention over T tokens, d = 512 (mid.attn_1 core):
- * q,k,v,o device bf16 [B,T,512]; softmax(q k^T / sqrt(512)) v. */
-int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int B, int T,
+ * q,k,v,o device [B,T,512] of dtype HDRVAE_F16 or HDRVAE_BF16; softmax(q k^T / sqrt(512)) v. */
+int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int dtype, int B, int T,
                      void* o, void* stream);
 
 /* fp32 -> fp16 round-to-nearest-even pack for LinearEXRExport

@@ -1,5 +1,4 @@
 """End-to-end parity of the B200 decode against the fp32 oracle (same seeded weights and latents)."""
-import numpy as np
 import pytest
 import torch
 
@@ -16,7 +15,7 @@ def setup():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     dec = build_decoder(0).to(DEV)
-    eng = HdrVaeEngine(dec.state_dict(), DEV)
+    eng = HdrVaeEngine(dec.state_dict(), DEV)          # default precision: fp16 operands, fp32 streams
     yield dec, eng
     eng.close()
 
@@ -25,22 +24,23 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
 
 
-@pytest.mark.parametrize("B,h,w", [(1, 8, 8), (2, 4, 6), (1, 16, 16), (1, 5, 9)])
+@pytest.mark.parametrize("B,h,w", [(1, 8, 8), (2, 4, 6), (1, 16, 16), (1, 5, 9), (1, 32, 32)])
 def test_decoder_features_vs_oracle(setup, B, h, w):
-    """SiLU(norm_out(h)) — the tensor the reference's hook captures — bf16 pipeline vs fp32 oracle.
-    Tolerance: BASELINE.json north_star, rel-L2 <= 1e-2 for the bf16 decode."""
+    """SiLU(norm_out(h)) — the tensor the reference's hook captures — 16-bit tensor-core pipeline vs the fp32
+    oracle.  The end-to-end tolerance is rel-L2 <= 1e-2 on the IMAGE (north_star); the HDR math amplifies
+    feature error about 4x (exposure mode), so the features are held to 3e-3 here (measured ~1.7e-3)."""
     dec, eng = setup
     z = make_latent(B, h, w, seed=100 + h * w).to(DEV)
     with torch.no_grad():
         ref = dec.features(z).permute(0, 2, 3, 1)
     got = eng.decode_features(z).float()
     assert got.shape == ref.shape and torch.isfinite(got).all()
-    assert _rel(got, ref) < 1e-2, _rel(got, ref)
+    assert _rel(got, ref) < 3e-3, _rel(got, ref)
 
 
 def test_tcgen05_path_equals_direct_path(setup):
-    """Whole decoder with the tcgen05 kernels vs the CUDA-core validation kernels: same bf16 operands,
-    only the fp32 accumulation order differs (amplified a little by ~60 layers of bf16 re-rounding)."""
+    """Whole decoder with the tcgen05 kernels vs the CUDA-core validation kernels: same rounded operands,
+    only the fp32 accumulation order (and where the GroupNorm statistics are summed) differs."""
     from vae_decode_hdr_b200 import _native as N
     dec, eng = setup
     z = make_latent(1, 8, 8, seed=5).to(DEV)
@@ -50,12 +50,12 @@ def test_tcgen05_path_equals_direct_path(setup):
         b = eng.decode_features(z).float()
     finally:
         eng.set_conv_impl(N.CONV_TCGEN05)
-    assert _rel(a, b) < 3e-3, _rel(a, b)
+    assert _rel(a, b) < 1e-3, _rel(a, b)
 
 
 @pytest.mark.parametrize("mode", list(ho.HDR_MODES) + ["moderate"])
 def test_full_decode_vs_oracle(setup, mode):
-    """Node-level output.  bf16 decode within rel-L2 <= 1e-2 of the fp32 reference output (north_star)."""
+    """Node-level output within rel-L2 <= 1e-2 of the fp32 reference output (BASELINE.json north_star)."""
     dec, eng = setup
     z = make_latent(2, 16, 16, seed=77).to(DEV)
     out, st = eng.decode(z, mode, 1.0)
@@ -64,8 +64,28 @@ def test_full_decode_vs_oracle(setup, mode):
     assert st["accepted"] == rst["accepted"] == 1
     assert st["norm_function"] == rst["norm_function"] and st["has_hdr"] == rst["has_hdr"]
     assert _rel(out, ref.to(DEV)) < 1e-2, _rel(out, ref.to(DEV))
-    assert st["pre_max"] == pytest.approx(rst["pre_max"], rel=2e-2)
+    assert st["pre_max"] == pytest.approx(rst["pre_max"], rel=5e-3)
     assert st["hdr_pixels"] == int((out > 1.0).sum())
+
+
+def test_bf16_operand_mode_documented_error(setup):
+    """HDRVAE_PRECISION_BF16: same kernels and speed, bf16 operand rounding (2^-8 instead of 2^-11).  It does
+    NOT meet the 1e-2 image tolerance with random-init weights (DESIGN.md 'Precision'); bounds documented here."""
+    from vae_decode_hdr_b200.engine import HdrVaeEngine
+    dec, _ = setup
+    eng = HdrVaeEngine(dec.state_dict(), DEV, precision="bf16")
+    try:
+        z = make_latent(1, 16, 16, seed=1234).to(DEV)
+        with torch.no_grad():
+            ref = dec.features(z).permute(0, 2, 3, 1)
+        got = eng.decode_features(z)
+        assert got.dtype == torch.bfloat16
+        assert _rel(got.float(), ref) < 2e-2
+        out, st = eng.decode(z, "conservative")
+        oref, _, _ = ho.simple_hdr_decode(dec, z, "conservative", 1.0)
+        assert _rel(out, oref.to(DEV)) < 2e-2
+    finally:
+        eng.close()
 
 
 def test_node_api_matches_reference_surface(setup):
@@ -106,3 +126,25 @@ def test_decode_is_deterministic(setup):
     a, _ = eng.decode(z, "exposure")
     b, _ = eng.decode(z, "exposure")
     assert torch.equal(a, b)
+
+
+def test_batch_sharded_decode_equals_whole_batch(setup):
+    """Multi-GPU batch sharding emulated on one GPU: two 'ranks' decode half the batch each, the raw statistics
+    are merged exactly as the NCCL all-reduce does (MIN/MAX/SUM), and the result must equal the whole-batch
+    decode up to the summation order of the double-precision sums (statistics are batch-global in the reference)."""
+    from vae_decode_hdr_b200.sharding import merge_raw_stats, shard_bounds
+    _, eng = setup
+    z = make_latent(4, 8, 8, seed=31).to(DEV)
+    whole, st = eng.decode(z, "adaptive_recovery")
+    blocks, outs = [], []
+    bounds = shard_bounds(4, 2)
+    for s, e in bounds:
+        vmin, vmax, vsum = eng.decode_begin(z[s:e])
+        blocks.append((vmin.clone(), vmax.clone(), vsum.clone()))
+    mmin, mmax, msum = merge_raw_stats(blocks)
+    for s, e in bounds:
+        vmin, vmax, vsum = eng.decode_begin(z[s:e])           # recompute the slice, then install the merged block
+        vmin.copy_(mmin); vmax.copy_(mmax); vsum.copy_(msum)
+        o, _ = eng.decode_finish("adaptive_recovery")
+        outs.append(o)
+    assert torch.allclose(torch.cat(outs), whole, rtol=1e-6, atol=1e-7)

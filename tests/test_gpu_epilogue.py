@@ -31,17 +31,25 @@ def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a))
 
 
-def _check_image(out, ref, post3_ref):
-    """1e-5 gate (BASELINE.json north_star), stated as rel-L2 and max-abs/max-ref (SURVEY.md §7 'Epilogue
-    tolerance near saturation').  The max-abs test leaves out elements whose clamped sRGB value lies within
-    1e-3 of the clamp ends 0/1: there logit'(s) = 1/(s(1-s)) >= 1e3 multiplies the 1-ulp summation-order
-    difference of conv_out (which torch itself does not reproduce across thread counts)."""
+def _check_image(out, ref, pre_nchw, post3_cuda, mode, mult=1.0):
+    """The 1e-5 gate of BASELINE.json north_star, in the two forms SURVEY.md §7 asks for:
+      (1) rel-L2 against the reference / oracle image;
+      (2) max-abs / max-ref, element by element, against the oracle's HDR math evaluated on the kernel's OWN
+          clamp((conv_out+1)/2) — this takes the fp32 summation order of conv_out out of the comparison:
+          near the clamp ends logit'(s) = 1/(s(1-s)) multiplies a 1-ulp difference of conv_out by up to 1e7,
+          which torch itself does not reproduce across thread counts; conv_out is checked on its own."""
     out, ref = out.double(), ref.double()
     rel = float((out - ref).norm() / ref.norm())
     assert rel < 1e-5, rel
-    safe = (post3_ref > 1e-3) & (post3_ref < 1 - 1e-3) | (post3_ref == 0) | (post3_ref == 1)
-    err = ((out - ref).abs() * safe).max() / ref.abs().max()
-    assert float(err) < 1e-5, float(err)
+    m, factor = ho.resolve_mode(mode)
+    pre = pre_nchw.float()
+    st = {"pre_min": float(pre.min()), "pre_max": float(pre.max()), "pre_mean": float(pre.mean())}
+    pmin, pmax = float(post3_cuda.min()), float(post3_cuda.max())
+    st["norm_function"] = 1 if abs(pmax - 1) < 1e-3 and abs(pmin) < 1e-3 else (2 if abs(pmax - 1) < 1e-3 and abs(pmin + 1) < 1e-3 else 0)
+    same_s, _ = ho.intelligent(post3_cuda, pre, st, m, factor)
+    same_s = (same_s * mult if mult != 1.0 else same_s).double()
+    err = float((out - same_s).abs().max() / same_s.abs().max())
+    assert err < 1e-5, err
 
 
 @pytest.mark.parametrize("case", GOLD)
@@ -70,7 +78,7 @@ def test_epilogue_matches_reference_goldens(engine, case, mode):
     else:   # reference raised TypeError -> bypass; deterministic rule: linear LDR (oracle docstring)
         assert st["has_hdr"] == 0
         ref = ho.srgb_to_linear(_t(g["final_result"]))
-    _check_image(out, ref, _t(g["final_result"]))
+    _check_image(out, ref, pre, post3, mode)
     assert st["hdr_pixels"] == int((out > 1.0).sum()) and st["negative_pixels"] == int((out < 0).sum())
     assert st["highlight_count"] == int((pre3 > 1.0).sum())
     assert st["out_max"] == float(out.max()) and st["out_min"] == float(out.min())
@@ -80,19 +88,21 @@ def test_epilogue_matches_reference_goldens(engine, case, mode):
 def test_epilogue_multiplier_and_aliases(engine, mode, mult):
     g = _load("b_b2_4x6")
     pre = _t(g["pre_conv_out"])
-    out, st = engine.epilogue(pre.permute(0, 2, 3, 1).contiguous().to(DEV), _t(g["conv_w"]), _t(g["conv_b"]), mode, mult)
+    out, st, post3, _, _ = engine.epilogue(pre.permute(0, 2, 3, 1).contiguous().to(DEV), _t(g["conv_w"]), _t(g["conv_b"]),
+                                           mode, mult, debug=True)
     ref, rst = ho.hdr_epilogue(pre, _t(g["conv_w"]), _t(g["conv_b"]), mode, mult)
-    _check_image(out.cpu(), ref, _t(g["final_result"]))
+    _check_image(out.cpu(), ref, pre, post3.cpu(), mode, mult)
     assert st["accepted"] == rst["accepted"] == 1
     key = f"node.{mode}.x{mult}"
     if key in g:
-        _check_image(out.cpu(), _t(g[key]), _t(g["final_result"]))
+        _check_image(out.cpu(), _t(g[key]), pre, post3.cpu(), mode, mult)
 
 
-def test_epilogue_bf16_activations_and_ragged_tiles(engine):
-    """bf16 activations (the product path's input type), sizes that do not divide the 32x8 tile."""
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_epilogue_16bit_activations_and_ragged_tiles(engine, dt):
+    """16-bit activations (the product path's input type), sizes that do not divide the 32x8 tile."""
     gen = torch.Generator().manual_seed(21)
-    pre = (torch.randn(2, 128, 19, 45, generator=gen) * 0.6 + 0.2).to(torch.bfloat16)
+    pre = (torch.randn(2, 128, 19, 45, generator=gen) * 0.6 + 0.2).to(dt)
     pre[0, 5, 3, 7] = 7.5
     w = torch.randn(3, 128, 3, 3, generator=gen) * 0.05
     b = torch.randn(3, generator=gen) * 0.1
@@ -102,7 +112,8 @@ def test_epilogue_bf16_activations_and_ragged_tiles(engine):
         assert torch.equal(pre3.cpu(), ho.channel_maxpool3(pre.float()).contiguous())
         assert torch.equal(am3.cpu(), ho.channel_argmax3(pre.float()))
         an = ho.analyze(pre.float(), w, b)
-        _check_image(out.cpu(), ref, an["standard"].contiguous())
+        assert float((post3.cpu() - an["standard"]).abs().max()) < 2e-6
+        _check_image(out.cpu(), ref, pre, post3.cpu(), mode)
         assert st["has_hdr"] == rst["has_hdr"] == 1 and st["norm_function"] == rst["norm_function"]
 
 

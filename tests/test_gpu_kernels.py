@@ -1,6 +1,6 @@
 """Kernel-level parity on the B200, through the C ABI (vae_decode_hdr_b200.engine -> libhdrvae.so).
-Each CUDA kernel against a plain PyTorch fp32 evaluation of the same op on the same bf16-rounded
-operands (tolerances written at each check)."""
+Each CUDA kernel against a plain PyTorch fp32 evaluation of the same op on the same (rounded) operands;
+the tolerance and where it comes from is written at each check."""
 import math
 
 import numpy as np
@@ -11,6 +11,9 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
+OPS = {"fp16": torch.float16, "bf16": torch.bfloat16, "tf32": torch.float32}
+# relative rounding step of one operand element: fp16/tf32 2^-11, bf16 2^-8 (half an ulp)
+W_ROUND = {"fp16": 2.0 ** -11, "bf16": 2.0 ** -8, "tf32": 2.0 ** -11}
 
 
 @pytest.fixture(scope="module")
@@ -19,8 +22,7 @@ def engine():
     from vae_decode_hdr_b200.engine import HdrVaeEngine
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    dec = build_decoder(0)
-    eng = HdrVaeEngine(dec.state_dict(), DEV)
+    eng = HdrVaeEngine(build_decoder(0).state_dict(), DEV)
     yield eng
     eng.close()
 
@@ -30,12 +32,19 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def _bf(x):
-    return x.to(torch.bfloat16).float()
+def _round_tf32(x):
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _as_operand(x, op):
+    """Values exactly representable in the operand type, as float32."""
+    if op == "tf32":
+        return _round_tf32(x)
+    return x.to(OPS[op]).float()
 
 
 def _conv_ref(x_nhwc, w, b, ksize, upsample, residual):
-    """fp32 conv on the bf16-rounded activations, fp32 weights -> NHWC."""
     x = x_nhwc.float().permute(0, 3, 1, 2)
     if upsample:
         x = F.interpolate(x, scale_factor=2.0, mode="nearest")
@@ -59,63 +68,108 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("op", list(OPS))
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
-def test_conv_tcgen05_matches_torch_and_direct(engine, case):
+def test_conv_tcgen05_matches_torch_and_direct(engine, case, op):
     from vae_decode_hdr_b200 import _native as N
     B, H, W, cin, cout, ks, up, res = case
-    g = torch.Generator(device="cpu").manual_seed(hash(case) % (2 ** 31))
-    x = _bf(torch.randn(B, H, W, cin, generator=g)).to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(abs(hash(case)) % (2 ** 31))
+    x = _as_operand(torch.randn(B, H, W, cin, generator=g), op).to(DEV)
     w = (torch.randn(cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks)).to(DEV)
     b = torch.randn(cout, generator=g).to(DEV)
     OH, OW = (2 * H, 2 * W) if up else (H, W)
-    r = _bf(torch.randn(B, OH, OW, cout, generator=g)).to(DEV) if res else None
-    y_tc = engine.conv2d(x.bfloat16(), w, b, ks, up, r.bfloat16() if res else None, out_f32=True, impl=N.CONV_TCGEN05)
-    y_dr = engine.conv2d(x.bfloat16(), w, b, ks, up, r.bfloat16() if res else None, out_f32=True, impl=N.CONV_DIRECT)
+    r = torch.randn(B, OH, OW, cout, generator=g).to(DEV) if res else None     # fp32 residual stream
+    xo = x.to(OPS[op])
+    stats_ok = cout in (128, 256, 512)
+    got = engine.conv2d(xo, w, b, ks, up, r, out_dtype=torch.float32, want_stats=stats_ok, impl=N.CONV_TCGEN05)
+    y_tc, part = got if stats_ok else (got, None)
+    y_dr = engine.conv2d(xo, w, b, ks, up, r, out_dtype=torch.float32, impl=N.CONV_DIRECT)
     torch.cuda.synchronize()
     assert torch.isfinite(y_tc).all()
-    # same bf16 operands, fp32 accumulation in a different order: 1e-5 relative
+    # same rounded operands, fp32 accumulation in a different order: 1e-5 relative
     assert _rel(y_tc, y_dr) < 1e-5, ("tcgen05 vs direct", _rel(y_tc, y_dr))
-    # torch fp32 conv with UNROUNDED weights: the bf16 weight rounding (2^-9 relative per weight,
-    # averaged over K terms) bounds the difference
+    # torch fp32 conv with UNROUNDED weights: only the operand rounding of the weights differs
+    # (relative step W_ROUND per weight, averaged over the K terms; upsample phase weights are pre-summed)
     ref = _conv_ref(x, w, b, ks, up, r)
-    assert _rel(y_tc, ref) < 4e-3, ("tcgen05 vs torch", _rel(y_tc, ref))
-    # bf16 output path
-    y_bf = engine.conv2d(x.bfloat16(), w, b, ks, up, r.bfloat16() if res else None, out_f32=False)
-    assert _rel(y_bf.float(), y_tc) < 4e-3
+    assert _rel(y_tc, ref) < 1.1 * W_ROUND[op], ("tcgen05 vs torch", _rel(y_tc, ref))
+    # 16-bit output paths
+    for od in (torch.float16, torch.bfloat16):
+        y16 = engine.conv2d(xo, w, b, ks, up, r, out_dtype=od)
+        assert _rel(y16.float(), y_tc) < (2.0 ** -10 if od == torch.float16 else 2.0 ** -7)
+    if stats_ok:
+        # GroupNorm partials emitted by the conv epilogue == (sum, sum of squares) per group of the fp32 output
+        cpg = cout // 32
+        yg = y_tc.double().reshape(B, OH * OW, 32, cpg)
+        want = torch.stack([yg.sum((1, 3)), (yg * yg).sum((1, 3))], dim=-1)       # [B,32,2]
+        assert torch.allclose(part.double().sum(1), want, rtol=2e-5, atol=1e-3), float((part.double().sum(1) - want).abs().max())
 
 
-def test_conv_weight_rounding_is_the_only_difference(engine):
-    """With weights that are exactly representable in bf16 the kernel must agree with torch to fp32 noise."""
+def test_conv_exact_operands_agree_with_torch_to_fp32_noise(engine):
+    """With weights exactly representable in the operand type the kernel must agree with torch to fp32 noise."""
     g = torch.Generator().manual_seed(5)
-    x = _bf(torch.randn(1, 16, 24, 128, generator=g)).to(DEV)
-    w = _bf(torch.randn(256, 128, 3, 3, generator=g) / 34.0).to(DEV)
-    b = torch.randn(256, generator=g).to(DEV)
-    y = engine.conv2d(x.bfloat16(), w, b, 3, out_f32=True)
-    ref = _conv_ref(x, w, b, 3, False, None)
-    assert _rel(y, ref) < 2e-6
+    for op in OPS:
+        x = _as_operand(torch.randn(1, 16, 24, 128, generator=g), op).to(DEV)
+        w = _as_operand(torch.randn(256, 128, 3, 3, generator=g) / 34.0, op).to(DEV)
+        b = torch.randn(256, generator=g).to(DEV)
+        y = engine.conv2d(x.to(OPS[op]), w, b, 3)
+        assert _rel(y, _conv_ref(x, w, b, 3, False, None)) < 2e-6, op
 
 
-@pytest.mark.parametrize("shape,silu", [((2, 16, 16, 512), True), ((1, 9, 13, 256), True), ((3, 32, 32, 128), True),
-                                        ((1, 64, 64, 512), False), ((1, 1, 1, 128), True)])
-def test_groupnorm_silu(engine, shape, silu):
+def test_tf32_conv_on_unrounded_stream_and_round_flag(engine):
+    """kind::tf32 reads the top 19 bits of each fp32: feeding an un-rounded stream costs < 2^-10 relative;
+    round_tf32 rounds the fp32 output (RN) so the next tf32 conv reads it exactly."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 16, 16, 256, generator=g).to(DEV)
+    w = (torch.randn(128, 256, 1, 1, generator=g) / 16.0).to(DEV)
+    y = engine.conv2d(x, w, None, 1)
+    ref = _conv_ref(x, w, None, 1, False, None)
+    assert _rel(y, ref) < 2.0 ** -10
+    yr = engine.conv2d(x, w, None, 1, round_tf32=True)
+    assert torch.equal(yr, _round_tf32(yr)) and _rel(yr, y) < 2.0 ** -11
+
+
+GN_CASES = [((2, 16, 16, 512), True), ((1, 9, 13, 256), True), ((3, 32, 32, 128), True), ((1, 64, 64, 512), False),
+            ((1, 1, 1, 128), True)]
+
+
+@pytest.mark.parametrize("in_dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("out_dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,silu", GN_CASES)
+def test_groupnorm_silu(engine, shape, silu, in_dt, out_dt):
     g = torch.Generator().manual_seed(11)
     B, H, W, Cc = shape
-    x = _bf(torch.randn(shape, generator=g) * 2.0 + 0.7).to(DEV)
+    x = (torch.randn(shape, generator=g) * 2.0 + 0.7).to(in_dt).to(DEV)
     gamma = (1.0 + 0.1 * torch.randn(Cc, generator=g)).to(DEV)
     beta = (0.1 * torch.randn(Cc, generator=g)).to(DEV)
-    y = engine.groupnorm_silu(x.bfloat16(), gamma, beta, silu).float()
-    ref = F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)
+    y = engine.groupnorm_silu(x, gamma, beta, silu, out_dtype=out_dt).float()
+    ref = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)
     if silu:
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 3, 1)
-    # output is rounded to bf16: half an ulp = 2^-9 relative
-    assert torch.allclose(y, ref, rtol=2 ** -8, atol=2e-3), float((y - ref).abs().max())
-    assert _rel(y, ref) < 3e-3
+    half_ulp = 2.0 ** -11 if out_dt == torch.float16 else 2.0 ** -8     # the output rounding
+    assert torch.allclose(y, ref, rtol=2 * half_ulp, atol=2e-3 if out_dt == torch.bfloat16 else 3e-4), float((y - ref).abs().max())
+    assert _rel(y, ref) < 1.5 * half_ulp
+
+
+def test_groupnorm_from_conv_partials_equals_standalone(engine):
+    """The decoder path: statistics emitted by the producing conv's epilogue instead of a second read."""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 20, 28, 128, generator=g).to(DEV).half()
+    w = (torch.randn(256, 128, 3, 3, generator=g) / 34.0).to(DEV)
+    b = torch.randn(256, generator=g).to(DEV)
+    y, part = engine.conv2d(x, w, b, 3, want_stats=True)
+    gamma = (1.0 + 0.1 * torch.randn(256, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(256, generator=g)).to(DEV)
+    a = engine.groupnorm_silu(y, gamma, beta, True, partials=part).float()
+    s = engine.groupnorm_silu(y, gamma, beta, True).float()
+    ref = F.silu(F.group_norm(y.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
+    assert _rel(a, ref) < 2.0 ** -10 and _rel(a, s) < 2.0 ** -10
+    assert float((a - s).abs().max()) < 2e-3
 
 
 def test_groupnorm_is_run_to_run_deterministic(engine):
     g = torch.Generator().manual_seed(12)
-    x = torch.randn(2, 40, 40, 256, generator=g).to(DEV).bfloat16()
+    x = torch.randn(2, 40, 40, 256, generator=g).to(DEV)
     gamma = torch.ones(256, device=DEV)
     beta = torch.zeros(256, device=DEV)
     a = engine.groupnorm_silu(x, gamma, beta, True)
@@ -123,17 +177,18 @@ def test_groupnorm_is_run_to_run_deterministic(engine):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,T", [(1, 64), (2, 256), (1, 24), (1, 1000), (1, 4096)])
-def test_attention(engine, B, T):
+def test_attention(engine, B, T, dt):
     g = torch.Generator().manual_seed(T)
-    q = _bf(torch.randn(B, T, 512, generator=g)).to(DEV)
-    k = _bf(torch.randn(B, T, 512, generator=g)).to(DEV)
-    v = _bf(torch.randn(B, T, 512, generator=g)).to(DEV)
-    o = engine.attention(q.bfloat16(), k.bfloat16(), v.bfloat16()).float()
-    p = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(512.0), dim=-1)
-    ref = p @ v
-    # probabilities are rounded to bf16 before PV and the output to bf16: ~2^-9 relative each
-    assert _rel(o, ref) < 6e-3, _rel(o, ref)
+    q = torch.randn(B, T, 512, generator=g).to(dt).to(DEV)
+    k = torch.randn(B, T, 512, generator=g).to(dt).to(DEV)
+    v = torch.randn(B, T, 512, generator=g).to(dt).to(DEV)
+    o = engine.attention(q, k, v).float()
+    p = torch.softmax(q.float() @ k.float().transpose(1, 2) / math.sqrt(512.0), dim=-1)
+    ref = p @ v.float()
+    # exp(s - max) is rounded to the operand type before PV, the output once more: ~half an ulp each
+    assert _rel(o, ref) < (1.2e-3 if dt == torch.float16 else 6e-3), _rel(o, ref)
 
 
 def test_pack_half_bit_exact_vs_numpy():
@@ -144,7 +199,8 @@ def test_pack_half_bit_exact_vs_numpy():
     img[0, 0, 0, 1] = -1e-8         # underflow -> -0
     img[0, 0, 0, 2] = 6.0e-6        # fp16 subnormal
     img[0, 0, 1, 0] = 1.00048828125  # exact tie -> round to even
-    want = img.numpy().astype(np.float16)
+    with np.errstate(over="ignore"):
+        want = img.numpy().astype(np.float16)
     got = pack_half(img.to(DEV)).cpu().numpy()
     assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
     planes = pack_half(img.to(DEV), exr_scanline_order=True).cpu().numpy()     # [B,H,3(B,G,R),W]

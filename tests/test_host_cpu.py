@@ -1,0 +1,169 @@
+"""Host-side logic without a GPU: the C-ABI library loads and exports every symbol include/hdrvae.h
+declares, struct layouts match the ctypes mirror, the node surface equals the reference's, error paths
+fail loudly (no CPU fallback), multi-GPU host logic on gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vae_decode_hdr_b200 import _native
+    if not os.path.isfile(_native.LIB_PATH):
+        _native.build_library()
+    return _native.load_library()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hdrvae.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hdrvae_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from vae_decode_hdr_b200 import _native
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"libhdrvae.so lacks {n} declared in include/hdrvae.h"
+        assert n in _native.SIGNATURES, f"{n} has no ctypes signature in _native.py"
+    assert sorted(_native.SIGNATURES) == names
+    assert lib.hdrvae_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from vae_decode_hdr_b200 import _native as N
+    assert C.sizeof(N.HdrvaeStats) == 200           # static_assert'ed in csrc/api.cu
+    assert C.sizeof(N.HdrvaeRawStats) == 96
+    assert C.sizeof(N.HdrvaeWeightDesc) == 56
+    assert N.HdrvaeStats.norm_function.offset == 184 and N.HdrvaeStats.hdr_pixels.offset == 144
+
+
+def test_sass_is_blackwell_native():
+    """The product kernels must be tcgen05/TMA code, not recompiled mma.sync: UTCHMMA / UTMALDG / LDTM in SASS."""
+    import shutil
+    import subprocess
+    from vae_decode_hdr_b200 import _native
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product path must raise, never compute on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vae_decode_hdr_b200.engine import HdrVaeEngine
+    from vae_decode_hdr_b200 import NODE_CLASS_MAPPINGS
+    from vae_decode_hdr_b200.synthetic import SyntheticVAE
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HdrVaeEngine({}, "cuda")
+    ctx = C.c_void_p()
+    assert lib.hdrvae_create(C.byref(ctx), 0) != 0 and lib.hdrvae_last_error()
+    node = NODE_CLASS_MAPPINGS["HDRVAEDecode"]()
+    with pytest.raises(RuntimeError):
+        node.simple_hdr_decode({"samples": torch.zeros(1, 16, 4, 4)}, SyntheticVAE({}, device="cpu"))
+
+
+def test_product_package_never_imports_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "vae_decode_hdr_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "vae_decode_hdr_b200", fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_node_surface_equals_reference():
+    from vae_decode_hdr_b200 import NODE_CLASS_MAPPINGS, NODE_DISPLAY_NAME_MAPPINGS
+    cls = NODE_CLASS_MAPPINGS["HDRVAEDecode"]
+    it = cls.INPUT_TYPES()
+    assert NODE_DISPLAY_NAME_MAPPINGS == {"HDRVAEDecode": "HDR VAE Decode"}
+    assert (cls.RETURN_TYPES, cls.RETURN_NAMES, cls.FUNCTION, cls.CATEGORY) == (("IMAGE",), ("image",), "simple_hdr_decode", "latent")
+    from oracle.ref_loader import load_reference_module, reference_available
+    if reference_available():      # build container: compare with the unmodified reference class
+        ref = load_reference_module().HDRVAEDecode
+        assert it == ref.INPUT_TYPES()
+        assert (cls.RETURN_TYPES, cls.RETURN_NAMES, cls.FUNCTION, cls.CATEGORY) == \
+            (ref.RETURN_TYPES, ref.RETURN_NAMES, ref.FUNCTION, ref.CATEGORY)
+        import inspect
+        assert list(inspect.signature(cls.simple_hdr_decode).parameters) == \
+            list(inspect.signature(ref.simple_hdr_decode).parameters)
+
+
+def test_mode_resolution_and_synthetic_weights():
+    from vae_decode_hdr_b200.engine import resolve_mode
+    from vae_decode_hdr_b200.synthetic import decoder_param_shapes, random_decoder_state_dict
+    from oracle.flux_decoder import build_decoder
+    assert resolve_mode("conservative") == (0, 1.0) and resolve_mode("exposure") == (1, 1.0)
+    assert resolve_mode("adaptive_recovery") == (2, 1.0) and resolve_mode("mathematical_recovery") == (3, 1.0)
+    assert resolve_mode("Moderate") == (0, 3.0) and resolve_mode("aggressive") == (3, 1.0)
+    with pytest.raises(ValueError):
+        resolve_mode("bypass")
+    ref = build_decoder(0).state_dict()
+    assert {k: tuple(v.shape) for k, v in ref.items()} == dict(decoder_param_shapes())
+    sd = random_decoder_state_dict(0)
+    assert sum(v.numel() for v in sd.values()) == 49_545_475
+
+
+def test_shard_bounds():
+    from vae_decode_hdr_b200.sharding import shard_bounds
+    assert shard_bounds(32, 8) == [(4 * i, 4 * i + 4) for i in range(8)]
+    assert shard_bounds(5, 2) == [(0, 3), (3, 5)]
+    assert shard_bounds(1, 4) == [(0, 1), (1, 1), (1, 1), (1, 1)]
+    assert shard_bounds(0, 2) == [(0, 0), (0, 0)]
+    with pytest.raises(ValueError):
+        shard_bounds(4, 0)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle import hdr_oracle as ho
+    from vae_decode_hdr_b200.sharding import allreduce_raw_stats, shard_bounds
+    g = torch.Generator().manual_seed(0)
+    pre = torch.randn(4, 128, 8, 8, generator=g) * 0.7
+    w = torch.randn(3, 128, 3, 3, generator=g) * 0.05
+    b = torch.zeros(3)
+    s, e = shard_bounds(4, world)[rank]
+
+    def raw(x):     # the hdrvae_raw_stats block of a slice, computed by the oracle (CPU stand-in for phase A)
+        an = ho.analyze(x, w, b)
+        p3 = ho.channel_maxpool3(x)
+        st, co = an["standard"], an["conv_only"]
+        vmin = torch.tensor([x.min(), st.min(), co.min(), p3.min()])
+        vmax = torch.tensor([x.max(), st.max(), co.max(), p3.max()])
+        vsum = torch.tensor([x.double().sum(), (x.double() ** 2).sum(), st.double().sum(), (st.double() ** 2).sum(),
+                             co.double().sum(), x.numel(), st.numel(), float((p3 > 1).sum())], dtype=torch.float64)
+        return vmin, vmax, vsum
+    vmin, vmax, vsum = raw(pre[s:e])
+    allreduce_raw_stats(vmin, vmax, vsum)
+    fmin, fmax, fsum = raw(pre)
+    ok = torch.equal(vmin, fmin) and torch.equal(vmax, fmax) and torch.allclose(vsum, fsum, rtol=1e-12)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_batch_sharded_stats_allreduce_gloo_world2():
+    """N>1 host logic on CPU: sharded raw statistics + MIN/MAX/SUM all-reduce == whole-batch statistics."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -18,7 +18,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 MODE_CONSERVATIVE, MODE_EXPOSURE, MODE_ADAPTIVE_RECOVERY, MODE_MATHEMATICAL_RECOVERY = range(4)
 NORM_NONE, NORM_SIGMOID, NORM_TANH = range(3)
 F32, BF16, F16 = range(3)
-PRECISION_BF16 = 0
+PRECISION_BF16, PRECISION_F16 = 0, 1
 CONV_TCGEN05, CONV_DIRECT = 0, 1
 RAW_NMIN, RAW_NMAX, RAW_NSUM = 4, 4, 8
 
@@ -65,9 +65,12 @@ SIGNATURES = {
     "hdrvae_epilogue_scratch_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "hdrvae_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _vp, C.POINTER(HdrvaeStats),
                              _vp, _vp, _vp, _vp, _sz, _vp]),
-    "hdrvae_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
-    "hdrvae_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "hdrvae_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "hdrvae_operand_dtype": (_i, [_vp]),
+    "hdrvae_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp,
+                           C.POINTER(_i), _i, _vp]),
+    "hdrvae_conv2d_stats_chunks": (_i, [_i, _i, _i]),
+    "hdrvae_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "hdrvae_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "hdrvae_pack_half": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
 }
 

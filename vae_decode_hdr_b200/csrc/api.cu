@@ -1,9 +1,15 @@
 // C ABI of libhdrvae.so (include/hdrvae.h): context, weight repack, the decoder layer program and
 // the entry points.  The layer program restates the Flux.1 AE decoder graph that the reference
 // drives through vae.decode (hdr_vae_decode.py:859,:1022; graph in SURVEY.md §8 a3).
+//
+// Numeric plan (DESIGN.md "Precision"): tensor-core operands are 16-bit (fp16 by default, bf16 selectable)
+// for everything that is normalised or bounded (GroupNorm outputs, weights, attention q/k/v/probabilities);
+// the un-normalised residual stream x and the conv1 outputs h stay fp32 in HBM; the five convs that consume
+// the raw stream (3 upsample convs, 2 nin_shortcuts) read it as tf32 operands (kind::tf32).
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -30,16 +36,16 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream);
 int launch_gemm_direct(const GemmParams& p, cudaStream_t s);
 void choose_tile(int H, int W, GemmParams* p);
 int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStream_t s);
-int launch_pack_weight(const float* w, __nv_bfloat16* out, int cout, int cin, int ks, int ntaps, int cin_pad,
+int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
                        const int* tap_mask, float scale, cudaStream_t s);
-int launch_latent_to_nhwc(const float* z, __nv_bfloat16* out, int B, int C, int HW, int cpad, cudaStream_t s);
-int launch_softmax_rows(const float* s, __nv_bfloat16* p, int n_rows, int n_valid, int n_pad, long long s_ld,
-                        long long p_ld, cudaStream_t st);
-int launch_transpose_pad(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int out_ld, cudaStream_t s);
+int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C, int HW, int cpad, cudaStream_t s);
+int launch_softmax_rows(const float* s, void* p, int p_dtype, float* inv_sum, int n_rows, int n_valid, int n_pad,
+                        long long s_ld, long long p_ld, cudaStream_t st);
+int launch_transpose_pad(const void* in, void* out, int rows, int cols, int out_ld, cudaStream_t s);
 int launch_pack_half(const float* img, uint16_t* out, int B, int H, int W, int layout, cudaStream_t s);
-size_t gn_scratch_bytes(int B, int C);
-int launch_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, const float* gamma,
-                     const float* beta, bool silu, void* scratch, cudaStream_t s);
+size_t gn_scratch_bytes(int B, int C, int max_chunks);
+int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
+                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s);
 size_t epilogue_scratch_bytes(int B, int H, int W);
 void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W);
 float* epilogue_post3_ptr(void* scratch, int B, int H, int W);
@@ -61,15 +67,18 @@ struct ProfScope {
     cudaEventCreate(&e.e0); cudaEventCreate(&e.e1);
     cudaEventRecord(e.e0, s);
     g_prof.push_back(e);
+    idx = g_prof.size() - 1;
   }
-  ~ProfScope() { if (on) cudaEventRecord(g_prof.back().e1, s); }
+  ~ProfScope() { if (on) cudaEventRecord(g_prof[idx].e1, s); }
+  size_t idx = 0;
 };
 
 // ---- packed operands --------------------------------------------------------------------------
 struct PackedConv {
-  __nv_bfloat16* w[4] = {nullptr, nullptr, nullptr, nullptr};  // [Cout][ntaps*cin_pad]; 4 phase matrices when upsample
+  void* w[4] = {nullptr, nullptr, nullptr, nullptr};  // [Cout][ntaps*cin_pad] K-major; 4 phase matrices when upsample
   float* bias = nullptr;
   int cin = 0, cin_pad = 0, cout = 0, ks = 0;
+  int w_dtype = DT_F16;      // operand type of this conv (DT_F32 = tf32 MMA on the raw fp32 stream)
   bool upsample = false;
 };
 struct NormW {
@@ -81,6 +90,7 @@ struct ResW {
   NormW n1, n2;
   PackedConv c1, c2, nin;
   bool has_nin = false;
+  bool round_out = false;    // the block's output feeds a tf32 conv: round it to tf32 when it is written
 };
 
 }  // namespace hdrvae
@@ -92,6 +102,7 @@ struct hdrvae_ctx {
   int num_sms = 148;
   bool loaded = false;
   int conv_impl = HDRVAE_CONV_TCGEN05;
+  int op_dtype = DT_F16;                          // 16-bit tensor-core operand type (HDRVAE_PRECISION_*)
   std::vector<void*> owned;                       // every device allocation of the context
   std::map<std::string, float*> raw;              // fp32 device copies of the state dict
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -135,9 +146,10 @@ static void phase_taps(int py, int px, int* dy, int* dx, int* mask) {
 }
 
 static int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int cin, int ks, bool upsample,
-                     float scale, PackedConv* pc, cudaStream_t s) {
-  pc->cin = cin; pc->cout = cout; pc->ks = ks; pc->upsample = upsample;
+                     float scale, int w_dtype, PackedConv* pc, cudaStream_t s) {
+  pc->cin = cin; pc->cout = cout; pc->ks = ks; pc->upsample = upsample; pc->w_dtype = w_dtype;
   pc->cin_pad = (cin + 63) / 64 * 64;
+  const size_t eb = dt_bytes(w_dtype);
   if (bias != nullptr) {
     HDRVAE_TRY(dev_alloc(ctx, cout * sizeof(float), (void**)&pc->bias));
     HDRVAE_CUDA_OK(cudaMemcpyAsync(pc->bias, bias, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -146,41 +158,65 @@ static int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cou
     const int ntaps = ks * ks;
     int mask[9];
     for (int t = 0; t < ntaps; ++t) mask[t] = 1 << t;
-    HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * ntaps * pc->cin_pad * 2, (void**)&pc->w[0]));
-    HDRVAE_TRY(launch_pack_weight(w, pc->w[0], cout, cin, ks, ntaps, pc->cin_pad, mask, scale, s));
+    HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * ntaps * pc->cin_pad * eb, &pc->w[0]));
+    HDRVAE_TRY(launch_pack_weight(w, pc->w[0], w_dtype, cout, cin, ks, ntaps, pc->cin_pad, mask, scale, s));
   } else {
     HDRVAE_REQUIRE(ks == 3, "upsample folding needs a 3x3 kernel");
     for (int ph = 0; ph < 4; ++ph) {
       int dy[4], dx[4], mask[4];
       phase_taps(ph >> 1, ph & 1, dy, dx, mask);
-      HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * 4 * pc->cin_pad * 2, (void**)&pc->w[ph]));
-      HDRVAE_TRY(launch_pack_weight(w, pc->w[ph], cout, cin, 3, 4, pc->cin_pad, mask, scale, s));
+      HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * 4 * pc->cin_pad * eb, &pc->w[ph]));
+      HDRVAE_TRY(launch_pack_weight(w, pc->w[ph], w_dtype, cout, cin, 3, 4, pc->cin_pad, mask, scale, s));
     }
   }
   return 0;
 }
 
-// x [B,H,W,cin_pad] bf16 -> y [B,OH,OW,cout]; residual has y's layout.
-static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const __nv_bfloat16* x, int B, int H, int W, void* y,
-                    bool out_f32, const __nv_bfloat16* residual, int impl, cudaStream_t s) {
+static int tiles_for(int H, int W) {
+  GemmParams p;
+  choose_tile(H, W, &p);
+  return p.tiles_x * p.tiles_y;
+}
+
+struct ConvIO {
+  const void* x = nullptr;        // [B,H,W,cin_pad], element type = pc.w_dtype
+  void* y = nullptr;              // [B,OH,OW,cout]
+  int y_dtype = DT_F32;
+  const void* residual = nullptr; // y's layout
+  int res_dtype = DT_F32;
+  bool round_tf32 = false;
+  float* stats = nullptr;         // GroupNorm partials of y, or null
+  int* stats_chunks = nullptr;    // out: partial chunks per image written
+};
+
+static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int H, int W, int impl,
+                    cudaStream_t s) {
   char pname[96];
-  snprintf(pname, sizeof pname, "conv%dx%d%s %d->%d @%dx%dx%d", pc.ks, pc.ks, pc.upsample ? "up" : "", pc.cin, pc.cout, B, H, W);
+  snprintf(pname, sizeof pname, "conv%dx%d%s%s %d->%d @%dx%dx%d", pc.ks, pc.ks, pc.upsample ? "up" : "",
+           pc.w_dtype == DT_F32 ? " tf32" : "", pc.cin, pc.cout, B, H, W);
   const double out_px = (double)B * H * W * (pc.upsample ? 4 : 1);
   ProfScope prof(pname, 2.0 * out_px * pc.cout * pc.cin * pc.ks * pc.ks,
-                 (double)B * H * W * pc.cin_pad * 2 + out_px * pc.cout * 2 * (residual ? 2 : 1), s);
+                 (double)B * H * W * pc.cin_pad * dt_bytes(pc.w_dtype) +
+                     out_px * pc.cout * (dt_bytes(io.y_dtype) + (io.residual ? dt_bytes(io.res_dtype) : 0)), s);
   GemmParams p;
   memset(&p, 0, sizeof p);
-  p.a = x;
+  p.a = io.x;
+  p.ab_dtype = pc.w_dtype;
   p.a_px_stride = pc.cin_pad; p.a_row_stride = (long long)W * pc.cin_pad; p.a_img_stride = (long long)H * W * pc.cin_pad;
   p.n_img = B; p.H = H; p.W = W;
   p.k_per_tap = pc.cin_pad;
   p.n_cols = pc.cout;
-  p.out = y; p.out_f32 = out_f32 ? 1 : 0;
-  p.bias = pc.bias; p.bias_per_row = 0; p.residual = residual; p.alpha = 1.0f;
+  p.out = io.y; p.out_dtype = io.y_dtype;
+  p.bias = pc.bias; p.bias_per_row = 0; p.residual = io.residual; p.res_dtype = io.res_dtype; p.alpha = 1.0f;
+  p.round_tf32 = io.round_tf32 ? 1 : 0;
   choose_tile(H, W, &p);
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
   p.out_px_stride = pc.cout; p.out_row_stride = (long long)OW * pc.cout; p.out_img_stride = (long long)OH * OW * pc.cout;
+  const int tiles = p.tiles_x * p.tiles_y;
+  p.stats = io.stats;
+  p.stats_chunks_per_img = phases * tiles;
+  if (io.stats_chunks != nullptr) *io.stats_chunks = io.stats != nullptr ? phases * tiles : 0;
   for (int ph = 0; ph < phases; ++ph) {
     if (pc.upsample) {
       int mask[4];
@@ -192,29 +228,35 @@ static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const __nv_bfloat16* 
       else { p.ntaps = 1; p.tap_dy[0] = p.tap_dx[0] = 0; }
       p.sy = p.sx = 1; p.py = p.px = 0;
     }
+    p.stats_chunk0 = ph * tiles;
     p.b = pc.w[ph];
     p.b_row_stride = (long long)p.ntaps * pc.cin_pad;
     p.b_rows = pc.cout;
-    if (impl == HDRVAE_CONV_DIRECT) HDRVAE_TRY(launch_gemm_direct(p, s));
-    else HDRVAE_TRY(launch_gemm_tc(p, ctx->num_sms, s));
+    if (impl == HDRVAE_CONV_DIRECT) {
+      HDRVAE_REQUIRE(io.stats == nullptr, "the validation conv kernel does not emit GroupNorm statistics");
+      HDRVAE_TRY(launch_gemm_direct(p, s));
+    } else {
+      HDRVAE_TRY(launch_gemm_tc(p, ctx->num_sms, s));
+    }
   }
   return 0;
 }
 
-// Plain K-major GEMM: out[M][n_cols] = alpha * A[M][K] * Bm[n_cols][K]^T (+ bias) on the same kernel.
-static int run_gemm(hdrvae_ctx* ctx, const __nv_bfloat16* A, long long lda, int M, int K, const __nv_bfloat16* Bm,
-                    long long ldb, int b_rows, int n_cols, void* out, long long ldo, bool out_f32, const float* bias,
-                    bool bias_per_row, float alpha, int impl, cudaStream_t s) {
+// Plain K-major GEMM: out[M][n_cols] = row_scale[m] * alpha * A[M][K] * Bm[n_cols][K]^T (+ bias) on the same kernel.
+static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda, int M, int K, const void* Bm,
+                    long long ldb, int b_rows, int n_cols, void* out, long long ldo, int out_dtype, const float* bias,
+                    bool bias_per_row, float alpha, const float* row_scale, int impl, cudaStream_t s) {
   GemmParams p;
   memset(&p, 0, sizeof p);
-  p.a = A; p.a_px_stride = lda; p.a_row_stride = (long long)M * lda; p.a_img_stride = (long long)M * lda;
+  p.a = A; p.ab_dtype = ab_dtype;
+  p.a_px_stride = lda; p.a_row_stride = (long long)M * lda; p.a_img_stride = (long long)M * lda;
   p.n_img = 1; p.H = 1; p.W = M;
   p.k_per_tap = K; p.ntaps = 1;
   p.b = Bm; p.b_row_stride = ldb; p.b_rows = b_rows; p.n_cols = n_cols;
-  p.out = out; p.out_f32 = out_f32 ? 1 : 0;
+  p.out = out; p.out_dtype = out_dtype;
   p.out_px_stride = ldo; p.out_row_stride = 0; p.out_img_stride = 0;
   p.sy = p.sx = 1;
-  p.bias = bias; p.bias_per_row = bias_per_row ? 1 : 0; p.alpha = alpha;
+  p.bias = bias; p.bias_per_row = bias_per_row ? 1 : 0; p.alpha = alpha; p.row_scale = row_scale;
   p.tw_log2 = 7; p.TW = 128; p.TH = 1; p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
   if (impl == HDRVAE_CONV_DIRECT) return launch_gemm_direct(p, s);
   return launch_gemm_tc(p, ctx->num_sms, s);
@@ -222,9 +264,8 @@ static int run_gemm(hdrvae_ctx* ctx, const __nv_bfloat16* A, long long lda, int 
 
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
-  int B, h, w, T, Tp, s_rows;
-  size_t off_lat, off_act[3], off_gn, off_qk, off_vt, off_o, off_s, off_p, off_epi, total;
-  size_t act_bytes;
+  int B, h, w, T, Tp, s_rows, gn_chunks;
+  size_t off_lat, off_x, off_h, off_t, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_epi, total;
 };
 static constexpr long long kScoreBudgetElems = 256ll << 20;   // fp32 score chunk <= 1 GiB
 
@@ -239,127 +280,164 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   const long long t128 = (pl.T + 127) / 128 * 128;
   if (rows > t128) rows = t128;
   pl.s_rows = (int)rows;
+  pl.gn_chunks = 1184;
+  if (!attn_only)
+    for (int l = 1; l <= 8; l *= 2) pl.gn_chunks = std::max(pl.gn_chunks, 4 * tiles_for(l * h, l * w));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t widest = attn_only ? 0 : (size_t)B * pl.T * 64 * 256;   // elements of [B, 8h, 8w, 256]
   pl.off_lat = take(attn_only ? 0 : (size_t)B * pl.T * 64 * 2);
-  pl.act_bytes = attn_only ? 0 : (size_t)B * pl.T * 64 * 256 * 2;   // [B, 8h, 8w, 256] bf16 = widest activation
-  for (int i = 0; i < 3; ++i) pl.off_act[i] = take(pl.act_bytes);
-  pl.off_gn = take(gn_scratch_bytes(B, 512));
+  pl.off_x = take(widest * 4);       // residual stream, fp32
+  pl.off_h = take(widest * 4);       // conv1 / shortcut / upsample outputs, fp32
+  pl.off_t = take(widest * 2);       // GroupNorm outputs: 16-bit tensor-core operands
+  pl.off_gn = take(attn_only ? 0 : gn_scratch_bytes(B, 512, pl.gn_chunks));
   pl.off_qk = take((size_t)B * pl.Tp * 1024 * 2);
   pl.off_vt = take((size_t)B * 512 * pl.Tp * 2);
   pl.off_o = take((size_t)B * pl.T * 512 * 2);
   pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
   pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
+  pl.off_inv = take((size_t)pl.s_rows * 4);
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
   pl.total = off;
   return pl;
 }
 
 // ---- decoder layer program ------------------------------------------------------------------------
-struct Bufs {
-  __nv_bfloat16* x;   // residual stream
-  __nv_bfloat16* t;   // normalised / activated operand
-  __nv_bfloat16* hbuf;   // block-internal
+struct DecState {
+  float* x;        // residual stream (fp32)
+  float* hbuf;     // block-internal fp32 tensor
+  void* t;         // 16-bit operand buffer
+  void* gn;        // GroupNorm scratch (partials | scale | shift)
+  int gn_chunks;   // capacity of the partial area (chunks per image)
+  int pending;     // partial chunks per image currently valid for the tensor about to be normalised
 };
 
-static int run_gn(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, const NormW& nw, bool silu, void* scratch,
-                  cudaStream_t s) {
+static int run_gn(hdrvae_ctx* ctx, const void* x, int x_dtype, void* y, int B, int HW, const NormW& nw, bool silu,
+                  DecState* st, cudaStream_t s) {
   char pname[64];
   snprintf(pname, sizeof pname, "groupnorm%s C=%d @%dx%d", silu ? "+silu" : "", nw.C, B, HW);
-  ProfScope prof(pname, 0.0, (double)B * HW * nw.C * 6.0, s);
-  return launch_groupnorm(x, y, B, HW, nw.C, nw.gamma, nw.beta, silu, scratch, s);
+  ProfScope prof(pname, 0.0, (double)B * HW * nw.C * (dt_bytes(x_dtype) * (st->pending > 0 ? 1 : 2) + 2.0), s);
+  const int partials = st->pending;
+  st->pending = 0;
+  return launch_groupnorm(x, x_dtype, y, ctx->op_dtype, B, HW, nw.C, nw.gamma, nw.beta, silu, st->gn, st->gn_chunks,
+                          partials, s);
 }
 
-static int run_res(hdrvae_ctx* ctx, const ResW& rw, Bufs* bf, int B, int H, int W, void* gn_scratch, cudaStream_t s) {
+static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
+  return ctx->conv_impl == HDRVAE_CONV_TCGEN05 ? reinterpret_cast<float*>(st->gn) : nullptr;
+}
+
+static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, int W, cudaStream_t s) {
   const int impl = ctx->conv_impl;
-  HDRVAE_TRY(run_gn(bf->x, bf->t, B, H * W, rw.n1, true, gn_scratch, s));
-  HDRVAE_TRY(run_conv(ctx, rw.c1, bf->t, B, H, W, bf->hbuf, false, nullptr, impl, s));
-  HDRVAE_TRY(run_gn(bf->hbuf, bf->t, B, H * W, rw.n2, true, gn_scratch, s));
+  HDRVAE_TRY(run_gn(ctx, st->x, DT_F32, st->t, B, H * W, rw.n1, true, st, s));
+  {
+    ConvIO io; io.x = st->t; io.y = st->hbuf; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+    HDRVAE_TRY(run_conv(ctx, rw.c1, io, B, H, W, impl, s));
+  }
+  HDRVAE_TRY(run_gn(ctx, st->hbuf, DT_F32, st->t, B, H * W, rw.n2, true, st, s));
+  ConvIO io; io.x = st->t; io.round_tf32 = rw.round_out; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
   if (rw.has_nin) {
-    // shortcut into hbuf (free after norm2), then conv2 accumulates onto it in place
-    HDRVAE_TRY(run_conv(ctx, rw.nin, bf->x, B, H, W, bf->hbuf, false, nullptr, impl, s));
-    HDRVAE_TRY(run_conv(ctx, rw.c2, bf->t, B, H, W, bf->hbuf, false, bf->hbuf, impl, s));
-    std::swap(bf->x, bf->hbuf);
+    // shortcut (tf32 on the raw stream) into hbuf (free after norm2), then conv2 accumulates onto it in place
+    ConvIO sc; sc.x = st->x; sc.y = st->hbuf;
+    HDRVAE_TRY(run_conv(ctx, rw.nin, sc, B, H, W, impl, s));
+    io.y = st->hbuf; io.residual = st->hbuf;
+    HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
+    std::swap(st->x, st->hbuf);
   } else {
-    HDRVAE_TRY(run_conv(ctx, rw.c2, bf->t, B, H, W, bf->x, false, bf->x, impl, s));   // x += conv2(t), in place
+    io.y = st->x; io.residual = st->x;                  // x += conv2(t), in place
+    HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
   }
   return 0;
 }
 
-static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const __nv_bfloat16* qk /*[B][Tp][1024]*/,
-                              const __nv_bfloat16* vt /*[B][512][Tp]*/, __nv_bfloat16* o /*[B][T][512]*/,
-                              float qk_alpha, cudaStream_t s) {
-  const int impl = ctx->conv_impl;
+static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const void* qk /*[B][Tp][1024]*/,
+                              const void* vt /*[B][512][Tp]*/, void* o /*[B][T][512]*/, float qk_alpha,
+                              cudaStream_t s) {
+  const int impl = ctx->conv_impl, dt = ctx->op_dtype;
   float* S = reinterpret_cast<float*>(ws + pl.off_s);
-  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_p);
+  uint16_t* P = reinterpret_cast<uint16_t*>(ws + pl.off_p);
+  float* inv = reinterpret_cast<float*>(ws + pl.off_inv);
   for (int b = 0; b < pl.B; ++b) {
-    const __nv_bfloat16* q = qk + (size_t)b * pl.Tp * 1024;
-    const __nv_bfloat16* k = q + 512;
-    const __nv_bfloat16* v = vt + (size_t)b * 512 * pl.Tp;
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(qk) + (size_t)b * pl.Tp * 1024;
+    const uint16_t* k = q + 512;
+    const uint16_t* v = reinterpret_cast<const uint16_t*>(vt) + (size_t)b * 512 * pl.Tp;
     for (int r0 = 0; r0 < pl.T; r0 += pl.s_rows) {
       const int rows = std::min(pl.s_rows, pl.T - r0);
       // S = alpha q k^T, fp32 (the decoder folds 1/sqrt(d) into the q weights: alpha = 1); padded key
       // columns give 0 and are masked by the softmax
-      HDRVAE_TRY(run_gemm(ctx, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, pl.Tp, pl.Tp, S, pl.Tp, true, nullptr,
-                          false, qk_alpha, impl, s));
-      HDRVAE_TRY(launch_softmax_rows(S, P, rows, pl.T, pl.Tp, pl.Tp, pl.Tp, s));
-      HDRVAE_TRY(run_gemm(ctx, P, pl.Tp, rows, pl.Tp, v, pl.Tp, 512, 512, o + ((size_t)b * pl.T + r0) * 512, 512, false,
-                          nullptr, false, 1.0f, impl, s));
+      HDRVAE_TRY(run_gemm(ctx, dt, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, pl.Tp, pl.Tp, S, pl.Tp, DT_F32,
+                          nullptr, false, qk_alpha, nullptr, impl, s));
+      // P = exp(S - rowmax) (16-bit), inv = 1 / rowsum; O = inv * (P V)
+      HDRVAE_TRY(launch_softmax_rows(S, P, dt, inv, rows, pl.T, pl.Tp, pl.Tp, pl.Tp, s));
+      HDRVAE_TRY(run_gemm(ctx, dt, P, pl.Tp, rows, pl.Tp, v, pl.Tp, 512, 512,
+                          reinterpret_cast<uint16_t*>(o) + ((size_t)b * pl.T + r0) * 512, 512, dt, nullptr, false, 1.0f,
+                          inv, impl, s));
     }
   }
   return 0;
 }
 
-static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uint8_t* ws, __nv_bfloat16** features,
+static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uint8_t* ws, void** features,
                        cudaStream_t s) {
   HDRVAE_REQUIRE(ctx->loaded, "hdrvae: weights not loaded");
-  const int B = pl.B, impl = ctx->conv_impl;
+  const int B = pl.B, impl = ctx->conv_impl, dt = ctx->op_dtype;
   int H = pl.h, W = pl.w;
-  __nv_bfloat16* lat = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_lat);
-  Bufs bf;
-  bf.x = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_act[0]);
-  bf.t = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_act[1]);
-  bf.hbuf = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_act[2]);
-  void* gns = ws + pl.off_gn;
+  void* lat = ws + pl.off_lat;
+  DecState st;
+  st.x = reinterpret_cast<float*>(ws + pl.off_x);
+  st.hbuf = reinterpret_cast<float*>(ws + pl.off_h);
+  st.t = ws + pl.off_t;
+  st.gn = ws + pl.off_gn;
+  st.gn_chunks = pl.gn_chunks;
+  st.pending = 0;
 
-  HDRVAE_TRY(launch_latent_to_nhwc(latent, lat, B, 16, H * W, 64, s));
-  HDRVAE_TRY(run_conv(ctx, ctx->conv_in, lat, B, H, W, bf.x, false, nullptr, impl, s));
-  HDRVAE_TRY(run_res(ctx, ctx->mid1, &bf, B, H, W, gns, s));
+  HDRVAE_TRY(launch_latent_to_nhwc(latent, lat, dt, B, 16, H * W, 64, s));
+  {
+    ConvIO io; io.x = lat; io.y = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
+    HDRVAE_TRY(run_conv(ctx, ctx->conv_in, io, B, H, W, impl, s));
+  }
+  HDRVAE_TRY(run_res(ctx, ctx->mid1, &st, B, H, W, s));
   {
     // mid.attn_1: x += proj_out(softmax(q k^T / sqrt(c)) v), q,k,v = 1x1 convs of GroupNorm(x) (no SiLU)
-    __nv_bfloat16* qk = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qk);
-    __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_vt);
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_o);
-    HDRVAE_TRY(run_gn(bf.x, bf.t, B, H * W, ctx->attn_norm, false, gns, s));
+    void* qk = ws + pl.off_qk;
+    void* vt = ws + pl.off_vt;
+    void* o = ws + pl.off_o;
+    HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->attn_norm, false, &st, s));
     if (pl.Tp != pl.T) HDRVAE_CUDA_OK(cudaMemsetAsync(qk, 0, (size_t)B * pl.Tp * 1024 * 2, s));
-    ProfScope* pq = new ProfScope("attention q|k and v^T projections", 2.0 * B * (double)pl.T * 512 * 1536, 0.0, s);
-    for (int b = 0; b < B; ++b) {
-      const __nv_bfloat16* tb = bf.t + (size_t)b * pl.T * 512;
-      // [q*scale | k] = t Wqk^T + bqk : [T][1024]
-      HDRVAE_TRY(run_gemm(ctx, tb, 512, pl.T, 512, ctx->qk.w[0], 512, 1024, 1024, qk + (size_t)b * pl.Tp * 1024, 1024,
-                          false, ctx->qk.bias, false, 1.0f, impl, s));
-      // v^T = Wv t^T + bv : [512][Tp]  (operand roles swapped so PV sees a K-major B operand)
-      HDRVAE_TRY(run_gemm(ctx, ctx->vproj.w[0], 512, 512, 512, tb, 512, pl.T, pl.Tp, vt + (size_t)b * 512 * pl.Tp,
-                          pl.Tp, false, ctx->vproj.bias, true, 1.0f, impl, s));
-    }
-    delete pq;
     {
-      ProfScope prof("attention core (QK^T, softmax, PV)", 4.0 * B * (double)pl.T * pl.T * 512, 12.0 * B * (double)pl.T * pl.Tp, s);
+      ProfScope pq("attention q|k and v^T projections", 2.0 * B * (double)pl.T * 512 * 1536, 0.0, s);
+      for (int b = 0; b < B; ++b) {
+        const uint16_t* tb = reinterpret_cast<const uint16_t*>(st.t) + (size_t)b * pl.T * 512;
+        // [q*scale | k] = t Wqk^T + bqk : [T][1024]
+        HDRVAE_TRY(run_gemm(ctx, dt, tb, 512, pl.T, 512, ctx->qk.w[0], 512, 1024, 1024,
+                            reinterpret_cast<uint16_t*>(qk) + (size_t)b * pl.Tp * 1024, 1024, dt, ctx->qk.bias, false, 1.0f,
+                            nullptr, impl, s));
+        // v^T = Wv t^T + bv : [512][Tp]  (operand roles swapped so PV sees a K-major B operand)
+        HDRVAE_TRY(run_gemm(ctx, dt, ctx->vproj.w[0], 512, 512, 512, tb, 512, pl.T, pl.Tp,
+                            reinterpret_cast<uint16_t*>(vt) + (size_t)b * 512 * pl.Tp, pl.Tp, dt, ctx->vproj.bias, true, 1.0f,
+                            nullptr, impl, s));
+      }
+    }
+    {
+      ProfScope prof("attention core (QK^T, softmax, PV)", 4.0 * B * (double)pl.T * pl.T * 512, 10.0 * B * (double)pl.T * pl.Tp, s);
       HDRVAE_TRY(run_attention_core(ctx, pl, ws, qk, vt, o, 1.0f, s));
     }
-    HDRVAE_TRY(run_conv(ctx, ctx->proj_out, o, B, H, W, bf.x, false, bf.x, impl, s));
+    ConvIO io; io.x = o; io.y = st.x; io.residual = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
+    HDRVAE_TRY(run_conv(ctx, ctx->proj_out, io, B, H, W, impl, s));
   }
-  HDRVAE_TRY(run_res(ctx, ctx->mid2, &bf, B, H, W, gns, s));
+  HDRVAE_TRY(run_res(ctx, ctx->mid2, &st, B, H, W, s));
   for (int lvl = 3; lvl >= 0; --lvl) {
-    for (int i = 0; i < 3; ++i) HDRVAE_TRY(run_res(ctx, ctx->up[lvl][i], &bf, B, H, W, gns, s));
+    for (int i = 0; i < 3; ++i) HDRVAE_TRY(run_res(ctx, ctx->up[lvl][i], &st, B, H, W, s));
     if (lvl != 0) {
-      HDRVAE_TRY(run_conv(ctx, ctx->upsample[lvl], bf.x, B, H, W, bf.hbuf, false, nullptr, impl, s));
-      std::swap(bf.x, bf.hbuf);
+      ConvIO io; io.x = st.x; io.y = st.hbuf; io.round_tf32 = (lvl <= 2);   // feeds a nin_shortcut (tf32) one block later
+      io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
+      HDRVAE_TRY(run_conv(ctx, ctx->upsample[lvl], io, B, H, W, impl, s));
+      std::swap(st.x, st.hbuf);
       H *= 2; W *= 2;
     }
   }
-  HDRVAE_TRY(run_gn(bf.x, bf.t, B, H * W, ctx->norm_out, true, gns, s));
-  *features = bf.t;
+  HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->norm_out, true, &st, s));
+  *features = st.t;
   return 0;
 }
 
@@ -441,11 +519,16 @@ int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl) {
   return 0;
 }
 
+int hdrvae_operand_dtype(hdrvae_ctx* ctx) { return ctx ? ctx->op_dtype : -1; }
+
 int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n, int precision) {
   HDRVAE_REQUIRE(ctx != nullptr && descs != nullptr, "hdrvae_load_weights: null argument");
-  HDRVAE_REQUIRE(precision == HDRVAE_PRECISION_BF16, "hdrvae_load_weights: unsupported precision %d", precision);
+  HDRVAE_REQUIRE(precision == HDRVAE_PRECISION_BF16 || precision == HDRVAE_PRECISION_F16,
+                 "hdrvae_load_weights: unsupported precision %d", precision);
   HDRVAE_REQUIRE(!ctx->loaded, "hdrvae_load_weights: context already holds weights (create a new one)");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  ctx->op_dtype = precision == HDRVAE_PRECISION_BF16 ? DT_BF16 : DT_F16;
+  const int op = ctx->op_dtype;
   cudaStream_t s = nullptr;
   std::vector<void*> staging;
   for (int i = 0; i < n; ++i) {
@@ -474,9 +557,9 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
                    "%s.weight has the wrong shape (want [%d,%d,%d,%d])", k.c_str(), cout, cin, ks, ks);
     return 0;
   };
-  auto conv = [&](const std::string& k, int cout, int cin, int ks, bool up, float scale, PackedConv* pc) -> int {
+  auto conv = [&](const std::string& k, int cout, int cin, int ks, bool up, int w_dtype, PackedConv* pc) -> int {
     HDRVAE_TRY(need_conv(k, cout, cin, ks));
-    return pack_conv(ctx, W(k + ".weight"), W(k + ".bias"), cout, cin, ks, up, scale, pc, s);
+    return pack_conv(ctx, W(k + ".weight"), W(k + ".bias"), cout, cin, ks, up, 1.f, w_dtype, pc, s);
   };
   auto norm = [&](const std::string& k, int C, NormW* nw) -> int {
     HDRVAE_REQUIRE(W(k + ".weight") && W(k + ".bias") && ctx->shapes[k + ".weight"].size() == 1 &&
@@ -486,15 +569,15 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
   };
   auto res = [&](const std::string& k, int cin, int cout, ResW* rw) -> int {
     HDRVAE_TRY(norm(k + ".norm1", cin, &rw->n1));
-    HDRVAE_TRY(conv(k + ".conv1", cout, cin, 3, false, 1.f, &rw->c1));
+    HDRVAE_TRY(conv(k + ".conv1", cout, cin, 3, false, op, &rw->c1));
     HDRVAE_TRY(norm(k + ".norm2", cout, &rw->n2));
-    HDRVAE_TRY(conv(k + ".conv2", cout, cout, 3, false, 1.f, &rw->c2));
+    HDRVAE_TRY(conv(k + ".conv2", cout, cout, 3, false, op, &rw->c2));
     rw->has_nin = cin != cout;
-    if (rw->has_nin) HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, 1.f, &rw->nin));
+    if (rw->has_nin) HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, DT_F32, &rw->nin));   // raw stream: tf32
     return 0;
   };
 
-  HDRVAE_TRY(conv("conv_in", 512, 16, 3, false, 1.f, &ctx->conv_in));
+  HDRVAE_TRY(conv("conv_in", 512, 16, 3, false, op, &ctx->conv_in));
   HDRVAE_TRY(res("mid.block_1", 512, 512, &ctx->mid1));
   HDRVAE_TRY(res("mid.block_2", 512, 512, &ctx->mid2));
   HDRVAE_TRY(norm("mid.attn_1.norm", 512, &ctx->attn_norm));
@@ -504,13 +587,13 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
     HDRVAE_TRY(need_conv("mid.attn_1.k", 512, 512, 1));
     const float scale = 1.0f / sqrtf(512.0f);
     PackedConv& qk = ctx->qk;
-    qk.cin = qk.cin_pad = 512; qk.cout = 1024; qk.ks = 1;
-    HDRVAE_TRY(dev_alloc(ctx, (size_t)1024 * 512 * 2, (void**)&qk.w[0]));
+    qk.cin = qk.cin_pad = 512; qk.cout = 1024; qk.ks = 1; qk.w_dtype = op;
+    HDRVAE_TRY(dev_alloc(ctx, (size_t)1024 * 512 * 2, &qk.w[0]));
     HDRVAE_TRY(dev_alloc(ctx, 1024 * sizeof(float), (void**)&qk.bias));
     int mask1[1] = {1};
-    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.q.weight"), qk.w[0], 512, 512, 1, 1, 512, mask1, scale, s));
-    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.k.weight"), qk.w[0] + 512 * 512, 512, 512, 1, 1, 512, mask1, 1.f, s));
-    // bias: q part scaled
+    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.q.weight"), qk.w[0], op, 512, 512, 1, 1, 512, mask1, scale, s));
+    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.k.weight"), reinterpret_cast<uint16_t*>(qk.w[0]) + 512 * 512, op, 512, 512, 1,
+                                  1, 512, mask1, 1.f, s));
     std::vector<float> hb(1024);
     HDRVAE_CUDA_OK(cudaMemcpyAsync(hb.data(), W("mid.attn_1.q.bias"), 512 * 4, cudaMemcpyDeviceToHost, s));
     HDRVAE_CUDA_OK(cudaMemcpyAsync(hb.data() + 512, W("mid.attn_1.k.bias"), 512 * 4, cudaMemcpyDeviceToHost, s));
@@ -518,8 +601,8 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
     for (int i = 0; i < 512; ++i) hb[i] *= scale;
     HDRVAE_CUDA_OK(cudaMemcpy(qk.bias, hb.data(), 1024 * 4, cudaMemcpyHostToDevice));
   }
-  HDRVAE_TRY(conv("mid.attn_1.v", 512, 512, 1, false, 1.f, &ctx->vproj));
-  HDRVAE_TRY(conv("mid.attn_1.proj_out", 512, 512, 1, false, 1.f, &ctx->proj_out));
+  HDRVAE_TRY(conv("mid.attn_1.v", 512, 512, 1, false, op, &ctx->vproj));
+  HDRVAE_TRY(conv("mid.attn_1.proj_out", 512, 512, 1, false, op, &ctx->proj_out));
   const int ch[4] = {128, 256, 512, 512};
   int cin = 512;
   for (int lvl = 3; lvl >= 0; --lvl) {
@@ -527,7 +610,10 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
       HDRVAE_TRY(res("up." + std::to_string(lvl) + ".block." + std::to_string(i), cin, ch[lvl], &ctx->up[lvl][i]));
       cin = ch[lvl];
     }
-    if (lvl != 0) HDRVAE_TRY(conv("up." + std::to_string(lvl) + ".upsample.conv", cin, cin, 3, true, 1.f, &ctx->upsample[lvl]));
+    if (lvl != 0) {
+      ctx->up[lvl][2].round_out = true;     // its output is the upsample conv's tf32 operand
+      HDRVAE_TRY(conv("up." + std::to_string(lvl) + ".upsample.conv", cin, cin, 3, true, DT_F32, &ctx->upsample[lvl]));
+    }
   }
   HDRVAE_TRY(norm("norm_out", 128, &ctx->norm_out));
   HDRVAE_TRY(need_conv("conv_out", 3, 128, 3));
@@ -555,11 +641,11 @@ int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int 
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* feat = nullptr;
+  void* feat = nullptr;
   HDRVAE_TRY(run_decoder(ctx, latent, pl, ws, &feat, s));
   {
     ProfScope prof("epilogue phase A (conv_out, max-pool, stats)", 2.0 * B * 64.0 * h * w * 3 * 1152, B * 64.0 * h * w * (256 + 24), s);
-    HDRVAE_TRY(launch_epilogue_phase_a(feat, HDRVAE_BF16, B, 8 * h, 8 * w, ctx->conv_out_w, ctx->conv_out_b, nullptr,
+    HDRVAE_TRY(launch_epilogue_phase_a(feat, ctx->op_dtype, B, 8 * h, 8 * w, ctx->conv_out_w, ctx->conv_out_b, nullptr,
                                        ws + pl.off_epi, s));
   }
   if (raw_stats_dev != nullptr) *raw_stats_dev = epilogue_raw_stats_ptr(ws + pl.off_epi, B, 8 * h, 8 * w);
@@ -594,7 +680,7 @@ int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent, int B, int h, i
   const Plan pl = make_plan(B, h, w);
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  __nv_bfloat16* feat = nullptr;
+  void* feat = nullptr;
   HDRVAE_TRY(run_decoder(ctx, latent, pl, reinterpret_cast<uint8_t*>(workspace), &feat, s));
   HDRVAE_CUDA_OK(cudaMemcpyAsync(features, feat, (size_t)B * 64 * h * w * 128 * 2, cudaMemcpyDeviceToDevice, s));
   return 0;
@@ -624,60 +710,80 @@ int hdrvae_epilogue(hdrvae_ctx* ctx, const void* pre, int dtype, int B, int H, i
 }
 
 // ---- kernel-level entry points -------------------------------------------------------------------
-int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int B, int H, int W, int Cin, const float* w, const float* bias,
-                  int Cout, int ksize, int upsample2x, const void* residual, void* y, int out_f32, int impl,
-                  void* stream) {
+int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, int H, int W, int Cin, const float* w,
+                  const float* bias, int Cout, int ksize, int upsample2x, const void* residual, int res_dtype, void* y,
+                  int y_dtype, int round_tf32, float* gn_partials, int* gn_chunks, int impl, void* stream) {
   HDRVAE_REQUIRE(ctx && x && w && y, "hdrvae_conv2d: null argument");
   HDRVAE_REQUIRE(Cin % 64 == 0, "hdrvae_conv2d: Cin must be a multiple of 64 (pad the activation channels)");
   HDRVAE_REQUIRE(Cout % 32 == 0 && (ksize == 1 || ksize == 3), "hdrvae_conv2d: Cout %% 32 == 0 and ksize in {1,3}");
+  HDRVAE_REQUIRE(x_dtype >= 0 && x_dtype <= 2 && y_dtype >= 0 && y_dtype <= 2 && res_dtype >= 0 && res_dtype <= 2,
+                 "hdrvae_conv2d: bad dtype");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   hdrvae_ctx tmp;                     // owns the temporary packed operands
   tmp.device = ctx->device; tmp.num_sms = ctx->num_sms;
   PackedConv pc;
-  int r = pack_conv(&tmp, w, bias, Cout, Cin, ksize, upsample2x != 0, 1.f, &pc, s);
-  if (r == 0) r = run_conv(&tmp, pc, reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, y, out_f32 != 0,
-                           reinterpret_cast<const __nv_bfloat16*>(residual), impl, s);
+  int r = pack_conv(&tmp, w, bias, Cout, Cin, ksize, upsample2x != 0, 1.f, x_dtype, &pc, s);
+  if (r == 0) {
+    ConvIO io; io.x = x; io.y = y; io.y_dtype = y_dtype; io.residual = residual; io.res_dtype = res_dtype;
+    io.round_tf32 = round_tf32 != 0; io.stats = gn_partials; io.stats_chunks = gn_chunks;
+    r = run_conv(&tmp, pc, io, B, H, W, impl, s);
+  }
   cudaStreamSynchronize(s);
   for (void* p : tmp.owned) cudaFree(p);
   if (r == 0) HDRVAE_CUDA_OK(cudaGetLastError());
   return r;
 }
 
-int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int B, int HW, int C, const float* gamma, const float* beta,
-                          int apply_silu, void* y, void* stream) {
+int hdrvae_conv2d_stats_chunks(int H, int W, int upsample2x) { return (upsample2x ? 4 : 1) * tiles_for(H, W); }
+
+int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, int HW, int C, const float* gamma,
+                          const float* beta, int apply_silu, void* y, int y_dtype, const float* gn_partials,
+                          int gn_chunks, void* stream) {
   HDRVAE_REQUIRE(ctx && x && gamma && beta && y, "hdrvae_groupnorm_silu: null argument");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int max_chunks = std::max(1184, gn_chunks);
   void* scratch = nullptr;
-  HDRVAE_CUDA_OK(cudaMalloc(&scratch, gn_scratch_bytes(B, C)));
-  int r = launch_groupnorm(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, HW, C,
-                           gamma, beta, apply_silu != 0, scratch, s);
+  HDRVAE_CUDA_OK(cudaMalloc(&scratch, gn_scratch_bytes(B, C, max_chunks)));
+  int r = 0;
+  if (gn_partials != nullptr && gn_chunks > 0)
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(scratch, gn_partials, (size_t)B * gn_chunks * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  r = launch_groupnorm(x, x_dtype, y, y_dtype, B, HW, C, gamma, beta, apply_silu != 0, scratch, max_chunks,
+                       gn_partials != nullptr ? gn_chunks : 0, s);
   cudaStreamSynchronize(s);
   cudaFree(scratch);
   return r;
 }
 
-int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int B, int T, void* o, void* stream) {
+int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int dtype, int B, int T, void* o,
+                     void* stream) {
   HDRVAE_REQUIRE(ctx && q && k && v && o && B >= 1 && T >= 1, "hdrvae_attention: bad argument");
+  HDRVAE_REQUIRE(dtype == HDRVAE_BF16 || dtype == HDRVAE_F16, "hdrvae_attention: q/k/v must be bf16 or fp16");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   Plan pl = make_plan(B, 1, T, true);
   uint8_t* ws = nullptr;
   HDRVAE_CUDA_OK(cudaMalloc((void**)&ws, pl.total));
-  __nv_bfloat16* qk = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_qk);
-  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_vt);
+  uint16_t* qk = reinterpret_cast<uint16_t*>(ws + pl.off_qk);
+  uint16_t* vt = reinterpret_cast<uint16_t*>(ws + pl.off_vt);
   int r = 0;
   const float scale = 1.0f / sqrtf(512.0f);
   cudaMemsetAsync(qk, 0, (size_t)B * pl.Tp * 1024 * 2, s);
   cudaMemsetAsync(vt, 0, (size_t)B * 512 * pl.Tp * 2, s);
+  const uint16_t* q16 = reinterpret_cast<const uint16_t*>(q);
+  const uint16_t* k16 = reinterpret_cast<const uint16_t*>(k);
+  const uint16_t* v16 = reinterpret_cast<const uint16_t*>(v);
   for (int b = 0; b < B && r == 0; ++b) {
-    // interleave q (scaled in fp32 -> bf16) and k rows into the [Tp][1024] operand, transpose v
-    r = launch_transpose_pad(reinterpret_cast<const __nv_bfloat16*>(v) + (size_t)b * T * 512, vt + (size_t)b * 512 * pl.Tp, T, 512, pl.Tp, s);
-    if (r == 0) HDRVAE_CUDA_OK(cudaMemcpy2DAsync(qk + (size_t)b * pl.Tp * 1024, 2048, reinterpret_cast<const __nv_bfloat16*>(q) + (size_t)b * T * 512, 1024, 1024, T, cudaMemcpyDeviceToDevice, s));
-    if (r == 0) HDRVAE_CUDA_OK(cudaMemcpy2DAsync(qk + (size_t)b * pl.Tp * 1024 + 512, 2048, reinterpret_cast<const __nv_bfloat16*>(k) + (size_t)b * T * 512, 1024, 1024, T, cudaMemcpyDeviceToDevice, s));
+    // interleave q and k rows into the [Tp][1024] operand, transpose v
+    r = launch_transpose_pad(v16 + (size_t)b * T * 512, vt + (size_t)b * 512 * pl.Tp, T, 512, pl.Tp, s);
+    if (r == 0) HDRVAE_CUDA_OK(cudaMemcpy2DAsync(qk + (size_t)b * pl.Tp * 1024, 2048, q16 + (size_t)b * T * 512, 1024, 1024, T, cudaMemcpyDeviceToDevice, s));
+    if (r == 0) HDRVAE_CUDA_OK(cudaMemcpy2DAsync(qk + (size_t)b * pl.Tp * 1024 + 512, 2048, k16 + (size_t)b * T * 512, 1024, 1024, T, cudaMemcpyDeviceToDevice, s));
   }
-  if (r == 0) r = run_attention_core(ctx, pl, ws, qk, vt, reinterpret_cast<__nv_bfloat16*>(o), scale, s);
+  const int saved = ctx->op_dtype;
+  ctx->op_dtype = dtype;
+  if (r == 0) r = run_attention_core(ctx, pl, ws, qk, vt, o, scale, s);
+  ctx->op_dtype = saved;
   cudaStreamSynchronize(s);
   cudaFree(ws);
   return r;

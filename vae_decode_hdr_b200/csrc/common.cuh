@@ -42,20 +42,27 @@ inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ----------------------------------------------------------------- GEMM / conv descriptor
-// out[n, y*sy+py, x*sx+px, col] = bias[col] + sum_{t<ntaps} sum_{c<K_per_tap}
-//        A[n, y+dy[t], x+dx[t], c] * Bw[col][t*K_per_tap + c]      (+ residual[...])
+// element type codes = the ABI codes of include/hdrvae.h
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+__host__ __device__ inline int dt_bytes(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// out[n, y*sy+py, x*sx+px, col] = row_scale[x] * alpha * sum_{t<ntaps} sum_{c<K_per_tap}
+//        A[n, y+dy[t], x+dx[t], c] * Bw[col][t*K_per_tap + c]  + bias[col]  (+ residual[...])
 // A is addressed as a 4-D NHWC tensor (plain matrices use H = N = 1, W = rows).
+// Operand type ab_dtype: DT_F16 / DT_BF16 -> tcgen05 kind::f16, DT_F32 -> kind::tf32 (the tensor core
+// reads the top 19 bits of each fp32).
 struct GemmParams {
   // A operand (activations): element strides, used by the direct kernel; the tcgen05 kernel
   // reads A through a TMA tensor map built from the same numbers.
-  const __nv_bfloat16* a;
+  const void* a;
   long long a_img_stride, a_row_stride, a_px_stride;
-  // B operand (weights / keys), [cols][ktot] K-major bf16
-  const __nv_bfloat16* b;
+  // B operand (weights / keys), [cols][ktot] K-major, same element type as A
+  const void* b;
   long long b_row_stride;
   int b_rows;       // rows of B that exist in memory (0: same as n_cols); rows beyond are zero-filled by TMA
+  int ab_dtype;
   int n_img, H, W;  // source grid of the M dimension
-  int k_per_tap;    // multiple of 64
+  int k_per_tap;    // elements; multiple of one 128-byte row (64 for 16-bit operands, 32 for tf32)
   int ntaps;
   int tap_dy[9], tap_dx[9];
   int n_cols;       // valid output columns (Cout)
@@ -63,13 +70,20 @@ struct GemmParams {
   int tw_log2, TW, TH, tiles_x, tiles_y, n_tiles_n;
   // output
   void* out;
-  int out_f32;
+  int out_dtype;
   long long out_img_stride, out_row_stride, out_px_stride;  // elements
   int sy, sx, py, px;
   const float* bias;
   int bias_per_row;  // bias indexed by the M row (x coordinate) instead of the column
-  const __nv_bfloat16* residual;  // same addressing as out, or null
+  const void* residual;  // same addressing as out, or null
+  int res_dtype;
+  const float* row_scale;  // per M row (x coordinate) multiplier of the accumulator, or null
   float alpha;       // accumulator scale applied before bias (1.0 for convs)
+  int round_tf32;    // round fp32 outputs to tf32 (RN) so a following kind::tf32 MMA reads them exactly
+  // GroupNorm statistics of the output, emitted per (image, m-tile) as (sum, sum of squares) of each of the
+  // 32 channel groups: stats[((img * tiles_per_img + m_tile) * 32 + group) * 2 + {0,1}], or null
+  float* stats;
+  int stats_chunks_per_img, stats_chunk0;
 };
 
 struct TensorMapPair {

@@ -61,6 +61,15 @@ template <> struct Load4<__nv_bfloat16> {
   }
 };
 
+template <> struct Load4<__half> {
+  static __device__ __forceinline__ float4 ld(const __half* p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
 __device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(~0u, v, o)); return v; }
 __device__ __forceinline__ float warp_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(~0u, v, o)); return v; }
 __device__ __forceinline__ double warp_sum(double v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(~0u, v, o); return v; }
@@ -435,6 +444,11 @@ int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, con
     if (!set) { HDRVAE_CUDA_OK(cudaFuncSetAttribute(hdr_phase_a_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
     hdr_phase_a_kernel<__nv_bfloat16><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(pre), conv_w,
                                                                          conv_b, H, W, e.post3, e.pre3, argmax3, e.pa);
+  } else if (dtype == HDRVAE_F16) {
+    static bool set = false;
+    if (!set) { HDRVAE_CUDA_OK(cudaFuncSetAttribute(hdr_phase_a_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    hdr_phase_a_kernel<__half><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const __half*>(pre), conv_w, conv_b, H, W,
+                                                                e.post3, e.pre3, argmax3, e.pa);
   } else {
     HDRVAE_REQUIRE(false, "epilogue: unsupported activation dtype %d", dtype);
   }

@@ -1,14 +1,16 @@
-// GroupNorm(32 groups, eps 1e-6, affine) + SiLU on NHWC bf16 — HBM-streaming kernels.
+// GroupNorm(32 groups, eps 1e-6, affine) + SiLU on NHWC activations — HBM-streaming kernels.
 // Replaces norm1/norm2/norm_out + swish of ComfyUI's Decoder (driven through vae.decode,
 // reference hdr_vae_decode.py:859,:1022).
 //
-//   gn_stats    : per (image, pixel chunk) partial (sum, sum of squares) of every group, fp32,
-//                 16-byte loads, smem reduction; partials are written (not atomically added) so the
-//                 final reduction order is fixed -> results do not depend on scheduling (and, under
-//                 row tiling, not on the number of GPUs once partials are all-reduced);
+//   statistics  : per (image, chunk) partial (sum, sum of squares) of every group in fp32.  In the decoder
+//                 they are emitted by the epilogue of the conv that produced the tensor (gemm_tc.cu), so the
+//                 tensor is not re-read; gn_stats_kernel is the standalone producer (test entry).  Partials are
+//                 written, never atomically added: the reduction order is fixed -> deterministic, and under
+//                 row tiling independent of the GPU count once the partials are all-reduced;
 //   gn_finalize : fixed-order double reduction of the partials -> per (image, channel) scale/shift;
-//   gn_apply    : y = silu(x * a[c] + b[c]), 16-byte loads/stores.
-// Algorithmic traffic: 2 B read (stats) + 2 B read + 2 B write (apply) per element.
+//   gn_apply    : y = silu(x * a[c] + b[c]); x fp32 (residual / conv stream) or 16-bit, y fp16/bf16 (the next
+//                 conv's tensor-core operand), 16-byte accesses.
+// Algorithmic traffic in the decoder: 4 B read + 2 B written per element.
 #include "common.cuh"
 
 namespace hdrvae {
@@ -16,28 +18,69 @@ namespace hdrvae {
 constexpr int kGroups = 32;
 constexpr int kGnThreads = 256;
 
+// 8 consecutive channels of one pixel as floats
+template <typename T> struct Ld8;
+template <> struct Ld8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Ld8<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  }
+};
+template <> struct Ld8<__half> {
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  }
+};
+template <typename T> struct St8;
+template <> struct St8<__nv_bfloat16> {
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 o; uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]); w[e] = *reinterpret_cast<uint32_t*>(&t); }
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+};
+template <> struct St8<__half> {
+  static __device__ __forceinline__ void st(__half* p, const float (&v)[8]) {
+    uint4 o; uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { __half2 t = __floats2half2_rn(v[2 * e], v[2 * e + 1]); w[e] = *reinterpret_cast<uint32_t*>(&t); }
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+};
+
+template <typename TIn>
 __global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int px_per_block) {
+gn_stats_kernel(const TIn* __restrict__ x, float* __restrict__ partial, int HW, int C, int px_per_block) {
   const int img = blockIdx.y;
   const int chunk = blockIdx.x;
-  const int vpp = C >> 3;                       // 16-byte vectors per pixel
+  const int vpp = C >> 3;                       // 8-channel vectors per pixel
   const int cpg = C / kGroups;
   const int vi = threadIdx.x % vpp;
   const int p_off = threadIdx.x / vpp;
   const int p_step = kGnThreads / vpp;
   const int p0 = chunk * px_per_block;
   const int p1 = min(HW, p0 + px_per_block);
-  const uint4* base = reinterpret_cast<const uint4*>(x + (long long)img * HW * C);
+  const TIn* base = x + (long long)img * HW * C;
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
   for (int p = p0 + p_off; p < p1; p += p_step) {
-    const uint4 v = __ldg(base + (long long)p * vpp + vi);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-    const float2 c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
-    s0 += (a.x + a.y) + (b.x + b.y);
-    q0 += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
-    s1 += (c.x + c.y) + (d.x + d.y);
-    q1 += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+    float v[8];
+    Ld8<TIn>::ld(base + ((long long)p * vpp + vi) * 8, v);
+    s0 += (v[0] + v[1]) + (v[2] + v[3]);
+    q0 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+    s1 += (v[4] + v[5]) + (v[6] + v[7]);
+    q1 += (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
   }
   // Fixed-order block reduction (no float atomics): every thread parks its 4 partials, then 64
   // threads (group, stat) each add the 16 entries that belong to their group in a fixed order.
@@ -49,7 +92,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial
   __syncthreads();
   if (threadIdx.x < kGroups * 2) {
     const int g = threadIdx.x >> 1, stat = threadIdx.x & 1;
-    const int halves_per_group = cpg >> 2;              // 4-channel halves of a 16-byte vector
+    const int halves_per_group = cpg >> 2;              // 4-channel halves of an 8-channel vector
     float t = 0.f;
     for (int hh = g * halves_per_group; hh < (g + 1) * halves_per_group; ++hh) {
       const int v = hh >> 1, half = hh & 1;
@@ -96,9 +139,9 @@ gn_finalize_kernel(const float* __restrict__ partial, int n_chunks, const float*
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
-template <bool kSilu>
+template <typename TIn, typename TOut, bool kSilu>
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, int HW, int C, int px_per_block) {
   extern __shared__ float tab[];   // [2][C]
   const int img = blockIdx.y;
@@ -116,64 +159,86 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = tab[vi * 8 + j]; b[j] = tab[C + vi * 8 + j]; }
-  const uint4* xin = reinterpret_cast<const uint4*>(x + (long long)img * HW * C);
-  uint4* yout = reinterpret_cast<uint4*>(y + (long long)img * HW * C);
+  const TIn* xin = x + (long long)img * HW * C;
+  TOut* yout = y + (long long)img * HW * C;
   for (int p = p0 + p_off; p < p1; p += p_step) {
-    const uint4 v = __ldg(xin + (long long)p * vpp + vi);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-    uint4 o;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    float v[8];
+    Ld8<TIn>::ld(xin + ((long long)p * vpp + vi) * 8, v);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __bfloat1622float2(h[e]);
-      float r0 = fmaf(f.x, a[2 * e], b[2 * e]);
-      float r1 = fmaf(f.y, a[2 * e + 1], b[2 * e + 1]);
-      if (kSilu) { r0 = silu_f(r0); r1 = silu_f(r1); }
-      __nv_bfloat162 pk = __floats2bfloat162_rn(r0, r1);
-      ow[e] = *reinterpret_cast<uint32_t*>(&pk);
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], a[j], b[j]);
+      if (kSilu) v[j] = silu_f(v[j]);
     }
-    yout[(long long)p * vpp + vi] = o;
+    St8<TOut>::st(yout + ((long long)p * vpp + vi) * 8, v);
   }
 }
 
-// scratch layout: [partials: B * chunks * 64 floats][scale: B*C][shift: B*C]
-size_t gn_scratch_bytes(int B, int C) {
-  return ((size_t)B * 4096 * kGroups * 2 + (size_t)2 * B * C) * sizeof(float);
+// scratch layout: [partials: B * max_chunks * 64 floats][scale: B*C][shift: B*C]
+size_t gn_scratch_bytes(int B, int C, int max_chunks) {
+  return ((size_t)B * max_chunks * kGroups * 2 + (size_t)2 * B * C) * sizeof(float);
 }
 
-static void gn_chunking(int B, int HW, int C, int* chunks, int* px_per_block) {
+static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* px_per_block) {
   const int px_per_iter = kGnThreads / (C >> 3);
   int want = (148 * 8 + B - 1) / B;                 // ~8 CTAs per SM over the whole batch
   int maxc = (HW + px_per_iter * 4 - 1) / (px_per_iter * 4);   // at least 4 iterations per thread
   if (maxc < 1) maxc = 1;
   int c = want < maxc ? want : maxc;
-  if (c > 4096) c = 4096;
+  if (c > max_chunks) c = max_chunks;
   int ppb = (HW + c - 1) / c;
   ppb = (ppb + px_per_iter - 1) / px_per_iter * px_per_iter;
   *px_per_block = ppb;
   *chunks = (HW + ppb - 1) / ppb;
 }
 
-int launch_groupnorm(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, const float* gamma,
-                     const float* beta, bool silu, void* scratch, cudaStream_t s) {
+template <typename TIn, typename TOut>
+static void launch_apply(const void* x, void* y, const float* scale, const float* shift, int B, int HW, int C, int chunks,
+                         int ppb, bool silu, cudaStream_t s) {
+  const dim3 grid(chunks, B);
+  const size_t sm = 2 * C * sizeof(float);
+  if (silu)
+    gn_apply_kernel<TIn, TOut, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
+                                                                  scale, shift, HW, C, ppb);
+  else
+    gn_apply_kernel<TIn, TOut, false><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
+                                                                   scale, shift, HW, C, ppb);
+}
+
+// partial_chunks > 0: the statistics partials [B][partial_chunks][32][2] are already in the scratch buffer
+// (emitted by the producing conv); otherwise a standalone statistics pass over x runs first.
+int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
+                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s) {
   HDRVAE_REQUIRE(C % 32 == 0 && C >= 128 && C <= 2048 && (kGnThreads % (C >> 3)) == 0,
                  "groupnorm: unsupported channel count %d", C);
+  HDRVAE_REQUIRE(y_dtype == DT_BF16 || y_dtype == DT_F16, "groupnorm: output must be a 16-bit operand type");
   int chunks, ppb;
-  gn_chunking(B, HW, C, &chunks, &ppb);
+  gn_chunking(B, HW, C, max_chunks, &chunks, &ppb);
   float* partial = reinterpret_cast<float*>(scratch);
-  float* scale = partial + (size_t)B * 4096 * kGroups * 2;
+  float* scale = partial + (size_t)B * max_chunks * kGroups * 2;
   float* shift = scale + (size_t)B * C;
-  gn_stats_kernel<<<dim3(chunks, B), kGnThreads, 0, s>>>(x, partial, HW, C, ppb);
-  HDRVAE_LAUNCHED();
-  HDRVAE_CUDA_OK(cudaGetLastError());
-  gn_finalize_kernel<<<B, 256, 0, s>>>(partial, chunks, gamma, beta, scale, shift, C,
+  int n_partials = partial_chunks;
+  if (partial_chunks <= 0) {
+    const dim3 grid(chunks, B);
+    if (x_dtype == DT_F32) gn_stats_kernel<float><<<grid, kGnThreads, 0, s>>>(reinterpret_cast<const float*>(x), partial, HW, C, ppb);
+    else if (x_dtype == DT_BF16) gn_stats_kernel<__nv_bfloat16><<<grid, kGnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), partial, HW, C, ppb);
+    else gn_stats_kernel<__half><<<grid, kGnThreads, 0, s>>>(reinterpret_cast<const __half*>(x), partial, HW, C, ppb);
+    HDRVAE_LAUNCHED();
+    HDRVAE_CUDA_OK(cudaGetLastError());
+    n_partials = chunks;
+  }
+  gn_finalize_kernel<<<B, 256, 0, s>>>(partial, n_partials, gamma, beta, scale, shift, C,
                                        (double)HW * (double)(C / kGroups), 1e-6f);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
-  if (silu)
-    gn_apply_kernel<true><<<dim3(chunks, B), kGnThreads, 2 * C * sizeof(float), s>>>(x, y, scale, shift, HW, C, ppb);
-  else
-    gn_apply_kernel<false><<<dim3(chunks, B), kGnThreads, 2 * C * sizeof(float), s>>>(x, y, scale, shift, HW, C, ppb);
+  if (y_dtype == DT_F16) {
+    if (x_dtype == DT_F32) launch_apply<float, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+    else launch_apply<__half, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+  } else {
+    if (x_dtype == DT_F32) launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+    else launch_apply<__half, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+  }
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;

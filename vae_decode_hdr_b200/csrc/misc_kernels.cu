@@ -28,11 +28,22 @@ int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStrea
 // Upsample phase matrices: 2x2 taps, each the sum of the 3x3 positions that land on the same
 // source pixel after nearest-2x upsampling.  `scale` multiplies every weight (attention 1/sqrt(d)).
 struct PackArgs {
-  int cout, cin, ks, ntaps, cin_pad;
+  int cout, cin, ks, ntaps, cin_pad, out_dtype;
   int tap_mask[9];
   float scale;
 };
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, PackArgs a) {
+__device__ __forceinline__ void store_as(void* out, long long i, int dtype, float v) {
+  if (dtype == DT_F32) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));      // fp32 operands feed kind::tf32 MMAs: pre-round (RN)
+    reinterpret_cast<float*>(out)[i] = __uint_as_float(r);
+  } else if (dtype == DT_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  } else {
+    reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+  }
+}
+__global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict__ out, PackArgs a) {
   const long long total = (long long)a.cout * a.ntaps * a.cin_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % a.cin_pad);
@@ -44,12 +55,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
       for (int s = 0; s < kk; ++s)
         if (a.tap_mask[t] & (1 << s)) acc += w[((long long)co * a.cin + ci) * kk + s];
     }
-    out[i] = __float2bfloat16_rn(acc * a.scale);
+    store_as(out, i, a.out_dtype, acc * a.scale);
   }
 }
-int launch_pack_weight(const float* w, __nv_bfloat16* out, int cout, int cin, int ks, int ntaps, int cin_pad,
+int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
                        const int* tap_mask, float scale, cudaStream_t s) {
   PackArgs a;
+  a.out_dtype = out_dtype;
   a.cout = cout; a.cin = cin; a.ks = ks; a.ntaps = ntaps; a.cin_pad = cin_pad; a.scale = scale;
   for (int t = 0; t < 9; ++t) a.tap_mask[t] = t < ntaps ? tap_mask[t] : 0;
   const long long total = (long long)cout * ntaps * cin_pad;
@@ -62,7 +74,7 @@ int launch_pack_weight(const float* w, __nv_bfloat16* out, int cout, int cin, in
 }
 
 // ------------------------------------------------------------------ latent NCHW fp32 -> NHWC bf16 (channels zero-padded)
-__global__ void latent_to_nhwc_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out, int B, int C,
+__global__ void latent_to_nhwc_kernel(const float* __restrict__ z, void* __restrict__ out, int out_dtype, int B, int C,
                                       int HW, int cpad) {
   const long long total = (long long)B * HW * cpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -70,14 +82,16 @@ __global__ void latent_to_nhwc_kernel(const float* __restrict__ z, __nv_bfloat16
     const long long p = i / cpad;
     const int hw = (int)(p % HW);
     const int b = (int)(p / HW);
-    out[i] = __float2bfloat16_rn(c < C ? z[((long long)b * C + c) * HW + hw] : 0.f);
+    const float v = c < C ? z[((long long)b * C + c) * HW + hw] : 0.f;
+    if (out_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
   }
 }
-int launch_latent_to_nhwc(const float* z, __nv_bfloat16* out, int B, int C, int HW, int cpad, cudaStream_t s) {
+int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C, int HW, int cpad, cudaStream_t s) {
   const long long total = (long long)B * HW * cpad;
   int grid = ceil_div(total, 256);
   if (grid > 2368) grid = 2368;
-  latent_to_nhwc_kernel<<<grid, 256, 0, s>>>(z, out, B, C, HW, cpad);
+  latent_to_nhwc_kernel<<<grid, 256, 0, s>>>(z, out, out_dtype, B, C, HW, cpad);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -86,8 +100,16 @@ int launch_latent_to_nhwc(const float* z, __nv_bfloat16* out, int B, int C, int 
 // ------------------------------------------------------------------ CUDA-core validation conv (same GemmParams)
 // One thread per output element; used only to validate the tcgen05 kernel on the GPU
 // (HDRVAE_CONV_DIRECT), never on the product path.
+__device__ __forceinline__ float load_as(const void* base, long long i, int dtype) {
+  if (dtype == DT_F32) return reinterpret_cast<const float*>(base)[i];
+  if (dtype == DT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[i]);
+  return __half2float(reinterpret_cast<const __half*>(base)[i]);
+}
+__device__ __forceinline__ float trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
 __global__ void gemm_direct_kernel(const GemmParams p) {
   const long long total = (long long)p.n_img * p.H * p.W * p.n_cols;
+  const bool tf32 = p.ab_dtype == DT_F32;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % p.n_cols);
     long long r = i / p.n_cols;
@@ -95,31 +117,29 @@ __global__ void gemm_direct_kernel(const GemmParams p) {
     const int y = (int)(r % p.H);
     const int img = (int)(r / p.H);
     float acc = 0.f;
-    for (int t = 0; t < p.ntaps; ++t) {
-      const int ys = y + p.tap_dy[t], xs = x + p.tap_dx[t];
-      if (ys < 0 || ys >= p.H || xs < 0 || xs >= p.W) continue;
-      const __nv_bfloat16* ap = p.a + img * p.a_img_stride + ys * p.a_row_stride + xs * p.a_px_stride;
-      if (p.b_rows > 0 && col >= p.b_rows) continue;
-      const __nv_bfloat16* bp = p.b + col * p.b_row_stride + (long long)t * p.k_per_tap;
-      for (int c = 0; c < p.k_per_tap; c += 8) {
-        const uint4 av = *reinterpret_cast<const uint4*>(ap + c);
-        const uint4 bv = *reinterpret_cast<const uint4*>(bp + c);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
-        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bv);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          acc = fmaf(__low2float(a2[e]), __low2float(b2[e]), acc);
-          acc = fmaf(__high2float(a2[e]), __high2float(b2[e]), acc);
+    if (!(p.b_rows > 0 && col >= p.b_rows)) {
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int ys = y + p.tap_dy[t], xs = x + p.tap_dx[t];
+        if (ys < 0 || ys >= p.H || xs < 0 || xs >= p.W) continue;
+        const long long ao = img * p.a_img_stride + ys * p.a_row_stride + xs * p.a_px_stride;
+        const long long bo = col * p.b_row_stride + (long long)t * p.k_per_tap;
+        for (int c = 0; c < p.k_per_tap; ++c) {
+          float av = load_as(p.a, ao + c, p.ab_dtype), bv = load_as(p.b, bo + c, p.ab_dtype);
+          if (tf32) { av = trunc_tf32(av); bv = trunc_tf32(bv); }     // the tensor core ignores the low 13 bits
+          acc = fmaf(av, bv, acc);
         }
       }
     }
-    float v = acc * p.alpha;
+    float v = acc * p.alpha * (p.row_scale != nullptr ? p.row_scale[x] : 1.f);
     if (p.bias != nullptr) v += p.bias_per_row ? p.bias[x] : p.bias[col];
     const long long off = (long long)img * p.out_img_stride + (long long)(y * p.sy + p.py) * p.out_row_stride +
                           (long long)(x * p.sx + p.px) * p.out_px_stride + col;
-    if (p.residual != nullptr) v += __bfloat162float(p.residual[off]);
-    if (p.out_f32) reinterpret_cast<float*>(p.out)[off] = v;
-    else reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+    if (p.residual != nullptr) v += load_as(p.residual, off, p.res_dtype);
+    if (p.out_dtype == DT_F32) {
+      if (p.round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
+      reinterpret_cast<float*>(p.out)[off] = v;
+    } else if (p.out_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+    else reinterpret_cast<__half*>(p.out)[off] = __float2half_rn(v);
   }
 }
 int launch_gemm_direct(const GemmParams& p, cudaStream_t s) {
@@ -132,13 +152,21 @@ int launch_gemm_direct(const GemmParams& p, cudaStream_t s) {
   return 0;
 }
 
-// ------------------------------------------------------------------ attention row softmax: fp32 scores -> bf16 probabilities
-// One CTA per query row; three passes over the row (max, sum, write); the row (<= 1 MB) stays in L2.
+// ------------------------------------------------------------------ attention row softmax, split form
+// fp32 scores -> e = exp(s - rowmax) as 16-bit operand (max element is exactly 1: no fp16 range problem
+// for long rows) + inv_sum[row] = 1 / sum(exp), applied later as the PV GEMM's per-row scale.
+// One CTA per query row; two passes over the row (max, exp+sum+write); the row (<= 1 MB) stays in L2.
 // Columns [n_valid, n_pad) are padding keys: excluded from the softmax and written as 0.
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
-                                                           int n_valid, int n_pad, long long s_ld, long long p_ld) {
+__device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
+  if (dtype == DT_BF16) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, void* __restrict__ p, int p_dtype,
+                                                           float* __restrict__ inv_sum, int n_valid, int n_pad,
+                                                           long long s_ld, long long p_ld) {
   const float* row = s + (long long)blockIdx.x * s_ld;
-  __nv_bfloat16* out = p + (long long)blockIdx.x * p_ld;
+  uint16_t* out = reinterpret_cast<uint16_t*>(p) + (long long)blockIdx.x * p_ld;
   __shared__ float red[8];
   __shared__ float bcast;
   const int nv = n_valid >> 2;                      // full float4 groups
@@ -160,11 +188,21 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   __syncthreads();
   m = bcast;
   float sum = 0.f;
+  uint2* out4 = reinterpret_cast<uint2*>(out);
   for (int i = threadIdx.x; i < nv; i += 256) {
     const float4 v = row4[i];
-    sum += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+    const float e0 = __expf(v.x - m), e1 = __expf(v.y - m), e2 = __expf(v.z - m), e3 = __expf(v.w - m);
+    sum += (e0 + e1) + (e2 + e3);
+    uint2 o2;
+    o2.x = pack2(e0, e1, p_dtype);
+    o2.y = pack2(e2, e3, p_dtype);
+    out4[i] = o2;
   }
-  for (int i = nv * 4 + threadIdx.x; i < n_valid; i += 256) sum += __expf(row[i] - m);
+  for (int i = nv * 4 + threadIdx.x; i < n_pad; i += 256) {
+    const float e = i < n_valid ? __expf(row[i] - m) : 0.f;
+    sum += e;
+    out[i] = (uint16_t)(pack2(e, 0.f, p_dtype) & 0xffffu);
+  }
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
@@ -172,40 +210,26 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i];
-    bcast = 1.f / t;
+    inv_sum[blockIdx.x] = 1.f / t;
   }
-  __syncthreads();
-  const float inv = bcast;
-  uint2* out4 = reinterpret_cast<uint2*>(out);
-  for (int i = threadIdx.x; i < nv; i += 256) {
-    const float4 v = row4[i];
-    __nv_bfloat162 lo = __floats2bfloat162_rn(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
-    __nv_bfloat162 hi = __floats2bfloat162_rn(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
-    uint2 o2;
-    o2.x = *reinterpret_cast<uint32_t*>(&lo);
-    o2.y = *reinterpret_cast<uint32_t*>(&hi);
-    out4[i] = o2;
-  }
-  for (int i = nv * 4 + threadIdx.x; i < n_pad; i += 256)
-    out[i] = __float2bfloat16_rn(i < n_valid ? __expf(row[i] - m) * inv : 0.f);
 }
-int launch_softmax_rows(const float* s, __nv_bfloat16* p, int n_rows, int n_valid, int n_pad, long long s_ld,
-                        long long p_ld, cudaStream_t st) {
+int launch_softmax_rows(const float* s, void* p, int p_dtype, float* inv_sum, int n_rows, int n_valid, int n_pad,
+                        long long s_ld, long long p_ld, cudaStream_t st) {
   HDRVAE_REQUIRE(s_ld % 4 == 0 && p_ld % 4 == 0 && n_pad >= n_valid, "softmax: bad leading dimensions");
-  softmax_rows_kernel<<<n_rows, 256, 0, st>>>(s, p, n_valid, n_pad, s_ld, p_ld);
+  softmax_rows_kernel<<<n_rows, 256, 0, st>>>(s, p, p_dtype, inv_sum, n_valid, n_pad, s_ld, p_ld);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // ------------------------------------------------------------------ [rows][cols] -> [cols][out_ld] transpose (test entry only)
-__global__ void transpose_pad_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
+__global__ void transpose_pad_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int rows,
                                      int cols, int out_ld) {
-  __shared__ __nv_bfloat16 tile[32][33];
+  __shared__ uint16_t tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : __float2bfloat16(0.f);
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : (uint16_t)0;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {
@@ -213,8 +237,8 @@ __global__ void transpose_pad_kernel(const __nv_bfloat16* __restrict__ in, __nv_
     if (c < cols && r < rows) out[(long long)c * out_ld + r] = tile[threadIdx.x][j];
   }
 }
-int launch_transpose_pad(const __nv_bfloat16* in, __nv_bfloat16* out, int rows, int cols, int out_ld, cudaStream_t s) {
-  transpose_pad_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, s>>>(in, out, rows, cols, out_ld);
+int launch_transpose_pad(const void* in, void* out, int rows, int cols, int out_ld, cudaStream_t s) {
+  transpose_pad_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), dim3(32, 8), 0, s>>>(reinterpret_cast<const uint16_t*>(in), reinterpret_cast<uint16_t*>(out), rows, cols, out_ld);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -19,6 +19,8 @@ DEFAULT_MODE = "mathematical_recovery"
 MODE_ALIASES = {"moderate": ("conservative", 3.0), "aggressive": ("mathematical_recovery", 1.0)}
 _MODE_ID = {m: i for i, m in enumerate(HDR_MODES)}
 _DTYPE_ID = {torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16}
+_ID_DTYPE = {v: k for k, v in _DTYPE_ID.items()}
+PRECISIONS = {"fp16": N.PRECISION_F16, "bf16": N.PRECISION_BF16}
 
 
 def resolve_mode(hdr_mode: str) -> Tuple[int, float]:
@@ -47,7 +49,12 @@ def _require_cuda(device: torch.device) -> torch.device:
 class HdrVaeEngine:
     """One libhdrvae context: packed decoder weights + workspace on one GPU."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda"):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", precision: str = "fp16"):
+        """precision: 16-bit tensor-core operand type, "fp16" (default, meets the 1e-2 tolerance) or "bf16";
+        the residual/conv streams are fp32 and raw-stream convs tf32 in both (include/hdrvae.h)."""
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {list(PRECISIONS)}")
+        self.precision = precision
         self.lib = N.load_library()
         self.device = _require_cuda(device)
         self._ctx = C.c_void_p()
@@ -76,7 +83,9 @@ class HdrVaeEngine:
         arr = (N.HdrvaeWeightDesc * len(descs))(*descs)
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
-            N.check(self.lib.hdrvae_load_weights(self._ctx, arr, len(descs), N.PRECISION_BF16), "hdrvae_load_weights")
+            N.check(self.lib.hdrvae_load_weights(self._ctx, arr, len(descs), PRECISIONS[self.precision]),
+                    "hdrvae_load_weights")
+        self.operand_dtype = _ID_DTYPE[self.lib.hdrvae_operand_dtype(self._ctx)]
 
     def set_conv_impl(self, impl: int) -> None:
         N.check(self.lib.hdrvae_set_conv_impl(self._ctx, impl), "hdrvae_set_conv_impl")
@@ -155,12 +164,13 @@ class HdrVaeEngine:
         return out, (st.as_dict() if want_stats else None)
 
     def decode_features(self, latent: torch.Tensor) -> torch.Tensor:
-        """Decoder only -> bf16 NHWC [B,8h,8w,128] = the tensor the reference's hook captures (:850-855)."""
+        """Decoder only -> NHWC [B,8h,8w,128] in the operand dtype (fp16 by default) = the tensor the reference's
+        hook captures (:850-855)."""
         B, h, w = self._check_latent(latent)
         with torch.cuda.device(self.device):
             z = latent.to(device=self.device, dtype=torch.float32).contiguous()
             ws = self._ws(B, h, w)
-            feat = torch.empty((B, 8 * h, 8 * w, 128), dtype=torch.bfloat16, device=self.device)
+            feat = torch.empty((B, 8 * h, 8 * w, 128), dtype=self.operand_dtype, device=self.device)
             N.check(self.lib.hdrvae_decode_features(self._ctx, z.data_ptr(), B, h, w, feat.data_ptr(), ws.data_ptr(),
                                                     ws.numel(), self._stream()), "hdrvae_decode_features")
         return feat
@@ -171,8 +181,8 @@ class HdrVaeEngine:
         """pre_nhwc: [B,H,W,128] float32 or bfloat16 on device.  -> (image, stats[, post3, pre3, argmax3])."""
         if pre_nhwc.dim() != 4 or pre_nhwc.shape[-1] != 128:
             raise ValueError(f"expected activations [B,H,W,128], got {tuple(pre_nhwc.shape)}")
-        if pre_nhwc.dtype not in (torch.float32, torch.bfloat16):
-            raise ValueError("activations must be float32 or bfloat16")
+        if pre_nhwc.dtype not in _DTYPE_ID:
+            raise ValueError("activations must be float32, float16 or bfloat16")
         B, H, W, _ = pre_nhwc.shape
         if B == 0 or H == 0 or W == 0:
             raise ValueError("empty activation batch")
@@ -202,42 +212,51 @@ class HdrVaeEngine:
 
     # -- kernel-level entry points (unit parity tests) ------------------------------------------------
     def conv2d(self, x_nhwc: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
-               upsample2x: bool = False, residual: Optional[torch.Tensor] = None, out_f32: bool = False,
-               impl: int = N.CONV_TCGEN05) -> torch.Tensor:
+               upsample2x: bool = False, residual: Optional[torch.Tensor] = None, out_dtype=torch.float32,
+               round_tf32: bool = False, want_stats: bool = False, impl: int = N.CONV_TCGEN05):
+        """x_nhwc dtype selects the MMA kind: float16/bfloat16 -> kind::f16, float32 -> kind::tf32."""
         B, H, W, cin = x_nhwc.shape
         cout = weight.shape[0]
         OH, OW = (2 * H, 2 * W) if upsample2x else (H, W)
         with torch.cuda.device(self.device):
-            x = x_nhwc.to(self.device, torch.bfloat16).contiguous()
+            x = x_nhwc.to(self.device).contiguous()
             wt = weight.to(self.device, torch.float32).contiguous()
             bs = bias.to(self.device, torch.float32).contiguous() if bias is not None else None
-            rs = residual.to(self.device, torch.bfloat16).contiguous() if residual is not None else None
-            y = torch.empty((B, OH, OW, cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
-            N.check(self.lib.hdrvae_conv2d(self._ctx, x.data_ptr(), B, H, W, cin, wt.data_ptr(),
-                                           bs.data_ptr() if bs is not None else None, cout, ksize, int(upsample2x),
-                                           rs.data_ptr() if rs is not None else None, y.data_ptr(), int(out_f32), impl,
-                                           self._stream()), "hdrvae_conv2d")
-        return y
+            rs = residual.to(self.device).contiguous() if residual is not None else None
+            y = torch.empty((B, OH, OW, cout), dtype=out_dtype, device=self.device)
+            chunks = self.lib.hdrvae_conv2d_stats_chunks(H, W, int(upsample2x))
+            part = torch.zeros((B, chunks, 32, 2), dtype=torch.float32, device=self.device) if want_stats else None
+            nch = C.c_int(0)
+            N.check(self.lib.hdrvae_conv2d(
+                self._ctx, x.data_ptr(), _DTYPE_ID[x.dtype], B, H, W, cin, wt.data_ptr(),
+                bs.data_ptr() if bs is not None else None, cout, ksize, int(upsample2x),
+                rs.data_ptr() if rs is not None else None, _DTYPE_ID[rs.dtype] if rs is not None else 0, y.data_ptr(),
+                _DTYPE_ID[out_dtype], int(round_tf32), part.data_ptr() if want_stats else None, C.byref(nch), impl,
+                self._stream()), "hdrvae_conv2d")
+        return (y, part) if want_stats else y
 
-    def groupnorm_silu(self, x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool = True):
+    def groupnorm_silu(self, x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool = True,
+                       out_dtype=torch.float16, partials: Optional[torch.Tensor] = None):
         B, H, W, Cc = x_nhwc.shape
         with torch.cuda.device(self.device):
-            x = x_nhwc.to(self.device, torch.bfloat16).contiguous()
+            x = x_nhwc.to(self.device).contiguous()
             g = gamma.to(self.device, torch.float32).contiguous()
             b = beta.to(self.device, torch.float32).contiguous()
-            y = torch.empty_like(x)
-            N.check(self.lib.hdrvae_groupnorm_silu(self._ctx, x.data_ptr(), B, H * W, Cc, g.data_ptr(), b.data_ptr(),
-                                                   int(silu), y.data_ptr(), self._stream()), "hdrvae_groupnorm_silu")
+            y = torch.empty(x.shape, dtype=out_dtype, device=self.device)
+            N.check(self.lib.hdrvae_groupnorm_silu(
+                self._ctx, x.data_ptr(), _DTYPE_ID[x.dtype], B, H * W, Cc, g.data_ptr(), b.data_ptr(), int(silu),
+                y.data_ptr(), _DTYPE_ID[out_dtype], partials.data_ptr() if partials is not None else None,
+                partials.shape[1] if partials is not None else 0, self._stream()), "hdrvae_groupnorm_silu")
         return y
 
     def attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
         B, T, d = q.shape
-        assert d == 512
+        assert d == 512 and q.dtype in (torch.float16, torch.bfloat16)
         with torch.cuda.device(self.device):
-            q, k, v = (t.to(self.device, torch.bfloat16).contiguous() for t in (q, k, v))
+            q, k, v = (t.to(self.device, q.dtype).contiguous() for t in (q, k, v))
             o = torch.empty_like(q)
-            N.check(self.lib.hdrvae_attention(self._ctx, q.data_ptr(), k.data_ptr(), v.data_ptr(), B, T, o.data_ptr(),
-                                              self._stream()), "hdrvae_attention")
+            N.check(self.lib.hdrvae_attention(self._ctx, q.data_ptr(), k.data_ptr(), v.data_ptr(), _DTYPE_ID[q.dtype], B, T,
+                                              o.data_ptr(), self._stream()), "hdrvae_attention")
         return o
 
     def close(self) -> None:
