@@ -259,7 +259,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 tensor-core operands (tf32 on the raw fp32 stream), fp32 accumulate", "data": "synthetic",
+            "dtype": "fp16 tensor-core operands, fp32 accumulate, fp32 residual stream", "data": "synthetic",
             "config": {"workload": f"C2 per GPU: {B}x16x{L}x{L} random latents -> {B} x {8 * L}x{8 * L}, mode {MODE} "
                                    "(smart expansion x3), Flux.1 AE decoder random-init, fp16 operands / fp32 accumulate / fp32 residual stream",
                        "global_batch": B * world,

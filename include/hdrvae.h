@@ -49,7 +49,8 @@ enum { HDRVAE_NORM_NONE = 0, HDRVAE_NORM_SIGMOID = 1, HDRVAE_NORM_TANH = 2 };
 enum { HDRVAE_F32 = 0, HDRVAE_BF16 = 1, HDRVAE_F16 = 2 };
 
 /* 16-bit tensor-core operand type of the decoder (kind::f16, fp32 accumulate in TMEM).  In both modes the
- * un-normalised residual / conv streams stay fp32 in HBM and the convs that read them run as kind::tf32.
+ * un-normalised residual / conv streams stay fp32 in HBM; the convs that read them directly get a 16-bit
+ * copy scaled by 2^-4 from the producing conv's epilogue.
  *   F16  (default): fp16 operands (GroupNorm outputs, weights, attention operands are bounded) — meets the
  *                   1e-2 end-to-end tolerance;
  *   BF16          : bf16 operands, same speed, ~8x larger operand rounding (DESIGN.md "Precision"). */

@@ -5,7 +5,9 @@
 // Numeric plan (DESIGN.md "Precision"): tensor-core operands are 16-bit (fp16 by default, bf16 selectable)
 // for everything that is normalised or bounded (GroupNorm outputs, weights, attention q/k/v/probabilities);
 // the un-normalised residual stream x and the conv1 outputs h stay fp32 in HBM; the five convs that consume
-// the raw stream (3 upsample convs, 2 nin_shortcuts) read it as tf32 operands (kind::tf32).
+// the raw stream (3 upsample convs, 2 nin_shortcuts) read a 16-bit copy of it scaled by 2^-4 that the producing
+// conv's epilogue writes next to the fp32 tensor (kind::tf32 on the fp32 tensor itself is also implemented in
+// gemm_tc.cu and reachable through hdrvae_conv2d, at half the MMA rate).
 #include <stdarg.h>
 #include <string.h>
 
@@ -90,7 +92,7 @@ struct ResW {
   NormW n1, n2;
   PackedConv c1, c2, nin;
   bool has_nin = false;
-  bool round_out = false;    // the block's output feeds a tf32 conv: round it to tf32 when it is written
+  bool dual_out = false;     // the block's output is also the operand of the next (upsample) conv: emit the scaled 16-bit copy
 };
 
 }  // namespace hdrvae
@@ -185,6 +187,10 @@ struct ConvIO {
   const void* residual = nullptr; // y's layout
   int res_dtype = DT_F32;
   bool round_tf32 = false;
+  void* y2 = nullptr;             // optional scaled 16-bit copy of y (operand of a conv that reads y un-normalised)
+  int y2_dtype = DT_F16;
+  float y2_scale = 1.f;
+  float alpha = 1.f;              // accumulator scale (undoes the operand scale of a y2-fed conv)
   float* stats = nullptr;         // GroupNorm partials of y, or null
   int* stats_chunks = nullptr;    // out: partial chunks per image written
 };
@@ -207,8 +213,9 @@ static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int
   p.k_per_tap = pc.cin_pad;
   p.n_cols = pc.cout;
   p.out = io.y; p.out_dtype = io.y_dtype;
-  p.bias = pc.bias; p.bias_per_row = 0; p.residual = io.residual; p.res_dtype = io.res_dtype; p.alpha = 1.0f;
+  p.bias = pc.bias; p.bias_per_row = 0; p.residual = io.residual; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
   p.round_tf32 = io.round_tf32 ? 1 : 0;
+  p.out2 = io.y2; p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
   choose_tile(H, W, &p);
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
@@ -265,7 +272,7 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
-  size_t off_lat, off_x, off_h, off_t, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_epi, total;
+  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_epi, total;
 };
 static constexpr long long kScoreBudgetElems = 256ll << 20;   // fp32 score chunk <= 1 GiB
 
@@ -290,6 +297,8 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   pl.off_x = take(widest * 4);       // residual stream, fp32
   pl.off_h = take(widest * 4);       // conv1 / shortcut / upsample outputs, fp32
   pl.off_t = take(widest * 2);       // GroupNorm outputs: 16-bit tensor-core operands
+  pl.off_x16 = take(widest / 2);     // scaled 16-bit copy of x feeding an upsample conv (<= [B,4h,4w,256] elements)
+  pl.off_x16b = take(widest * 2);    // scaled 16-bit copy of an upsample output feeding a nin_shortcut (<= [B,8h,8w,256])
   pl.off_gn = take(attn_only ? 0 : gn_scratch_bytes(B, 512, pl.gn_chunks));
   pl.off_qk = take((size_t)B * pl.Tp * 1024 * 2);
   pl.off_vt = take((size_t)B * 512 * pl.Tp * 2);
@@ -303,7 +312,14 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
 }
 
 // ---- decoder layer program ------------------------------------------------------------------------
+// Un-normalised tensors that feed a conv directly (upsample convs, nin_shortcuts) are handed over as a
+// 16-bit copy scaled by 2^-4: fp16 then covers |x| < 1e6 (no overflow for any sane activation) and loses
+// precision only below 1e-3 (absolute error < 5e-7); the consuming conv multiplies its accumulator by 2^4.
+static constexpr float kRawOperandScale = 1.0f / 16.0f;
+
 struct DecState {
+  void* xa16;      // scaled 16-bit copy of a level's last ResBlock output = operand of the level's upsample conv
+  void* xb16;      // scaled 16-bit copy of an upsample conv's output = operand of the next block's nin_shortcut
   float* x;        // residual stream (fp32)
   float* hbuf;     // block-internal fp32 tensor
   void* t;         // 16-bit operand buffer
@@ -335,10 +351,11 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
     HDRVAE_TRY(run_conv(ctx, rw.c1, io, B, H, W, impl, s));
   }
   HDRVAE_TRY(run_gn(ctx, st->hbuf, DT_F32, st->t, B, H * W, rw.n2, true, st, s));
-  ConvIO io; io.x = st->t; io.round_tf32 = rw.round_out; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+  ConvIO io; io.x = st->t; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+  if (rw.dual_out) { io.y2 = st->xa16; io.y2_dtype = ctx->op_dtype; io.y2_scale = kRawOperandScale; }
   if (rw.has_nin) {
-    // shortcut (tf32 on the raw stream) into hbuf (free after norm2), then conv2 accumulates onto it in place
-    ConvIO sc; sc.x = st->x; sc.y = st->hbuf;
+    // shortcut on the scaled 16-bit copy of x into hbuf (free after norm2), then conv2 accumulates onto it in place
+    ConvIO sc; sc.x = st->xb16; sc.y = st->hbuf; sc.alpha = 1.0f / kRawOperandScale;
     HDRVAE_TRY(run_conv(ctx, rw.nin, sc, B, H, W, impl, s));
     io.y = st->hbuf; io.residual = st->hbuf;
     HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
@@ -384,6 +401,8 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
   int H = pl.h, W = pl.w;
   void* lat = ws + pl.off_lat;
   DecState st;
+  st.xa16 = ws + pl.off_x16;
+  st.xb16 = ws + pl.off_x16b;
   st.x = reinterpret_cast<float*>(ws + pl.off_x);
   st.hbuf = reinterpret_cast<float*>(ws + pl.off_h);
   st.t = ws + pl.off_t;
@@ -429,7 +448,10 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
   for (int lvl = 3; lvl >= 0; --lvl) {
     for (int i = 0; i < 3; ++i) HDRVAE_TRY(run_res(ctx, ctx->up[lvl][i], &st, B, H, W, s));
     if (lvl != 0) {
-      ConvIO io; io.x = st.x; io.y = st.hbuf; io.round_tf32 = (lvl <= 2);   // feeds a nin_shortcut (tf32) one block later
+      // operand: the scaled 16-bit copy written by the level's last ResBlock; levels 2 and 1 feed a nin_shortcut
+      // one block later, so their output gets a scaled copy too
+      ConvIO io; io.x = st.xa16; io.y = st.hbuf; io.alpha = 1.0f / kRawOperandScale;
+      if (lvl <= 2) { io.y2 = st.xb16; io.y2_dtype = dt; io.y2_scale = kRawOperandScale; }
       io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
       HDRVAE_TRY(run_conv(ctx, ctx->upsample[lvl], io, B, H, W, impl, s));
       std::swap(st.x, st.hbuf);
@@ -573,7 +595,7 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
     HDRVAE_TRY(norm(k + ".norm2", cout, &rw->n2));
     HDRVAE_TRY(conv(k + ".conv2", cout, cout, 3, false, op, &rw->c2));
     rw->has_nin = cin != cout;
-    if (rw->has_nin) HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, DT_F32, &rw->nin));   // raw stream: tf32
+    if (rw->has_nin) HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, op, &rw->nin));   // reads the scaled 16-bit copy of x
     return 0;
   };
 
@@ -611,8 +633,8 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
       cin = ch[lvl];
     }
     if (lvl != 0) {
-      ctx->up[lvl][2].round_out = true;     // its output is the upsample conv's tf32 operand
-      HDRVAE_TRY(conv("up." + std::to_string(lvl) + ".upsample.conv", cin, cin, 3, true, DT_F32, &ctx->upsample[lvl]));
+      ctx->up[lvl][2].dual_out = true;      // its output is the upsample conv's operand
+      HDRVAE_TRY(conv("up." + std::to_string(lvl) + ".upsample.conv", cin, cin, 3, true, op, &ctx->upsample[lvl]));
     }
   }
   HDRVAE_TRY(norm("norm_out", 128, &ctx->norm_out));

@@ -79,6 +79,9 @@ struct GemmParams {
   int res_dtype;
   const float* row_scale;  // per M row (x coordinate) multiplier of the accumulator, or null
   float alpha;       // accumulator scale applied before bias (1.0 for convs)
+  void* out2;        // optional second output: out * out2_scale as a 16-bit tensor (same addressing), or null
+  int out2_dtype;
+  float out2_scale;
   int round_tf32;    // round fp32 outputs to tf32 (RN) so a following kind::tf32 MMA reads them exactly
   // GroupNorm statistics of the output, emitted per (image, m-tile) as (sum, sum of squares) of each of the
   // 32 channel groups: stats[((img * tiles_per_img + m_tile) * 32 + group) * 2 + {0,1}], or null

@@ -10,8 +10,8 @@
 // Operands: fp16 or bf16 (kind::f16) for normalised activations x weights, or fp32 read as tf32
 // (kind::tf32) where a conv consumes the raw fp32 residual stream.  Accumulation fp32 in TMEM.
 //
-// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05.mma issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> scale/bias/residual -> global, + GroupNorm partial
+// Roles (320 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05.mma issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> scale/bias/residual -> global, + GroupNorm partial
 // statistics of the output).  Two TMEM accumulator stages let the epilogue of tile i overlap the
 // MMAs of tile i+1.
 //
@@ -24,8 +24,8 @@ namespace hdrvae {
 constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;                    // K extent of one stage row (64 x 16-bit or 32 x tf32)
 constexpr int kABytes = kBlockM * kRowBytes;      // 16 KB
-constexpr int kNumThreads = 192;
-constexpr int kEpilogueThreads = 128;
+constexpr int kEpilogueThreads = 256;             // 8 warps: 2 per TMEM lane quarter, each taking half of the columns
+constexpr int kNumThreads = 64 + kEpilogueThreads;
 
 template <int BLOCK_N>
 struct TcConfig {
@@ -176,11 +176,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------ epilogue (8 warps; 128 TMEM lanes x 2 column halves)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp drains
     const int row = q * 32 + lane;          // accumulator row = pixel index inside the tile
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = threadIdx.x - 64;        // 0..255
     const int cpg = p.n_cols >> 5;          // channels per GroupNorm group (stats only; n_cols % 128 == 0 there)
+    constexpr int kChunksPerWarp = BLOCK_N / 64;
+    const bool res_f32 = p.residual != nullptr && p.res_dtype == DT_F32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -194,6 +197,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int y = ty * p.TH + (row >> p.tw_log2);
       const int x = tx * p.TW + (row & (p.TW - 1));
       const bool valid = (y < p.H) && (x < p.W);
+      const long long off = (long long)img * p.out_img_stride +
+                            (long long)(y * p.sy + p.py) * p.out_row_stride +
+                            (long long)(x * p.sx + p.px) * p.out_px_stride + n0;
+      const int cbase = half * (BLOCK_N / 2);
+
+      // fp32 residual of the first chunk: requested before anything else so it overlaps the MMA tail
+      float4 rcur[8], rnext[8];
+      const bool res_live = res_f32 && valid;
+      if (res_live && (n0 + cbase) < p.n_cols) {
+        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + cbase);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rcur[j] = rp[j];
+      }
 
       // stage the bias slice of this tile (double-buffered with the accumulator stage)
       float* bs = bias_s + acc * BLOCK_N;
@@ -203,21 +219,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bs[c] = (p.bias != nullptr && col < p.n_cols) ? __ldg(p.bias + col) : 0.f;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
       const float row_bias = (p.bias_per_row && p.bias != nullptr && valid) ? __ldg(p.bias + x) : 0.f;
       const float scale = p.alpha * ((p.row_scale != nullptr && valid) ? __ldg(p.row_scale + x) : 1.f);
 
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
 
-      const long long off = (long long)img * p.out_img_stride +
-                            (long long)(y * p.sy + p.py) * p.out_row_stride +
-                            (long long)(x * p.sx + p.px) * p.out_px_stride + n0;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+#pragma unroll
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int c0 = cbase + ci * 32;
         uint32_t v[32];
         ptx::tmem_ld_32x32(t_row + c0, v);
+        // prefetch the next chunk's residual while the TMEM load is in flight
+        if (ci + 1 < kChunksPerWarp && res_live && (n0 + c0 + 32) < p.n_cols) {
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + c0 + 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
+        }
         ptx::tmem_ld_wait(v);
         const bool cols_ok = (n0 + c0) < p.n_cols;       // n_cols is a multiple of 32 on every call site
         float f[32];
@@ -225,30 +245,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j)
           f[j] = __uint_as_float(v[j]) * scale + (p.bias_per_row ? row_bias : bs[c0 + j]);
         if (valid && cols_ok) {
-          if (p.residual != nullptr) {
-            // plain loads: the residual may alias the output (in-place add, same thread reads then writes)
-            if (p.res_dtype == DT_F32) {
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + c0);
+          if (res_f32) {
+            // plain loads (above): the residual may alias the output (in-place add, same thread reads then writes)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = rp[j];
-                f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+            for (int j = 0; j < 8; ++j) {
+              f[4 * j] += rcur[j].x; f[4 * j + 1] += rcur[j].y; f[4 * j + 2] += rcur[j].z; f[4 * j + 3] += rcur[j].w;
+            }
+          } else if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + off + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = rp[j];
+              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 t2;
+                if (p.res_dtype == DT_BF16) t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                else t2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                f[j * 8 + e * 2 + 0] += t2.x;
+                f[j * 8 + e * 2 + 1] += t2.y;
               }
+            }
+          }
+          if (p.out2 != nullptr) {
+            // second, scaled 16-bit copy of the output: the tensor-core operand of a conv that consumes this
+            // (un-normalised) tensor directly; the power-of-two scale keeps fp16 far from overflow
+            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + off + c0);
+            const float s2 = p.out2_scale;
+            if (p.out2_dtype == DT_BF16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o2[j] = make_uint4(pack_bf16x2(f[8 * j] * s2, f[8 * j + 1] * s2), pack_bf16x2(f[8 * j + 2] * s2, f[8 * j + 3] * s2),
+                                   pack_bf16x2(f[8 * j + 4] * s2, f[8 * j + 5] * s2), pack_bf16x2(f[8 * j + 6] * s2, f[8 * j + 7] * s2));
             } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + off + c0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 r = rp[j];
-                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 t2;
-                  if (p.res_dtype == DT_BF16) t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                  else t2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                  f[j * 8 + e * 2 + 0] += t2.x;
-                  f[j * 8 + e * 2 + 1] += t2.y;
-                }
-              }
+              for (int j = 0; j < 4; ++j)
+                o2[j] = make_uint4(pack_f16x2(f[8 * j] * s2, f[8 * j + 1] * s2), pack_f16x2(f[8 * j + 2] * s2, f[8 * j + 3] * s2),
+                                   pack_f16x2(f[8 * j + 4] * s2, f[8 * j + 5] * s2), pack_f16x2(f[8 * j + 6] * s2, f[8 * j + 7] * s2));
             }
           }
           if (p.out_dtype == DT_F32) {
@@ -281,12 +314,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else if (cpg == 8) emit_group_stats<8>(f, live, lane, stat_s + (q * 32 + c0 / 8) * 2);
           else emit_group_stats<16>(f, live, lane, stat_s + (q * 32 + c0 / 16) * 2);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
       if (p.stats != nullptr) {
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         const int groups_in_tile = BLOCK_N / cpg;        // 32 or 16
         if (et < groups_in_tile * 2) {
           const int gl = et >> 1, k = et & 1;

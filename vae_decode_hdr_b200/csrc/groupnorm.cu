@@ -161,7 +161,23 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
   for (int j = 0; j < 8; ++j) { a[j] = tab[vi * 8 + j]; b[j] = tab[C + vi * 8 + j]; }
   const TIn* xin = x + (long long)img * HW * C;
   TOut* yout = y + (long long)img * HW * C;
-  for (int p = p0 + p_off; p < p1; p += p_step) {
+  // 4 pixels per iteration: all loads are issued before the first use (memory-level parallelism)
+  int p = p0 + p_off;
+  for (; p + 3 * p_step < p1; p += 4 * p_step) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Ld8<TIn>::ld(xin + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[u][j] = fmaf(v[u][j], a[j], b[j]);
+        if (kSilu) v[u][j] = silu_f(v[u][j]);
+      }
+      St8<TOut>::st(yout + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
+    }
+  }
+  for (; p < p1; p += p_step) {
     float v[8];
     Ld8<TIn>::ld(xin + ((long long)p * vpp + vi) * 8, v);
 #pragma unroll

@@ -135,6 +135,10 @@ __global__ void gemm_direct_kernel(const GemmParams p) {
     const long long off = (long long)img * p.out_img_stride + (long long)(y * p.sy + p.py) * p.out_row_stride +
                           (long long)(x * p.sx + p.px) * p.out_px_stride + col;
     if (p.residual != nullptr) v += load_as(p.residual, off, p.res_dtype);
+    if (p.out2 != nullptr) {
+      if (p.out2_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out2)[off] = __float2bfloat16_rn(v * p.out2_scale);
+      else reinterpret_cast<__half*>(p.out2)[off] = __float2half_rn(v * p.out2_scale);
+    }
     if (p.out_dtype == DT_F32) {
       if (p.round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
       reinterpret_cast<float*>(p.out)[off] = v;
