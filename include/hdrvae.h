@@ -120,6 +120,8 @@ int hdrvae_destroy(hdrvae_ctx* ctx);
 int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl);
 /* HDRVAE_F16 or HDRVAE_BF16: element type of hdrvae_decode_features' output (set by hdrvae_load_weights). */
 int hdrvae_operand_dtype(hdrvae_ctx* ctx);
+/* tcgen05 cta_group of the GEMM/conv kernel: 0 = default (2: CTA pairs, M = 256 MMAs), 1 = single CTAs, 2 = pairs. */
+int hdrvae_set_cta_group(hdrvae_ctx* ctx, int cta_group);
 
 /* Diagnostics: per-op CUDA-event timing of everything the library launches between begin and end
  * (the reference's only instrumentation is logging with host syncs, hdr_vae_decode.py:81-84,188-193). */

@@ -68,11 +68,13 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("cta_group", [2, 1], ids=["pair", "single"])
 @pytest.mark.parametrize("op", list(OPS))
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
-def test_conv_tcgen05_matches_torch_and_direct(engine, case, op):
+def test_conv_tcgen05_matches_torch_and_direct(engine, case, op, cta_group):
     from vae_decode_hdr_b200 import _native as N
     B, H, W, cin, cout, ks, up, res = case
+    engine.set_cta_group(cta_group)        # tcgen05 cta_group::2 (CTA pairs, the default) and ::1
     g = torch.Generator(device="cpu").manual_seed(abs(hash(case)) % (2 ** 31))
     x = _as_operand(torch.randn(B, H, W, cin, generator=g), op).to(DEV)
     w = (torch.randn(cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks)).to(DEV)
@@ -102,6 +104,7 @@ def test_conv_tcgen05_matches_torch_and_direct(engine, case, op):
         yg = y_tc.double().reshape(B, OH * OW, 32, cpg)
         want = torch.stack([yg.sum((1, 3)), (yg * yg).sum((1, 3))], dim=-1)       # [B,32,2]
         assert torch.allclose(part.double().sum(1), want, rtol=2e-5, atol=1e-3), float((part.double().sum(1) - want).abs().max())
+    engine.set_cta_group(0)
 
 
 def test_conv_exact_operands_agree_with_torch_to_fp32_noise(engine):

@@ -66,6 +66,7 @@ SIGNATURES = {
     "hdrvae_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _vp, C.POINTER(HdrvaeStats),
                              _vp, _vp, _vp, _vp, _sz, _vp]),
     "hdrvae_operand_dtype": (_i, [_vp]),
+    "hdrvae_set_cta_group": (_i, [_vp, _i]),
     "hdrvae_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp,
                            C.POINTER(_i), _i, _vp]),
     "hdrvae_conv2d_stats_chunks": (_i, [_i, _i, _i]),

@@ -105,6 +105,7 @@ struct hdrvae_ctx {
   bool loaded = false;
   int conv_impl = HDRVAE_CONV_TCGEN05;
   int op_dtype = DT_F16;                          // 16-bit tensor-core operand type (HDRVAE_PRECISION_*)
+  int cta_group = 0;                              // 0 = default (CTA pairs), 1 / 2 forced
   std::vector<void*> owned;                       // every device allocation of the context
   std::map<std::string, float*> raw;              // fp32 device copies of the state dict
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -216,6 +217,7 @@ static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int
   p.bias = pc.bias; p.bias_per_row = 0; p.residual = io.residual; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
   p.round_tf32 = io.round_tf32 ? 1 : 0;
   p.out2 = io.y2; p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
+  p.cta_group = ctx->cta_group;
   choose_tile(H, W, &p);
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
@@ -264,6 +266,7 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
   p.out_px_stride = ldo; p.out_row_stride = 0; p.out_img_stride = 0;
   p.sy = p.sx = 1;
   p.bias = bias; p.bias_per_row = bias_per_row ? 1 : 0; p.alpha = alpha; p.row_scale = row_scale;
+  p.cta_group = ctx->cta_group;
   p.tw_log2 = 7; p.TW = 128; p.TH = 1; p.tiles_x = (M + 127) / 128; p.tiles_y = 1;
   if (impl == HDRVAE_CONV_DIRECT) return launch_gemm_direct(p, s);
   return launch_gemm_tc(p, ctx->num_sms, s);
@@ -543,6 +546,12 @@ int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl) {
 
 int hdrvae_operand_dtype(hdrvae_ctx* ctx) { return ctx ? ctx->op_dtype : -1; }
 
+int hdrvae_set_cta_group(hdrvae_ctx* ctx, int cta_group) {
+  HDRVAE_REQUIRE(ctx != nullptr && cta_group >= 0 && cta_group <= 2, "bad cta_group");
+  ctx->cta_group = cta_group;
+  return 0;
+}
+
 int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n, int precision) {
   HDRVAE_REQUIRE(ctx != nullptr && descs != nullptr, "hdrvae_load_weights: null argument");
   HDRVAE_REQUIRE(precision == HDRVAE_PRECISION_BF16 || precision == HDRVAE_PRECISION_F16,
@@ -743,7 +752,7 @@ int hdrvae_conv2d(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, int H, int
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   hdrvae_ctx tmp;                     // owns the temporary packed operands
-  tmp.device = ctx->device; tmp.num_sms = ctx->num_sms;
+  tmp.device = ctx->device; tmp.num_sms = ctx->num_sms; tmp.cta_group = ctx->cta_group;
   PackedConv pc;
   int r = pack_conv(&tmp, w, bias, Cout, Cin, ksize, upsample2x != 0, 1.f, x_dtype, &pc, s);
   if (r == 0) {

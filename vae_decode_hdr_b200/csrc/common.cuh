@@ -87,6 +87,8 @@ struct GemmParams {
   // 32 channel groups: stats[((img * tiles_per_img + m_tile) * 32 + group) * 2 + {0,1}], or null
   float* stats;
   int stats_chunks_per_img, stats_chunk0;
+  int cta_group;     // 0 = library default (CTA pairs), 1 = single CTA, 2 = CTA pair (tcgen05 cta_group::2)
+  int dbg;           // diagnostics (env HDRVAE_GEMM_DBG): bit0 = producer skips the TMA loads, bit1 = issuer skips the MMAs
 };
 
 struct TensorMapPair {

@@ -27,14 +27,23 @@ constexpr int kABytes = kBlockM * kRowBytes;      // 16 KB
 constexpr int kEpilogueThreads = 256;             // 8 warps: 2 per TMEM lane quarter, each taking half of the columns
 constexpr int kNumThreads = 64 + kEpilogueThreads;
 
-template <int BLOCK_N>
+constexpr int kSmemLimit = 232448;                // 227 KB opt-in shared memory per CTA on sm_100
+constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 4 * 64 * 4 /*stats*/ + 256 /*barriers*/ +
+                           1024 /*align slack*/;
+
+// CG = CTAs cooperating on one MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256-pixel x BLOCK_N
+// tile with M = 256 instructions; each CTA then stages only half of the B (weight) tile, which cuts the
+// L2->SM operand traffic by a third, deepens the pipeline and halves the per-MMA issue/barrier overhead.
+template <int BLOCK_N, int CG, int KSUB>
 struct TcConfig {
-  static constexpr int kBBytes = BLOCK_N * kRowBytes;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int kBBytes = (BLOCK_N / CG) * kRowBytes;       // one k-sub-block of B staged by this CTA
+  static constexpr int kSubBytes = kABytes + kBBytes;              // bytes one CTA loads per k-sub-block
+  static constexpr int kStageBytes = KSUB * kSubBytes;
+  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 256 / 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * BLOCK_N * 4 /*bias*/ + 4 * 64 * 4 /*stats*/ +
-                                    256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSmemFixed;
+  static_assert(kStages >= 3 && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -73,20 +82,31 @@ __device__ __forceinline__ void emit_group_stats(const float (&f)[32], bool live
   }
 }
 
-template <int BLOCK_N, bool kTf32>
+// Epilogue feature sets compiled in (EPI template parameter)
+enum : int {
+  EPI_GENERIC = 1,   // every switch decided at run time (test entry, tf32, single-CTA builds)
+  EPI_OUT16 = 2,     // 16-bit output (else fp32)
+  EPI_RES = 4,       // + fp32 residual
+  EPI_OUT2 = 8,      // + scaled 16-bit second output
+  EPI_STATS = 16,    // + GroupNorm partial statistics
+  EPI_ROWOPS = 32,   // per-row bias / per-row scale (attention GEMMs)
+};
+
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
-  using Cfg = TcConfig<BLOCK_N>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB>;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position in the CTA pair (0 = leader)
   constexpr int kStages = Cfg::kStages;
   constexpr int kElemsPerRow = kTf32 ? 32 : 64;   // K elements per stage
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage buffers.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * kABytes;
-  float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);      // [2][BLOCK_N]
-  float* stat_s = bias_s + 2 * BLOCK_N;                                             // [4 warps][32 groups][2]
+  uint8_t* smem_b = smem + kStages * KSUB * kABytes;
+  float* stage_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);     // [8 warps][32 rows][32 floats]
+  float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
   uint64_t* full_bar = bars;                      // [kStages]
   uint64_t* empty_bar = bars + kStages;           // [kStages]
@@ -106,242 +126,329 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], kEpilogueThreads / 32);
+      ptx::mbar_init(&tmem_empty_bar[i], CG * kEpilogueThreads / 32);   // epilogue warps of every CTA of the pair
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  if (warp == 1) {
+    if (CG == 2) ptx::tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_s);
+    else ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
 
+  // Work items: (group of CG consecutive m-tiles, n-tile), n fastest; CTA `rank` of the pair takes m-tile
+  // group*CG + rank.  An m-tile past the end is processed as an empty tile (TMA zero-fills, nothing is stored).
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int num_tiles = p.n_img * tiles_per_img * p.n_tiles_n;
+  const int m_tiles = p.n_img * tiles_per_img;
+  const int num_tiles = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
+  const int w_first = blockIdx.x / CG, w_step = gridDim.x / CG;
   const int kb_per_tap = p.k_per_tap / kElemsPerRow;
   const int num_kb = p.ntaps * kb_per_tap;
 
-  if (warp == 0 && lane == 0) {
+  // Producer and MMA issuer run as whole (converged) warps with one elected lane issuing: loop state and
+  // addresses are then warp-uniform and stay in the uniform datapath that UTMALDG / UTCHMMA read from (a
+  // single-lane loop costs ~70 cycles of register->uniform moves per MMA: measured with HDRVAE_GEMM_DBG).
+  // A pipeline stage holds KSUB k-sub-blocks (128 bytes of K each), so one full/empty handshake (~380 cycles
+  // of latency in the issuing thread) is amortised over 4*KSUB MMAs.
+  const int num_groups = (num_kb + KSUB - 1) / KSUB;
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
-      const int mt = tile / p.n_tiles_n;
-      const int img = mt / tiles_per_img;
+      const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
+      const int img = mt / tiles_per_img;                  // == n_img for the empty tile: out of bounds -> zeros
       const int rem = mt - img * tiles_per_img;
       const int ty = rem / p.tiles_x;
       const int tx = rem - ty * p.tiles_x;
-      const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BLOCK_N;
-      for (int t = 0; t < p.ntaps; ++t) {
-        const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t];
-        for (int kb = 0; kb < kb_per_tap; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          ptx::tma_load_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], kb * kElemsPerRow, xs, ys, img);
-          ptx::tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage],
-                           (t * kb_per_tap + kb) * kElemsPerRow, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+      const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / CG);
+      for (int g = 0; g < num_groups; ++g) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int kb0 = g * KSUB;
+        const int nsub = min(KSUB, num_kb - kb0);
+        if (ptx::elect_one()) {
+          if (p.dbg & 1) {                                 // diagnostics: no loads, just hand the slot over
+            if (rank == 0) ptx::mbar_arrive(&full_bar[stage]);
+          } else {
+            // the leader's barrier collects the bytes of both CTAs' loads
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * nsub * Cfg::kSubBytes));
+            for (int j = 0; j < nsub; ++j) {
+              const int kbl = kb0 + j;
+              const int t = kbl / kb_per_tap;
+              const int kb = kbl - t * kb_per_tap;
+              uint8_t* sa = smem_a + (stage * KSUB + j) * kABytes;
+              uint8_t* sb = smem_b + (stage * KSUB + j) * Cfg::kBBytes;
+              const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t];
+              if (CG == 2) {
+                ptx::tma_load_4d_pair(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, xs, ys, img);
+                ptx::tma_load_2d_pair(sb, &tmB, &full_bar[stage], kbl * kElemsPerRow, n0);
+              } else {
+                ptx::tma_load_4d(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, xs, ys, img);
+                ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kbl * kElemsPerRow, n0);
+              }
+            }
+          }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    const uint32_t idesc = kTf32 ? ptx::make_idesc(2u, kBlockM, BLOCK_N)
-                                 : ptx::make_idesc(p.ab_dtype == DT_BF16 ? 1u : 0u, kBlockM, BLOCK_N);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (one warp of the leader CTA)
+    const uint32_t idesc = kTf32 ? ptx::make_idesc(2u, kBlockM * CG, BLOCK_N)
+                                 : ptx::make_idesc(p.ab_dtype == DT_BF16 ? 1u : 0u, kBlockM * CG, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = w_first; tile < num_tiles; tile += w_step) {
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int g = 0; g < num_groups; ++g) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
-        const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + stage * kABytes));
-        const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+        const int nsub = min(KSUB, num_kb - g * KSUB);
+        if (ptx::elect_one()) {
+          for (int j = 0; j < nsub; ++j) {
+            if (p.dbg & 2) break;                          // diagnostics: barriers only
+            const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + (stage * KSUB + j) * kABytes));
+            const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + (stage * KSUB + j) * Cfg::kBBytes));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // one MMA consumes 32 bytes of K (16 x 16-bit or 8 x tf32) of the 128-byte swizzle row:
-          // advance the start address by 32 B = +2 in 16-byte units
-          if (kTf32) ptx::umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // one MMA consumes 32 bytes of K (16 x 16-bit or 8 x tf32) of the 128-byte swizzle row:
+              // advance the start address by 32 B = +2 in 16-byte units
+              const uint32_t accum = (g | j | k) != 0 ? 1u : 0u;
+              if (CG == 2) {
+                if (kTf32) ptx::umma_tf32_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                else ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              } else {
+                if (kTf32) ptx::umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              }
+            }
+          }
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+          if (g == num_groups - 1) {
+            if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
+          }
         }
-        ptx::umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
-        if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue (8 warps; 128 TMEM lanes x 2 column halves)
+    // TMEM hands every thread one accumulator ROW (pixel).  Writing rows straight to global memory makes each
+    // warp-level access touch 32 different 128-byte lines (ncu: 31 sectors/request, LSU wavefront bound), so
+    // each 32x32 chunk is transposed through a 4 KB swizzled shared-memory patch: afterwards 8 lanes cover 128
+    // contiguous bytes of one pixel and a warp access touches 4 lines.  Bias, residual, GroupNorm statistics
+    // and the stores all happen in that coalesced layout; the residual never goes through shared memory.
+    // The feature set is a template parameter (EPI): the generic build keeps every switch at run time and cost
+    // ~800 instructions per chunk (ncu: issue/latency bound); the specialised builds drop to ~250.
+    constexpr bool kGen = (EPI & EPI_GENERIC) != 0;
+    const bool out_f32 = kGen ? (p.out_dtype == DT_F32) : ((EPI & EPI_OUT16) == 0);
+    const bool has_res_f32 = kGen ? (p.residual != nullptr && p.res_dtype == DT_F32) : ((EPI & EPI_RES) != 0);
+    const bool has_res_16 = kGen && p.residual != nullptr && p.res_dtype != DT_F32;
+    const bool has_out2 = kGen ? (p.out2 != nullptr) : ((EPI & EPI_OUT2) != 0);
+    const bool has_stats = kGen ? (p.stats != nullptr) : ((EPI & EPI_STATS) != 0);
+    const bool row_ops = kGen ? (p.bias_per_row != 0 || p.row_scale != nullptr) : ((EPI & EPI_ROWOPS) != 0);
+    const bool do_round = kGen && p.round_tf32 != 0;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp drains
-    const int row = q * 32 + lane;          // accumulator row = pixel index inside the tile
+    const int we = warp - 2;                // 0..7
+    const int half = we >> 2;               // which half of the tile's columns this warp drains
     const int et = threadIdx.x - 64;        // 0..255
     const int cpg = p.n_cols >> 5;          // channels per GroupNorm group (stats only; n_cols % 128 == 0 there)
+    const int slot = lane & 7;              // 4-channel slot inside the 32-column chunk
+    const int sr = lane >> 3;               // pixel sub-row 0..3 handled by this lane in each iteration
+    float4* patch = reinterpret_cast<float4*>(stage_s) + we * 256;      // [32 rows][8 float4], XOR-swizzled
     constexpr int kChunksPerWarp = BLOCK_N / 64;
-    const bool res_f32 = p.residual != nullptr && p.res_dtype == DT_F32;
+    const float alpha = p.alpha;
+    const bool out16_bf = p.out_dtype == DT_BF16, out2_bf = p.out2_dtype == DT_BF16;
+    const float s2 = p.out2_scale;
+    float* const outf = reinterpret_cast<float*>(p.out);
+    uint16_t* const outh = reinterpret_cast<uint16_t*>(p.out);
+    uint16_t* const out2h = reinterpret_cast<uint16_t*>(p.out2);
+    const float* const resf = reinterpret_cast<const float*>(p.residual);
+    const long long px_step = (long long)p.sx * p.out_px_stride;
+    const bool wide = p.tw_log2 >= 5;       // a warp's 32 pixels are consecutive in x (all but tiny images)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
-      const int mt = tile / p.n_tiles_n;
+      const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
+      const bool tile_live = mt < m_tiles;                 // false: the pair's padding tile, nothing to store
       const int img = mt / tiles_per_img;
       const int rem = mt - img * tiles_per_img;
       const int ty = rem / p.tiles_x;
       const int tx = rem - ty * p.tiles_x;
       const int n0 = nt * BLOCK_N;
-      const int y = ty * p.TH + (row >> p.tw_log2);
-      const int x = tx * p.TW + (row & (p.TW - 1));
-      const bool valid = (y < p.H) && (x < p.W);
-      const long long off = (long long)img * p.out_img_stride +
-                            (long long)(y * p.sy + p.py) * p.out_row_stride +
-                            (long long)(x * p.sx + p.px) * p.out_px_stride + n0;
       const int cbase = half * (BLOCK_N / 2);
+      const long long img_off = (long long)img * p.out_img_stride + n0;
 
-      // fp32 residual of the first chunk: requested before anything else so it overlaps the MMA tail
-      float4 rcur[8], rnext[8];
-      const bool res_live = res_f32 && valid;
-      if (res_live && (n0 + cbase) < p.n_cols) {
-        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + cbase);
+      // coalesced-layout geometry of the 8 pixels this lane touches per chunk
+      long long poff[8];
+      uint32_t pmask = 0;                   // bit it: pixel it is inside the image
+      int x_first = 0;                      // x of pixel it = 0 (wide case), for per-row bias / scale lookups
+      if (wide) {
+        const int row0 = q * 32 + sr;
+        const int y = ty * p.TH + (row0 >> p.tw_log2);
+        const int x = tx * p.TW + (row0 & (p.TW - 1));
+        x_first = x;
+        const long long o0 = img_off + (long long)(y * p.sy + p.py) * p.out_row_stride + (long long)(x * p.sx + p.px) * p.out_px_stride;
+        const bool row_live = tile_live && y < p.H;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rcur[j] = rp[j];
-      }
-
-      // stage the bias slice of this tile (double-buffered with the accumulator stage)
-      float* bs = bias_s + acc * BLOCK_N;
-      if (!p.bias_per_row) {
-        for (int c = et; c < BLOCK_N; c += kEpilogueThreads) {
-          const int col = n0 + c;
-          bs[c] = (p.bias != nullptr && col < p.n_cols) ? __ldg(p.bias + col) : 0.f;
+        for (int it = 0; it < 8; ++it) {
+          poff[it] = o0 + it * 4 * px_step;
+          if (row_live && (x + it * 4) < p.W) pmask |= 1u << it;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = q * 32 + it * 4 + sr;
+          const int y = ty * p.TH + (row >> p.tw_log2);
+          const int x = tx * p.TW + (row & (p.TW - 1));
+          if (tile_live && y < p.H && x < p.W) pmask |= 1u << it;
+          poff[it] = img_off + (long long)(y * p.sy + p.py) * p.out_row_stride + (long long)(x * p.sx + p.px) * p.out_px_stride;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
-      const float row_bias = (p.bias_per_row && p.bias != nullptr && valid) ? __ldg(p.bias + x) : 0.f;
-      const float scale = p.alpha * ((p.row_scale != nullptr && valid) ? __ldg(p.row_scale + x) : 1.f);
 
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-      ptx::tc_fence_after_sync();
-
+      bool waited = false;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-#pragma unroll
+#pragma unroll 1
       for (int ci = 0; ci < kChunksPerWarp; ++ci) {
         const int c0 = cbase + ci * 32;
+        const int col = c0 + slot * 4;                    // first of this lane's 4 columns (tile-relative)
+        const uint32_t cmask = (n0 + c0) < p.n_cols ? pmask : 0u;   // n_cols is a multiple of 32 on every call site
+        // residual: coalesced loads issued first so they overlap the accumulator wait / TMEM load / transpose
+        float4 rres[8];
+        if (has_res_f32) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (cmask >> it & 1) rres[it] = *reinterpret_cast<const float4*>(resf + poff[it] + col);   // plain load: may alias out
+        }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(row_ops && p.bias_per_row) && p.bias != nullptr && cmask != 0u) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
+        if (!waited) {
+          ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+          ptx::tc_fence_after_sync();
+          waited = true;
+        }
         uint32_t v[32];
         ptx::tmem_ld_32x32(t_row + c0, v);
-        // prefetch the next chunk's residual while the TMEM load is in flight
-        if (ci + 1 < kChunksPerWarp && res_live && (n0 + c0 + 32) < p.n_cols) {
-          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + off + c0 + 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rnext[j] = rp[j];
-        }
         ptx::tmem_ld_wait(v);
-        const bool cols_ok = (n0 + c0) < p.n_cols;       // n_cols is a multiple of 32 on every call site
-        float f[32];
+        __syncwarp();                                     // previous chunk's readers are done with the patch
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          f[j] = __uint_as_float(v[j]) * scale + (p.bias_per_row ? row_bias : bs[c0 + j]);
-        if (valid && cols_ok) {
-          if (res_f32) {
-            // plain loads (above): the residual may alias the output (in-place add, same thread reads then writes)
+        for (int j = 0; j < 8; ++j)
+          patch[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        float s_acc = 0.f, q_acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[4 * j] += rcur[j].x; f[4 * j + 1] += rcur[j].y; f[4 * j + 2] += rcur[j].z; f[4 * j + 3] += rcur[j].w;
-            }
-          } else if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + off + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 r = rp[j];
-              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 t2;
-                if (p.res_dtype == DT_BF16) t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                else t2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                f[j * 8 + e * 2 + 0] += t2.x;
-                f[j * 8 + e * 2 + 1] += t2.y;
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sr;
+          float4 a = patch[rr * 8 + (slot ^ (rr & 7))];
+          if (cmask >> it & 1) {
+            float scale = alpha;
+            if (row_ops) {
+              // per-row scale / bias (attention GEMMs); x of this pixel: rows are consecutive there (H = 1)
+              const int xr = x_first + it * 4;
+              if (p.row_scale != nullptr) scale *= __ldg(p.row_scale + xr);
+              if (p.bias_per_row) {
+                const float rb = p.bias != nullptr ? __ldg(p.bias + xr) : 0.f;
+                bias4 = make_float4(rb, rb, rb, rb);
               }
             }
-          }
-          if (p.out2 != nullptr) {
-            // second, scaled 16-bit copy of the output: the tensor-core operand of a conv that consumes this
-            // (un-normalised) tensor directly; the power-of-two scale keeps fp16 far from overflow
-            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + off + c0);
-            const float s2 = p.out2_scale;
-            if (p.out2_dtype == DT_BF16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o2[j] = make_uint4(pack_bf16x2(f[8 * j] * s2, f[8 * j + 1] * s2), pack_bf16x2(f[8 * j + 2] * s2, f[8 * j + 3] * s2),
-                                   pack_bf16x2(f[8 * j + 4] * s2, f[8 * j + 5] * s2), pack_bf16x2(f[8 * j + 6] * s2, f[8 * j + 7] * s2));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o2[j] = make_uint4(pack_f16x2(f[8 * j] * s2, f[8 * j + 1] * s2), pack_f16x2(f[8 * j + 2] * s2, f[8 * j + 3] * s2),
-                                   pack_f16x2(f[8 * j + 4] * s2, f[8 * j + 5] * s2), pack_f16x2(f[8 * j + 6] * s2, f[8 * j + 7] * s2));
+            a.x = fmaf(a.x, scale, bias4.x); a.y = fmaf(a.y, scale, bias4.y);
+            a.z = fmaf(a.z, scale, bias4.z); a.w = fmaf(a.w, scale, bias4.w);
+            if (has_res_f32) { a.x += rres[it].x; a.y += rres[it].y; a.z += rres[it].z; a.w += rres[it].w; }
+            if (has_res_16) {
+              // 16-bit residual (test entry only); plain load: the residual may alias the output
+              const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + poff[it] + col);
+              float2 lo, hi;
+              if (p.res_dtype == DT_BF16) {
+                lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+                hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+              } else {
+                lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+                hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+              }
+              a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
             }
-          }
-          if (p.out_dtype == DT_F32) {
-            if (p.round_tf32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
+            if (has_out2) {
+              // second, scaled 16-bit copy of the output: the tensor-core operand of a conv that consumes this
+              // (un-normalised) tensor directly; the power-of-two scale keeps fp16 far from overflow
+              uint2 o2;
+              if (out2_bf) { o2.x = pack_bf16x2(a.x * s2, a.y * s2); o2.y = pack_bf16x2(a.z * s2, a.w * s2); }
+              else { o2.x = pack_f16x2(a.x * s2, a.y * s2); o2.y = pack_f16x2(a.z * s2, a.w * s2); }
+              *reinterpret_cast<uint2*>(out2h + poff[it] + col) = o2;
             }
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + off + c0);
-            if (p.out_dtype == DT_BF16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            if (out_f32) {
+              if (do_round) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
+              *reinterpret_cast<float4*>(outf + poff[it] + col) = a;
             } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_uint4(pack_f16x2(f[8 * j], f[8 * j + 1]), pack_f16x2(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_f16x2(f[8 * j + 4], f[8 * j + 5]), pack_f16x2(f[8 * j + 6], f[8 * j + 7]));
+              uint2 o;
+              if (out16_bf) { o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); }
+              else { o.x = pack_f16x2(a.x, a.y); o.y = pack_f16x2(a.z, a.w); }
+              *reinterpret_cast<uint2*>(outh + poff[it] + col) = o;
+            }
+            if (has_stats) {
+              s_acc += (a.x + a.y) + (a.z + a.w);
+              q_acc += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
             }
           }
         }
-        if (p.stats != nullptr) {
-          // GroupNorm partial statistics of what was just written (0 for masked pixels / columns)
-          const bool live = valid && cols_ok;
-          if (cpg == 4) emit_group_stats<4>(f, live, lane, stat_s + (q * 32 + c0 / 4) * 2);
-          else if (cpg == 8) emit_group_stats<8>(f, live, lane, stat_s + (q * 32 + c0 / 8) * 2);
-          else emit_group_stats<16>(f, live, lane, stat_s + (q * 32 + c0 / 16) * 2);
+        if (has_stats) {
+          // GroupNorm partials of what was just written: this lane holds (sum, sum of squares) of 4 channels x 8
+          // pixels; fold the 4 pixel sub-rows (lanes +8, +16, +24), then the slots that share a group
+          s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 8);  q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 8);
+          s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 16); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 16);
+          if (cpg >= 8) { s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 1); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 1); }
+          if (cpg >= 16) { s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 2); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 2); }
+          const int slots_per_group = cpg >> 2;           // 1, 2 or 4
+          if (lane < 8 && (slot % slots_per_group) == 0) {
+            const int gl = (c0 + slot * 4) / cpg;          // group index inside this tile (< 32)
+            stat_s[(q * 32 + gl) * 2 + 0] = s_acc;
+            stat_s[(q * 32 + gl) * 2 + 1] = q_acc;
+          }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
-      if (p.stats != nullptr) {
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread owns the accumulators
+        else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (has_stats) {
         asm volatile("bar.sync 2, 256;" ::: "memory");
         const int groups_in_tile = BLOCK_N / cpg;        // 32 or 16
         if (et < groups_in_tile * 2) {
           const int gl = et >> 1, k = et & 1;
           const int gg = n0 / cpg + gl;                  // group index in the layer
-          if (gg < 32) {
+          if (gg < 32 && tile_live) {
             const float t = ((stat_s[(0 * 32 + gl) * 2 + k] + stat_s[(1 * 32 + gl) * 2 + k]) +
                              (stat_s[(2 * 32 + gl) * 2 + k] + stat_s[(3 * 32 + gl) * 2 + k]));
             p.stats[(((long long)img * p.stats_chunks_per_img + p.stats_chunk0 + rem) * 32 + gg) * 2 + k] = t;
           }
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // stat_s is rewritten by the next tile
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();    // the peer may still be read by the leader's MMAs
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG == 2) ptx::tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -415,22 +522,43 @@ void choose_tile(int H, int W, GemmParams* p) {
   p->tiles_y = (H + p->TH - 1) / p->TH;
 }
 
-template <int BLOCK_N, bool kTf32>
+template <int BLOCK_N, bool kTf32, int CG, int EPI>
 static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
+  // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
+  constexpr int KSUB = (BLOCK_N <= 128) ? 2 : 1;
   GemmParams p = p_in;
-  using Cfg = TcConfig<BLOCK_N>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB>;
+  {
+    const char* d = getenv("HDRVAE_GEMM_DBG");
+    p.dbg = d ? atoi(d) : 0;
+  }
   p.n_tiles_n = (p.n_cols + BLOCK_N - 1) / BLOCK_N;
   TensorMapPair maps;
-  HDRVAE_TRY(make_maps(p, BLOCK_N, &maps));
+  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps));            // a CTA of a pair stages half of the B rows
   static bool attr_set = false;
   if (!attr_set) {
-    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
-  const long long num_tiles = (long long)p.n_img * p.tiles_x * p.tiles_y * p.n_tiles_n;
-  const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-  gemm_tc_kernel<BLOCK_N, kTf32><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(maps.a, maps.b, p);
+  const long long m_tiles = (long long)p.n_img * p.tiles_x * p.tiles_y;
+  const long long work = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
+  long long groups = num_sms / CG;
+  if (work < groups) groups = work;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB>, maps.a, maps.b, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -442,11 +570,53 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
                  p.k_per_tap, row_elems);
   HDRVAE_REQUIRE(p.n_cols % 32 == 0, "gemm_tc: output columns (%d) must be a multiple of 32", p.n_cols);
   HDRVAE_REQUIRE(p.TW * p.TH == kBlockM, "gemm_tc: tile must cover 128 pixels");
+  HDRVAE_REQUIRE(!(p.bias_per_row || p.row_scale) || p.tw_log2 >= 5, "gemm_tc: per-row bias/scale needs row-major tiles");
   HDRVAE_REQUIRE(p.stats == nullptr || (p.n_cols % 128 == 0 && p.n_cols <= 512),
                  "gemm_tc: GroupNorm statistics need 128/256/512 output channels");
   const bool tf32 = p.ab_dtype == DT_F32;
-  if (p.n_cols <= 128) return tf32 ? launch_tc<128, true>(p, num_sms, stream) : launch_tc<128, false>(p, num_sms, stream);
-  return tf32 ? launch_tc<256, true>(p, num_sms, stream) : launch_tc<256, false>(p, num_sms, stream);
+  static int cg = -1;                                       // CTA pairs by default; HDRVAE_CTA_GROUP=1 selects single CTAs
+  if (cg < 0) { const char* e = getenv("HDRVAE_CTA_GROUP"); cg = (e && atoi(e) == 1) ? 1 : 2; }
+  const int use_cg = p.cta_group > 0 ? p.cta_group : cg;
+  const bool n128 = p.n_cols <= 128;
+  if (use_cg == 2 && !tf32) {
+    // specialised epilogues for what the decoder launches; anything else takes the generic build
+    int epi = 0;
+    const bool simple_res = p.residual == nullptr || p.res_dtype == DT_F32;
+    const bool rowops = p.bias_per_row != 0 || p.row_scale != nullptr;
+    if (simple_res && !p.round_tf32) {
+      if (p.out_dtype == DT_F32 && !rowops) {
+        epi = (p.residual ? EPI_RES : 0) | (p.out2 ? EPI_OUT2 : 0) | (p.stats ? EPI_STATS : 0);
+        if ((epi & EPI_OUT2) && !(epi & EPI_STATS)) epi = -1;        // not a decoder combination
+      } else if (p.out_dtype != DT_F32 && p.residual == nullptr && p.out2 == nullptr && p.stats == nullptr) {
+        epi = EPI_OUT16 | (rowops ? EPI_ROWOPS : 0);
+      } else {
+        epi = -1;
+      }
+    } else {
+      epi = -1;
+    }
+#define HDRVAE_EPI_CASE(E)                                                                       \
+    case E:                                                                                      \
+      return n128 ? launch_tc<128, false, 2, E>(p, num_sms, stream) : launch_tc<256, false, 2, E>(p, num_sms, stream);
+    switch (epi) {
+      HDRVAE_EPI_CASE(0)
+      HDRVAE_EPI_CASE(EPI_RES)
+      HDRVAE_EPI_CASE(EPI_STATS)
+      HDRVAE_EPI_CASE(EPI_RES | EPI_STATS)
+      HDRVAE_EPI_CASE(EPI_OUT2 | EPI_STATS)
+      HDRVAE_EPI_CASE(EPI_RES | EPI_OUT2 | EPI_STATS)
+      HDRVAE_EPI_CASE(EPI_OUT16)
+      HDRVAE_EPI_CASE(EPI_OUT16 | EPI_ROWOPS)
+      default: break;
+    }
+#undef HDRVAE_EPI_CASE
+  }
+  if (use_cg == 2) {
+    if (n128) return tf32 ? launch_tc<128, true, 2, EPI_GENERIC>(p, num_sms, stream) : launch_tc<128, false, 2, EPI_GENERIC>(p, num_sms, stream);
+    return tf32 ? launch_tc<256, true, 2, EPI_GENERIC>(p, num_sms, stream) : launch_tc<256, false, 2, EPI_GENERIC>(p, num_sms, stream);
+  }
+  if (n128) return tf32 ? launch_tc<128, true, 1, EPI_GENERIC>(p, num_sms, stream) : launch_tc<128, false, 1, EPI_GENERIC>(p, num_sms, stream);
+  return tf32 ? launch_tc<256, true, 1, EPI_GENERIC>(p, num_sms, stream) : launch_tc<256, false, 1, EPI_GENERIC>(p, num_sms, stream);
 }
 
 }  // namespace hdrvae

@@ -90,6 +90,10 @@ class HdrVaeEngine:
     def set_conv_impl(self, impl: int) -> None:
         N.check(self.lib.hdrvae_set_conv_impl(self._ctx, impl), "hdrvae_set_conv_impl")
 
+    def set_cta_group(self, cta_group: int) -> None:
+        """0 = default (CTA pairs, tcgen05 cta_group::2), 1 = single-CTA kernel, 2 = pairs."""
+        N.check(self.lib.hdrvae_set_cta_group(self._ctx, cta_group), "hdrvae_set_cta_group")
+
     # -- workspace -----------------------------------------------------------------------------
     def workspace_bytes(self, B: int, h: int, w: int) -> int:
         n = C.c_size_t()
