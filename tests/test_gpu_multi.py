@@ -1,0 +1,46 @@
+"""Batch-sharded decode on 2 GPUs over NCCL == single-GPU decode of the whole batch (needs >= 2 GPUs;
+skipped on the 1-GPU test box, run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from vae_decode_hdr_b200.engine import HdrVaeEngine
+    from vae_decode_hdr_b200.sharding import decode_batch_sharded, shard_bounds
+    from vae_decode_hdr_b200.synthetic import random_decoder_state_dict, synthetic_latent
+    eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
+    z = synthetic_latent(4, 8, 8, seed=5)
+    s, e = shard_bounds(4, world)[rank]
+    out, st = decode_batch_sharded(eng, z[s:e].to(dev), "adaptive_recovery", 1.0)
+    whole, st1 = eng.decode(z.to(dev), "adaptive_recovery", 1.0)        # every rank also decodes the whole batch alone
+    same = torch.allclose(out, whole[s:e], rtol=1e-6, atol=1e-7)
+    stats_same = all(abs(st[k] - st1[k]) <= 1e-6 * max(1.0, abs(st1[k])) for k in ("pre_min", "pre_max", "pre_mean", "post_mean", "rec_max", "aligned_max"))
+    q.put((rank, bool(same), bool(stats_same), int(st["hdr_pixels"])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_batch_sharded_decode_two_gpus_nccl():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] and r[2] for r in res), res
