@@ -44,6 +44,8 @@ int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C
 int launch_softmax_rows(const float* s, void* p, int p_dtype, float* inv_sum, int n_rows, int n_valid, int n_pad,
                         long long s_ld, long long p_ld, cudaStream_t st);
 int launch_transpose_pad(const void* in, void* out, int rows, int cols, int out_ld, cudaStream_t s);
+int launch_attn_reduce_splits(const float* part, const float* inv_sum, void* out, int out_dtype, int rows, int cols,
+                              int splits, cudaStream_t st);
 int launch_pack_half(const float* img, uint16_t* out, int B, int H, int W, int layout, cudaStream_t s);
 size_t gn_scratch_bytes(int B, int C, int max_chunks);
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
@@ -275,9 +277,10 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
-  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_epi, total;
+  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_part, off_epi, total;
 };
 static constexpr long long kScoreBudgetElems = 256ll << 20;   // fp32 score chunk <= 1 GiB
+static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
 
 static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   Plan pl;
@@ -309,6 +312,7 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
   pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
   pl.off_inv = take((size_t)pl.s_rows * 4);
+  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials of the PV GEMM
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
   pl.total = off;
   return pl;
@@ -389,9 +393,36 @@ static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, cons
                           nullptr, false, qk_alpha, nullptr, impl, s));
       // P = exp(S - rowmax) (16-bit), inv = 1 / rowsum; O = inv * (P V)
       HDRVAE_TRY(launch_softmax_rows(S, P, dt, inv, rows, pl.T, pl.Tp, pl.Tp, pl.Tp, s));
-      HDRVAE_TRY(run_gemm(ctx, dt, P, pl.Tp, rows, pl.Tp, v, pl.Tp, 512, 512,
-                          reinterpret_cast<uint16_t*>(o) + ((size_t)b * pl.T + r0) * 512, 512, dt, nullptr, false, 1.0f,
-                          inv, impl, s));
+      // O = inv * (P V).  A row chunk gives only rows/128 x 2 tiles: when that cannot fill the GPU the K (key)
+      // dimension is split across `splits` images of one GEMM (fp32 partials) and reduced afterwards.
+      const int tiles = ((rows + 127) / 128) * 2;
+      int splits = 1;
+      while (tiles * splits < ctx->num_sms && splits < 32 && (pl.Tp / (splits * 2)) % 128 == 0 &&
+             (long long)rows * splits * 2 <= kSplitRowsBudget)
+        splits *= 2;
+      uint16_t* o_rows = reinterpret_cast<uint16_t*>(o) + ((size_t)b * pl.T + r0) * 512;
+      if (splits == 1) {
+        HDRVAE_TRY(run_gemm(ctx, dt, P, pl.Tp, rows, pl.Tp, v, pl.Tp, 512, 512, o_rows, 512, dt, nullptr, false, 1.0f,
+                            inv, impl, s));
+      } else {
+        float* part = reinterpret_cast<float*>(ws + pl.off_part);
+        const int ks = pl.Tp / splits;
+        GemmParams p;
+        memset(&p, 0, sizeof p);
+        p.a = P; p.ab_dtype = dt;
+        p.a_px_stride = pl.Tp; p.a_row_stride = (long long)rows * pl.Tp; p.a_img_stride = ks;   // image s = K range s
+        p.n_img = splits; p.H = 1; p.W = rows;
+        p.k_per_tap = ks; p.ntaps = 1;
+        p.b = v; p.b_row_stride = pl.Tp; p.b_rows = 512; p.n_cols = 512; p.b_img_k_stride = ks;
+        p.out = part; p.out_dtype = DT_F32;
+        p.out_px_stride = 512; p.out_row_stride = 0; p.out_img_stride = (long long)rows * 512;
+        p.sy = p.sx = 1; p.alpha = 1.0f;
+        p.tw_log2 = 7; p.TW = 128; p.TH = 1; p.tiles_x = (rows + 127) / 128; p.tiles_y = 1;
+        p.cta_group = ctx->cta_group;
+        if (impl == HDRVAE_CONV_DIRECT) HDRVAE_TRY(launch_gemm_direct(p, s));
+        else HDRVAE_TRY(launch_gemm_tc(p, ctx->num_sms, s));
+        HDRVAE_TRY(launch_attn_reduce_splits(part, inv, o_rows, dt, rows, 512, splits, s));
+      }
     }
   }
   return 0;

@@ -21,13 +21,17 @@
 
 namespace hdrvae {
 
-constexpr int kTileW = 32, kTileH = 8;               // output pixels per block (one per thread)
-constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
-constexpr int kTilePx = kHaloW * kHaloH;             // 340
-constexpr int kTilePad = kTilePx + 1;                // odd stride: conflict-free transposed stores
-constexpr int kChunk = 32;                           // channels staged per pass
+// Phase A tile: 64 x 16 output pixels per 256-thread block, 4 horizontally adjacent pixels per thread (register
+// blocking: 15 shared-memory loads per 108 FMAs; the one-pixel-per-thread version was LSU-wavefront bound, ncu 92 %).
+constexpr int kTileW = 64, kTileH = 16;
+constexpr int kPxPerThread = 4;
+constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;   // 66 x 18
+constexpr int kRowPitch = 68;                        // floats; multiple of 4 so the 16-byte / 8-byte reads are aligned
+constexpr int kTilePx = kHaloW * kHaloH;             // 1188 staged pixels
+constexpr int kChanStride = kRowPitch * kHaloH;      // 1224 floats (multiple of 4: aligned vector reads)
+constexpr int kChunk = 16;                           // channels staged per pass
 constexpr int kC = 128;
-constexpr int kEpiThreads = kTileW * kTileH;         // 256
+constexpr int kEpiThreads = (kTileW / kPxPerThread) * kTileH;   // 256
 
 struct PartialA {
   float vmin[4];   // pre, post, conv, pre3
@@ -70,19 +74,44 @@ template <> struct Load4<__half> {
   }
 };
 
+// raw 8-byte piece (4 x 16-bit) -> 4 floats
+template <typename T> struct Cvt4 {
+  static __device__ __forceinline__ float4 cvt(const uint2&) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <> struct Cvt4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 cvt(const uint2& r) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+template <> struct Cvt4<__half> {
+  static __device__ __forceinline__ float4 cvt(const uint2& r) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
 __device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(~0u, v, o)); return v; }
 __device__ __forceinline__ float warp_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(~0u, v, o)); return v; }
 __device__ __forceinline__ double warp_sum(double v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(~0u, v, o); return v; }
 
 // ------------------------------------------------------------------------------------ phase A
-template <typename T>
-__global__ void __launch_bounds__(kEpiThreads)
+template <bool kArgmax>
+__device__ __forceinline__ void maxpool_update(float v, int c, float& m, int& idx) {
+  if (kArgmax) { if (v > m) { m = v; idx = c; } }
+  else m = fmaxf(m, v);
+}
+
+template <typename T, bool kArgmax>
+__global__ void __launch_bounds__(kEpiThreads, 2)
 hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /*OIHW [3][128][3][3]*/,
                    const float* __restrict__ conv_b, int H, int W, float* __restrict__ post3,
                    float* __restrict__ pre3, int* __restrict__ argmax3, PartialA* __restrict__ partials) {
   extern __shared__ float sm[];
   float4* wsm = reinterpret_cast<float4*>(sm);                 // [9][128] (w_r, w_g, w_b, 0)
-  float* tile = sm + 9 * kC * 4;                               // [kChunk][kTilePad]
+  float* tile = sm + 9 * kC * 4;                               // [kChunk][kChanStride]: [channel][row][col]
   const int img = blockIdx.z;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const int tid = threadIdx.x;
@@ -93,26 +122,57 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
                          conv_w[(2 * kC + c) * 9 + tap], 0.f);
   }
 
-  const int px = tid % kTileW, py = tid / kTileW;
-  const int gx = x0 + px, gy = y0 + py;
-  const bool live = gx < W && gy < H;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY;
-  int a0 = 0, a1 = 42, a2 = 84;
+  const int tcx = tid % (kTileW / kPxPerThread), py = tid / (kTileW / kPxPerThread);
+  const int gx0 = x0 + tcx * kPxPerThread, gy = y0 + py;      // first of this thread's 4 pixels
+  float acc[kPxPerThread][3];
+  float mx[kPxPerThread][3];
+  int am[kPxPerThread][3];
+#pragma unroll
+  for (int q = 0; q < kPxPerThread; ++q) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { acc[q][k] = 0.f; mx[q][k] = -INFINITY; am[q][k] = 42 * k; }
+  }
   float smin = INFINITY, smax = -INFINITY, ssum = 0.f, ssq = 0.f;      // pre stats (this thread's loads)
 
   const T* img_base = pre + (long long)img * H * W * kC;
+  // Staging loads are software-pipelined for the 16-bit input types (the product path): the raw 8-byte pieces of
+  // chunk k+1 are fetched into registers while chunk k is being computed (ncu: the convert-after-load was 28 % of
+  // all stall samples); fp32 input (parity entry) loads in place.
+  constexpr bool kPrefetch = sizeof(T) == 2;
+  constexpr int kPieces = (kTilePx * (kChunk / 4) + kEpiThreads - 1) / kEpiThreads;     // 19
+  uint2 pf[kPrefetch ? kPieces : 1];
+  auto piece_src = [&](int i, int ch0, bool* ok) -> const T* {
+    const int quad = i / kTilePx;
+    const int tp = i - quad * kTilePx;
+    const int tx = tp % kHaloW, ty = tp / kHaloW;
+    const int sx = x0 + tx - 1, sy = y0 + ty - 1;
+    *ok = i < kTilePx * (kChunk / 4) && sx >= 0 && sx < W && sy >= 0 && sy < H;
+    return img_base + ((long long)sy * W + sx) * kC + ch0 + quad * 4;
+  };
+  if (kPrefetch) {
+#pragma unroll
+    for (int u = 0; u < kPieces; ++u) {
+      bool ok;
+      const T* src = piece_src(tid + u * kEpiThreads, 0, &ok);
+      pf[u] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
+    }
+  }
   for (int ch0 = 0; ch0 < kC; ch0 += kChunk) {
     __syncthreads();
-    // stage [kHaloH x kHaloW] pixels x 32 channels, transposed to [channel][pixel]
-    for (int i = tid; i < kTilePx * (kChunk / 4); i += kEpiThreads) {
-      const int quad = i % (kChunk / 4);
-      const int tp = i / (kChunk / 4);
+    // stage [kHaloH x kHaloW] pixels x 16 channels, transposed to [channel][row][col]
+    // (pixel-major lane order: a warp stores 32 consecutive pixels of one channel -> conflict-free)
+#pragma unroll
+    for (int u = 0; u < kPieces; ++u) {
+      const int i = tid + u * kEpiThreads;
+      if (i >= kTilePx * (kChunk / 4)) break;
+      const int quad = i / kTilePx;
+      const int tp = i - quad * kTilePx;
       const int tx = tp % kHaloW, ty = tp / kHaloW;
       const int sx = x0 + tx - 1, sy = y0 + ty - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
-        v = Load4<T>::ld(img_base + ((long long)sy * W + sx) * kC + ch0 + quad * 4);
+        if (kPrefetch) v = Cvt4<T>::cvt(pf[u]);
+        else v = Load4<T>::ld(img_base + ((long long)sy * W + sx) * kC + ch0 + quad * 4);
         if (tx >= 1 && tx <= kTileW && ty >= 1 && ty <= kTileH) {      // interior pixel: owned by this block
           smin = fminf(smin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
           smax = fmaxf(smax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
@@ -120,29 +180,55 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
           ssq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         }
       }
-      float* d = tile + (quad * 4) * kTilePad + tp;
-      d[0] = v.x; d[kTilePad] = v.y; d[2 * kTilePad] = v.z; d[3 * kTilePad] = v.w;
+      float* d = tile + (quad * 4) * kChanStride + ty * kRowPitch + tx;
+      d[0] = v.x; d[kChanStride] = v.y; d[2 * kChanStride] = v.z; d[3 * kChanStride] = v.w;
     }
     __syncthreads();
-    const float* tc = tile + (py + 1) * kHaloW + (px + 1);
-#pragma unroll 4
+    if (kPrefetch && ch0 + kChunk < kC) {
+#pragma unroll
+      for (int u = 0; u < kPieces; ++u) {
+        bool ok;
+        const T* src = piece_src(tid + u * kEpiThreads, ch0 + kChunk, &ok);
+        pf[u] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
+      }
+    }
+    const float* tc = tile + py * kRowPitch + tcx * kPxPerThread;    // halo row py = image row gy-1, col = gx0-1
+#pragma unroll 1
     for (int c = 0; c < kChunk; ++c) {
-      const float* t = tc + c * kTilePad;
       const int cg = ch0 + c;
-      const float ctr = t[0];
-      // channel MAX-pool 0-41 / 42-83 / 84-125 (hdr_vae_decode.py:1044-1051); strict > keeps the first max
-      if (cg < 42) { if (ctr > m0) { m0 = ctr; a0 = cg; } }
-      else if (cg < 84) { if (ctr > m1) { m1 = ctr; a1 = cg; } }
-      else if (cg < 126) { if (ctr > m2) { m2 = ctr; a2 = cg; } }
+      // 3 rows x 6 columns of this channel around the thread's 4 pixels
+      float a[3][6];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float* rp = tc + c * kChanStride + r * kRowPitch;
+        const float4 lo = *reinterpret_cast<const float4*>(rp);
+        const float2 hi = *reinterpret_cast<const float2*>(rp + 4);
+        a[r][0] = lo.x; a[r][1] = lo.y; a[r][2] = lo.z; a[r][3] = lo.w; a[r][4] = hi.x; a[r][5] = hi.y;
+      }
+      // channel MAX-pool 0-41 / 42-83 / 84-125 (hdr_vae_decode.py:1044-1051); strict > keeps the first max.
+      // The group is uniform per channel: one branch, then one FMNMX per pixel (compare+select with the index).
+      if (cg < 42) {
+#pragma unroll
+        for (int q = 0; q < kPxPerThread; ++q) maxpool_update<kArgmax>(a[1][q + 1], cg, mx[q][0], am[q][0]);
+      } else if (cg < 84) {
+#pragma unroll
+        for (int q = 0; q < kPxPerThread; ++q) maxpool_update<kArgmax>(a[1][q + 1], cg, mx[q][1], am[q][1]);
+      } else if (cg < 126) {
+#pragma unroll
+        for (int q = 0; q < kPxPerThread; ++q) maxpool_update<kArgmax>(a[1][q + 1], cg, mx[q][2], am[q][2]);
+      }
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const float a = t[(dy - 1) * kHaloW + (dx - 1)];
           const float4 w = wsm[(dy * 3 + dx) * kC + cg];
-          acc0 = fmaf(a, w.x, acc0);
-          acc1 = fmaf(a, w.y, acc1);
-          acc2 = fmaf(a, w.z, acc2);
+#pragma unroll
+          for (int q = 0; q < kPxPerThread; ++q) {
+            const float v = a[dy][q + dx];
+            acc[q][0] = fmaf(v, w.x, acc[q][0]);
+            acc[q][1] = fmaf(v, w.y, acc[q][1]);
+            acc[q][2] = fmaf(v, w.z, acc[q][2]);
+          }
         }
     }
   }
@@ -151,23 +237,27 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
   float cmin = INFINITY, cmax = -INFINITY, csum = 0.f;
   float pmin = INFINITY, pmax = -INFINITY, psum = 0.f, psq = 0.f;
   float p3min = INFINITY, p3max = -INFINITY;
-  float hl = 0.f;
-  if (live) {
-    const float cv[3] = {acc0 + conv_b[0], acc1 + conv_b[1], acc2 + conv_b[2]};
-    const float mv[3] = {m0, m1, m2};
-    const int av[3] = {a0, a1, a2};
-    const long long o = (((long long)img * H + gy) * W + gx) * 3;
+  float hl = 0.f, nlive = 0.f;
+  const float cb[3] = {conv_b[0], conv_b[1], conv_b[2]};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      // comfy.sd.VAE.decode process_output: clamp((x + 1) / 2, 0, 1)
-      const float s = fminf(fmaxf(__fdiv_rn(__fadd_rn(cv[k], 1.0f), 2.0f), 0.f), 1.f);
-      post3[o + k] = s;
-      pre3[o + k] = mv[k];
-      if (argmax3 != nullptr) argmax3[o + k] = av[k];
-      cmin = fminf(cmin, cv[k]); cmax = fmaxf(cmax, cv[k]); csum += cv[k];
-      pmin = fminf(pmin, s); pmax = fmaxf(pmax, s); psum += s; psq += s * s;
-      p3min = fminf(p3min, mv[k]); p3max = fmaxf(p3max, mv[k]);
-      hl += mv[k] > 1.0f ? 1.f : 0.f;
+  for (int q = 0; q < kPxPerThread; ++q) {
+    const int gx = gx0 + q;
+    if (gx < W && gy < H) {
+      const long long o = (((long long)img * H + gy) * W + gx) * 3;
+      nlive += 3.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float cv = acc[q][k] + cb[k];
+        // comfy.sd.VAE.decode process_output: clamp((x + 1) / 2, 0, 1)
+        const float sv = fminf(fmaxf(__fdiv_rn(__fadd_rn(cv, 1.0f), 2.0f), 0.f), 1.f);
+        post3[o + k] = sv;
+        pre3[o + k] = mx[q][k];
+        if (kArgmax) argmax3[o + k] = am[q][k];
+        cmin = fminf(cmin, cv); cmax = fmaxf(cmax, cv); csum += cv;
+        pmin = fminf(pmin, sv); pmax = fmaxf(pmax, sv); psum += sv; psq += sv * sv;
+        p3min = fminf(p3min, mx[q][k]); p3max = fmaxf(p3max, mx[q][k]);
+        hl += mx[q][k] > 1.0f ? 1.f : 0.f;
+      }
     }
   }
 
@@ -178,7 +268,7 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
   const float mins[4] = {warp_min(smin), warp_min(pmin), warp_min(cmin), warp_min(p3min)};
   const float maxs[4] = {warp_max(smax), warp_max(pmax), warp_max(cmax), warp_max(p3max)};
   const double sums[8] = {warp_sum((double)ssum), warp_sum((double)ssq), warp_sum((double)psum), warp_sum((double)psq),
-                          warp_sum((double)csum), 0.0, warp_sum(live ? 3.0 : 0.0), warp_sum((double)hl)};
+                          warp_sum((double)csum), 0.0, warp_sum((double)nlive), warp_sum((double)hl)};
   if (lane == 0) {
     for (int k = 0; k < 4; ++k) { rmin[k][warp] = mins[k]; rmax[k][warp] = maxs[k]; }
     for (int k = 0; k < 8; ++k) rsum[k][warp] = sums[k];
@@ -428,27 +518,33 @@ void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W) { return carve(
 float* epilogue_post3_ptr(void* scratch, int B, int H, int W) { return carve(scratch, B, H, W).post3; }
 float* epilogue_pre3_ptr(void* scratch, int B, int H, int W) { return carve(scratch, B, H, W).pre3; }
 
+template <typename T>
+static void launch_phase_a(const void* pre, const float* conv_w, const float* conv_b, int H, int W, float* post3, float* pre3,
+                           int* argmax3, PartialA* pa, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(hdr_phase_a_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(hdr_phase_a_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    set = true;
+  }
+  if (argmax3 != nullptr)
+    hdr_phase_a_kernel<T, true><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, argmax3, pa);
+  else
+    hdr_phase_a_kernel<T, false><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, nullptr, pa);
+}
+
 int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, const float* conv_w, const float* conv_b,
                             int* argmax3, void* scratch, cudaStream_t s) {
   EpilogueScratch e = carve(scratch, B, H, W);
   const dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH), B);
   HDRVAE_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "epilogue: image too large for the launch grid");
-  const size_t smem = (9 * kC * 4 + kChunk * kTilePad) * sizeof(float);
+  const size_t smem = (9 * kC * 4 + kChunk * kChanStride) * sizeof(float);
   if (dtype == HDRVAE_F32) {
-    static bool set = false;
-    if (!set) { HDRVAE_CUDA_OK(cudaFuncSetAttribute(hdr_phase_a_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-    hdr_phase_a_kernel<float><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const float*>(pre), conv_w, conv_b, H, W,
-                                                                 e.post3, e.pre3, argmax3, e.pa);
+    launch_phase_a<float>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, s);
   } else if (dtype == HDRVAE_BF16) {
-    static bool set = false;
-    if (!set) { HDRVAE_CUDA_OK(cudaFuncSetAttribute(hdr_phase_a_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-    hdr_phase_a_kernel<__nv_bfloat16><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(pre), conv_w,
-                                                                         conv_b, H, W, e.post3, e.pre3, argmax3, e.pa);
+    launch_phase_a<__nv_bfloat16>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, s);
   } else if (dtype == HDRVAE_F16) {
-    static bool set = false;
-    if (!set) { HDRVAE_CUDA_OK(cudaFuncSetAttribute(hdr_phase_a_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
-    hdr_phase_a_kernel<__half><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const __half*>(pre), conv_w, conv_b, H, W,
-                                                                e.post3, e.pre3, argmax3, e.pa);
+    launch_phase_a<__half>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, s);
   } else {
     HDRVAE_REQUIRE(false, "epilogue: unsupported activation dtype %d", dtype);
   }

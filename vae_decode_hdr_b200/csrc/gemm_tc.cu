@@ -166,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ty = rem / p.tiles_x;
       const int tx = rem - ty * p.tiles_x;
       const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / CG);
+      const int bk0 = (int)(img * p.b_img_k_stride);       // split-K: this image's K range of B
       for (int g = 0; g < num_groups; ++g) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         const int kb0 = g * KSUB;
@@ -185,10 +186,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t];
               if (CG == 2) {
                 ptx::tma_load_4d_pair(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, xs, ys, img);
-                ptx::tma_load_2d_pair(sb, &tmB, &full_bar[stage], kbl * kElemsPerRow, n0);
+                ptx::tma_load_2d_pair(sb, &tmB, &full_bar[stage], bk0 + kbl * kElemsPerRow, n0);
               } else {
                 ptx::tma_load_4d(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, xs, ys, img);
-                ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kbl * kElemsPerRow, n0);
+                ptx::tma_load_2d(sb, &tmB, &full_bar[stage], bk0 + kbl * kElemsPerRow, n0);
               }
             }
           }
@@ -495,7 +496,8 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps) {
                    p.n_img, p.k_per_tap);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)p.k_per_tap * p.ntaps, (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols)};
+    cuuint64_t dims[2] = {(cuuint64_t)(p.b_img_k_stride > 0 ? p.b_img_k_stride * p.n_img : (long long)p.k_per_tap * p.ntaps),
+                          (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols)};
     cuuint64_t strides[1] = {(cuuint64_t)p.b_row_stride * eb};
     cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)block_n};
     cuuint32_t estr[2] = {1, 1};

@@ -102,38 +102,37 @@ gn_stats_kernel(const TIn* __restrict__ x, float* __restrict__ partial, int HW, 
   }
 }
 
-// one block per image; thread (g, lane8): 32 groups x 8 lanes
+// one block per (group, image): fixed-order double reduction over the chunks, then the group's channels get
+// their scale / shift.  (One block per image was 47 us per layer at 8192 chunks: B x 32 blocks are ~10x faster.)
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ partial, int n_chunks, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int C,
                    double count, float eps) {
-  const int img = blockIdx.x;
-  const int g = threadIdx.x >> 3, l = threadIdx.x & 7;
+  const int g = blockIdx.x, img = blockIdx.y;
+  __shared__ double rs[256], rq[256];
   double s = 0.0, q = 0.0;
-  for (int c = l; c < n_chunks; c += 8) {
-    const float* pp = partial + ((long long)img * n_chunks + c) * (kGroups * 2) + g * 2;
-    s += (double)pp[0];
-    q += (double)pp[1];
+  for (int c = threadIdx.x; c < n_chunks; c += 256) {
+    const float2 pp = *reinterpret_cast<const float2*>(partial + ((long long)img * n_chunks + c) * (kGroups * 2) + g * 2);
+    s += (double)pp.x;
+    q += (double)pp.y;
   }
-  for (int o = 4; o; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  __shared__ float mean_s[kGroups], rstd_s[kGroups];
-  if (l == 0) {
-    const double mean = s / count;
-    double var = q / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mean_s[g] = (float)mean;
-    rstd_s[g] = (float)(1.0 / sqrt(var + (double)eps));
-  }
+  rs[threadIdx.x] = s;
+  rq[threadIdx.x] = q;
   __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double mean = rs[0] / count;
+  double var = rq[0] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const int cpg = C / kGroups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int gg = c / cpg;
-    const float a = gamma[c] * rstd_s[gg];
+  if (threadIdx.x < cpg) {
+    const int c = g * cpg + threadIdx.x;
+    const float a = gamma[c] * rstd;
     scale[(long long)img * C + c] = a;
-    shift[(long long)img * C + c] = beta[c] - mean_s[gg] * a;
+    shift[(long long)img * C + c] = beta[c] - (float)mean * a;
   }
 }
 
@@ -242,7 +241,7 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
     HDRVAE_CUDA_OK(cudaGetLastError());
     n_partials = chunks;
   }
-  gn_finalize_kernel<<<B, 256, 0, s>>>(partial, n_partials, gamma, beta, scale, shift, C,
+  gn_finalize_kernel<<<dim3(kGroups, B), 256, 0, s>>>(partial, n_partials, gamma, beta, scale, shift, C,
                                        (double)HW * (double)(C / kGroups), 1e-6f);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
