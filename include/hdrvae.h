@@ -214,6 +214,12 @@ int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, in
 int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int dtype, int B, int T,
                      void* o, void* stream);
 
+/* Exact quantiles by radix select over a device float32 array (statistical profiling; BASELINE.json north_star).
+ * The reference computes none: defined as torch.quantile(x, q, interpolation="lower") =
+ * the element of 0-based rank floor(q * (n - 1)); bit-exact.  q: host doubles in [0,1] (1..8 of them),
+ * out_host: host float32 [nq]; synchronises the stream. */
+int hdrvae_quantiles(const float* data, long long n, const double* q, int nq, float* out_host, void* stream);
+
 /* fp32 -> fp16 round-to-nearest-even pack for LinearEXRExport
  * (linear_exr_export.py:155,165: ndarray.astype(np.float16); overflow -> inf).
  * layout 0: same order as the input; layout 1: EXR scanline order

@@ -209,3 +209,19 @@ def test_pack_half_bit_exact_vs_numpy():
     planes = pack_half(img.to(DEV), exr_scanline_order=True).cpu().numpy()     # [B,H,3(B,G,R),W]
     assert np.array_equal(planes.view(np.uint16), np.ascontiguousarray(want[..., ::-1].transpose(0, 1, 3, 2)).view(np.uint16))
     assert pack_half(torch.empty(0, 4, 4, 3, device=DEV)).shape == (0, 4, 4, 3)
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 3 * 512 * 512 + 5])
+def test_quantiles_radix_select_bit_exact(n):
+    """Radix-select quantile indices must be bit-exact (BASELINE.json north_star): == torch.kthvalue."""
+    from vae_decode_hdr_b200.engine import quantiles
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, generator=g) * 3.0).to(DEV)
+    if n > 10:
+        x[3] = float("inf"); x[5] = -0.0; x[6] = 0.0; x[7] = -1e-30; x[8:60] = 1.25      # ties, signed zeros, inf
+    qs = [0.0, 0.01, 0.5, 0.99, 0.999, 1.0]
+    got = quantiles(x, qs)
+    for q, v in zip(qs, got):
+        k = int(math.floor(q * (n - 1))) + 1
+        want = float(torch.kthvalue(x.float().cpu(), k).values)
+        assert np.float32(v).tobytes() == np.float32(want).tobytes() or (v == want == 0.0), (q, v, want)

@@ -72,6 +72,7 @@ SIGNATURES = {
     "hdrvae_conv2d_stats_chunks": (_i, [_i, _i, _i]),
     "hdrvae_groupnorm_silu": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "hdrvae_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "hdrvae_quantiles": (_i, [_vp, C.c_longlong, C.POINTER(C.c_double), _i, C.POINTER(C.c_float), _vp]),
     "hdrvae_pack_half": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -47,11 +47,15 @@ int launch_transpose_pad(const void* in, void* out, int rows, int cols, int out_
 int launch_attn_reduce_splits(const float* part, const float* inv_sum, void* out, int out_dtype, int rows, int cols,
                               int splits, cudaStream_t st);
 int launch_pack_half(const float* img, uint16_t* out, int B, int H, int W, int layout, cudaStream_t s);
+size_t quantile_scratch_bytes();
+int launch_quantiles(const float* x, long long n, const unsigned long long* ranks_host, int nq, float* out, void* scratch,
+                     cudaStream_t s);
 size_t gn_scratch_bytes(int B, int C, int max_chunks);
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
                      const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s);
 size_t epilogue_scratch_bytes(int B, int H, int W);
 void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W);
+hdrvae_stats* epilogue_stats_dev_ptr(void* scratch, int B, int H, int W);
 float* epilogue_post3_ptr(void* scratch, int B, int H, int W);
 float* epilogue_pre3_ptr(void* scratch, int B, int H, int W);
 int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, const float* conv_w, const float* conv_b,
@@ -108,6 +112,10 @@ struct hdrvae_ctx {
   int conv_impl = HDRVAE_CONV_TCGEN05;
   int op_dtype = DT_F16;                          // 16-bit tensor-core operand type (HDRVAE_PRECISION_*)
   int cta_group = 0;                              // 0 = default (CTA pairs), 1 / 2 forced
+  struct GraphEntry { int B, h, w, mode, conv_impl, cta_group; float factor, ev; void* ws; cudaGraphExec_t exec; long long n_kernels; };
+  std::vector<GraphEntry> graphs;                 // captured whole-decode CUDA graphs (hdrvae_decode)
+  std::vector<GraphEntry> seen;                   // keys decoded once already (capture happens on the second use)
+  bool use_graphs = true;
   std::vector<void*> owned;                       // every device allocation of the context
   std::map<std::string, float*> raw;              // fp32 device copies of the state dict
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -277,7 +285,7 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
-  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_part, off_epi, total;
+  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_part, off_epi, off_lat_in, off_img, total;
 };
 static constexpr long long kScoreBudgetElems = 256ll << 20;   // fp32 score chunk <= 1 GiB
 static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
@@ -314,6 +322,8 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   pl.off_inv = take((size_t)pl.s_rows * 4);
   pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials of the PV GEMM
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
+  pl.off_lat_in = take(attn_only ? 0 : (size_t)B * 16 * pl.T * 4);          // graph input: fp32 latent copy
+  pl.off_img = take(attn_only ? 0 : (size_t)B * 64 * pl.T * 3 * 4);        // graph output: fp32 BHWC image
   pl.total = off;
   return pl;
 }
@@ -533,6 +543,7 @@ int hdrvae_create(hdrvae_ctx** out, int device) {
 int hdrvae_destroy(hdrvae_ctx* ctx) {
   if (ctx == nullptr) return 0;
   cudaSetDevice(ctx->device);
+  for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : ctx->owned) cudaFree(p);
   delete ctx;
   return 0;
@@ -726,12 +737,73 @@ int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float e
                                  ws + pl.off_epi, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// The whole decode (~130 launches) is captured into a CUDA graph the second time a (shape, mode, workspace) key
+// is seen and replayed afterwards: the latent is staged into / the image out of fixed workspace buffers so the
+// graph does not depend on the caller's tensor addresses.  HDRVAE_NO_GRAPH=1 disables it.
 int hdrvae_decode(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, int mode, float expansion_factor,
                   float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace, size_t ws_bytes,
                   void* stream) {
-  HDRVAE_TRY(hdrvae_decode_begin(ctx, latent, B, h, w, workspace, ws_bytes, nullptr, stream));
-  return hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, out_bhwc, stats, workspace, ws_bytes,
-                              stream);
+  HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
+  HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode: empty latent batch [%d,16,%d,%d]", B, h, w);
+  HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_decode: bad mode %d", mode);
+  static int no_graph = -1;
+  if (no_graph < 0) { const char* e = getenv("HDRVAE_NO_GRAPH"); no_graph = (e && atoi(e) != 0) ? 1 : 0; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool graphs = ctx->use_graphs && !no_graph && !g_prof_on && s != nullptr;     // capture needs a non-default stream
+  if (!graphs) {
+    HDRVAE_TRY(hdrvae_decode_begin(ctx, latent, B, h, w, workspace, ws_bytes, nullptr, stream));
+    return hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, out_bhwc, stats, workspace, ws_bytes,
+                                stream);
+  }
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  const Plan pl = make_plan(B, h, w);
+  HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* lat_in = reinterpret_cast<float*>(ws + pl.off_lat_in);
+  float* img = reinterpret_cast<float*>(ws + pl.off_img);
+  HDRVAE_CUDA_OK(cudaMemcpyAsync(lat_in, latent, (size_t)B * 16 * pl.T * 4, cudaMemcpyDeviceToDevice, s));
+  auto same = [&](const hdrvae_ctx::GraphEntry& g) {
+    return g.B == B && g.h == h && g.w == w && g.mode == mode && g.factor == expansion_factor && g.ev == ev_multiplier &&
+           g.ws == workspace && g.conv_impl == ctx->conv_impl && g.cta_group == ctx->cta_group;
+  };
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : ctx->graphs) if (same(g)) { exec = g.exec; g_launch_count += g.n_kernels; }
+  if (exec == nullptr) {
+    bool seen = false;
+    for (auto& g : ctx->seen) if (same(g)) seen = true;
+    hdrvae_ctx::GraphEntry key{B, h, w, mode, ctx->conv_impl, ctx->cta_group, expansion_factor, ev_multiplier, workspace, nullptr, 0};
+    if (!seen) {
+      // first use of this key: plain launches (also runs every one-time cudaFuncSetAttribute outside a capture)
+      if (ctx->seen.size() > 64) ctx->seen.clear();
+      ctx->seen.push_back(key);
+      HDRVAE_TRY(hdrvae_decode_begin(ctx, lat_in, B, h, w, workspace, ws_bytes, nullptr, stream));
+      HDRVAE_TRY(hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, img, nullptr, workspace, ws_bytes, stream));
+    } else {
+      const long long n_before = g_launch_count;    // launches recorded by the capture = kernels of every replay
+      HDRVAE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int r = hdrvae_decode_begin(ctx, lat_in, B, h, w, workspace, ws_bytes, nullptr, stream);
+      if (r == 0) r = hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, img, nullptr, workspace, ws_bytes, stream);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+      HDRVAE_REQUIRE(e == cudaSuccess && graph != nullptr, "hdrvae_decode: CUDA graph capture failed: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      HDRVAE_REQUIRE(e == cudaSuccess, "hdrvae_decode: cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+      if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+      key.exec = exec;
+      key.n_kernels = g_launch_count - n_before;
+      ctx->graphs.push_back(key);
+    }
+  }
+  if (exec != nullptr) HDRVAE_CUDA_OK(cudaGraphLaunch(exec, s));
+  HDRVAE_CUDA_OK(cudaMemcpyAsync(out_bhwc, img, (size_t)B * 64 * pl.T * 3 * 4, cudaMemcpyDeviceToDevice, s));
+  if (stats != nullptr) {
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(stats, epilogue_stats_dev_ptr(ws + pl.off_epi, B, 8 * h, 8 * w), sizeof(hdrvae_stats),
+                                   cudaMemcpyDeviceToHost, s));
+    HDRVAE_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  return 0;
 }
 
 int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, void* features, void* workspace,
@@ -848,6 +920,27 @@ int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* 
   ctx->op_dtype = saved;
   cudaStreamSynchronize(s);
   cudaFree(ws);
+  return r;
+}
+
+int hdrvae_quantiles(const float* data, long long n, const double* q, int nq, float* out_host, void* stream) {
+  HDRVAE_REQUIRE(data && q && out_host && n >= 1 && nq >= 1 && nq <= 8, "hdrvae_quantiles: bad argument (1..8 quantiles, n >= 1)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long ranks[8];
+  for (int i = 0; i < nq; ++i) {
+    HDRVAE_REQUIRE(q[i] >= 0.0 && q[i] <= 1.0, "hdrvae_quantiles: q must be in [0,1]");
+    ranks[i] = (unsigned long long)floor(q[i] * (double)(n - 1));      // torch.quantile(..., interpolation="lower")
+  }
+  void* scratch = nullptr;
+  HDRVAE_CUDA_OK(cudaMalloc(&scratch, quantile_scratch_bytes() + 8 * sizeof(float)));
+  float* out_dev = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + quantile_scratch_bytes());
+  int r = launch_quantiles(data, n, ranks, nq, out_dev, scratch, s);
+  if (r == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, out_dev, nq * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("hdrvae_quantiles: %s", cudaGetErrorString(e)); r = -1; }
+  }
+  cudaFree(scratch);
   return r;
 }
 

@@ -515,6 +515,7 @@ static EpilogueScratch carve(void* scratch, int B, int H, int W) {
 }
 
 void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W) { return carve(scratch, B, H, W).raw; }
+hdrvae_stats* epilogue_stats_dev_ptr(void* scratch, int B, int H, int W) { return carve(scratch, B, H, W).st; }
 float* epilogue_post3_ptr(void* scratch, int B, int H, int W) { return carve(scratch, B, H, W).post3; }
 float* epilogue_pre3_ptr(void* scratch, int B, int H, int W) { return carve(scratch, B, H, W).pre3; }
 

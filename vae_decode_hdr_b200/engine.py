@@ -60,6 +60,8 @@ class HdrVaeEngine:
         self._ctx = C.c_void_p()
         N.check(self.lib.hdrvae_create(C.byref(self._ctx), self.device.index), "hdrvae_create")
         self._workspace: Optional[torch.Tensor] = None
+        # the library captures the whole decode into a CUDA graph, which needs a non-default stream
+        self._side = torch.cuda.Stream(device=self.device)
         self._load(state_dict)
 
     # -- weights -------------------------------------------------------------------------------
@@ -131,9 +133,18 @@ class HdrVaeEngine:
             if out is None:
                 out = torch.empty((B, 8 * h, 8 * w, 3), dtype=torch.float32, device=self.device)
             st = N.HdrvaeStats() if want_stats else None
+            cur = torch.cuda.current_stream(self.device)
+            run_on = cur
+            if cur.cuda_stream == 0:        # legacy default stream: hop to the engine's stream (graph capture)
+                run_on = self._side
+                run_on.wait_stream(cur)
+                for t in (z, ws, out):
+                    t.record_stream(run_on)
             N.check(self.lib.hdrvae_decode(self._ctx, z.data_ptr(), B, h, w, mode, factor, float(ev_multiplier),
                                            out.data_ptr(), C.byref(st) if want_stats else None, ws.data_ptr(),
-                                           ws.numel(), self._stream()), "hdrvae_decode")
+                                           ws.numel(), run_on.cuda_stream), "hdrvae_decode")
+            if run_on is not cur:
+                cur.wait_stream(run_on)
         return out, (st.as_dict() if want_stats else None)
 
     def decode_begin(self, latent: torch.Tensor) -> torch.Tensor:
@@ -274,6 +285,25 @@ class HdrVaeEngine:
             self.close()
         except Exception:
             pass
+
+
+def quantiles(x: torch.Tensor, qs) -> list:
+    """Exact quantiles (lower interpolation = order statistic of rank floor(q*(n-1))) of a CUDA float32 tensor by
+    radix select on the GPU; == torch.quantile(x.flatten(), q, interpolation="lower"), bit-exact."""
+    lib = N.load_library()
+    dev = _require_cuda(x.device)
+    qs = [float(q) for q in qs]
+    if not 1 <= len(qs) <= 8:
+        raise ValueError("1..8 quantiles")
+    if x.numel() == 0:
+        raise ValueError("quantiles of an empty tensor")
+    with torch.cuda.device(dev):
+        xf = x.to(torch.float32).contiguous()
+        qa = (C.c_double * len(qs))(*qs)
+        out = (C.c_float * len(qs))()
+        N.check(lib.hdrvae_quantiles(xf.data_ptr(), xf.numel(), qa, len(qs), out,
+                                     torch.cuda.current_stream(dev).cuda_stream), "hdrvae_quantiles")
+    return [float(v) for v in out]
 
 
 def pack_half(image_bhwc: torch.Tensor, exr_scanline_order: bool = False) -> torch.Tensor:

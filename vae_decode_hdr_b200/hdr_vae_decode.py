@@ -21,7 +21,7 @@ from typing import Any, Dict, Optional, Tuple
 
 import torch
 
-from .engine import DEFAULT_MODE, HDR_MODES, HdrVaeEngine
+from .engine import DEFAULT_MODE, HDR_MODES, HdrVaeEngine, quantiles
 
 logger = logging.getLogger(__name__)
 
@@ -47,6 +47,7 @@ class HDRVAEDecode:
         self.logger = logger
         self.NORMALIZATION_FUNCTION = str()
         self.last_stats: Optional[Dict] = None
+        self.profile_quantiles = False      # True: last_stats["out_quantiles"] = {q: value} of the output image
 
     @classmethod
     def INPUT_TYPES(cls):
@@ -109,6 +110,10 @@ class HDRVAEDecode:
         device = self._compute_device(vae, latent)
         engine = self._engine_for(vae, device)
         image, stats = engine.decode(latent, hdr_mode, conservative_ev_multiplier, want_stats=True)
+        if self.profile_quantiles:
+            # statistical profiling beyond the reference's min/max/mean: exact quantiles by GPU radix select
+            qs = (0.01, 0.5, 0.99, 0.999)
+            stats["out_quantiles"] = dict(zip(qs, quantiles(image, qs)))
         self.last_stats = stats
         self.NORMALIZATION_FUNCTION = {0: "", 1: "SIGMOID", 2: "TANH"}[stats["norm_function"]]
         if not stats["accepted"]:
