@@ -163,6 +163,42 @@ int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float e
                          float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---- spatial row tiling across GPUs (BASELINE config C4) --------------------------------------
+ * One image, latent rows split evenly over `world` ranks (h % world == 0).  Every rank runs the same step
+ * program on its slab; between steps the HOST performs the exchange the library describes (NCCL in
+ * vae_decode_hdr_b200/sharding.py, plain copies when ranks are emulated in one process):
+ *   HALO      : the first / last interior row of up to two conv outputs goes to the upper / lower neighbour's halo row
+ *               (33 of these per decode, one per 3x3-conv input);
+ *   ALLREDUCE : SUM of `allreduce_count` doubles = the GroupNorm (sum, sum of squares) of every (image, group), so
+ *               that tiling does not change the normalisation;
+ *   ALLGATHER : in-place all-gather of `gather_bytes_per_rank` bytes per rank (attention K and V: mid.attn_1 is global);
+ *   RAW_STATS : MIN/MAX/SUM all-reduce of the hdrvae_raw_stats block (batch-global HDR statistics).
+ * All offsets are byte offsets into the rank's workspace (identical on every rank). */
+enum { HDRVAE_EX_END = 0, HDRVAE_EX_HALO = 1, HDRVAE_EX_ALLREDUCE_F64 = 2, HDRVAE_EX_ALLGATHER = 4, HDRVAE_EX_RAW_STATS = 8 };
+typedef struct hdrvae_exchange {
+  int32_t kind;                 /* bitmask of HDRVAE_EX_* ; HDRVAE_EX_END: the program is finished */
+  int32_t n_halo;               /* 0..2 buffers */
+  uint64_t halo_first_row_off[2], halo_last_row_off[2];   /* send: first interior row (up), last interior row (down) */
+  uint64_t halo_top_off[2], halo_bottom_off[2];           /* receive: halo row above (from up), below (from down) */
+  uint64_t halo_row_bytes[2];
+  uint64_t allreduce_off, allreduce_count;
+  int32_t n_gather, reserved;
+  uint64_t gather_off[2], gather_bytes_per_rank[2];
+  uint64_t raw_stats_off;
+} hdrvae_exchange;
+typedef struct hdrvae_rows hdrvae_rows;
+
+int hdrvae_rows_workspace_bytes(hdrvae_ctx* ctx, int h, int w, int world, size_t* bytes);
+/* latent_full_nchw: device float32 [1,16,h,w] (the whole latent, every rank has it; 16 MB at 4096^2);
+ * out_rows: device float32 [1, 8h/world, 8w, 3] = this rank's rows of the IMAGE. */
+int hdrvae_rows_begin(hdrvae_ctx* ctx, const float* latent_full_nchw, int h, int w, int rank, int world, int mode,
+                      float expansion_factor, float ev_multiplier, float* out_rows, void* workspace,
+                      size_t workspace_bytes, hdrvae_rows** state);
+/* Enqueue work up to the next exchange point; *ex describes what the host must exchange before calling again. */
+int hdrvae_rows_run(hdrvae_rows* state, hdrvae_exchange* ex, void* stream);
+/* After HDRVAE_EX_END: copy the statistics (global: pre/post/conv/pre3; local slab: out_*, pixel counts) and free. */
+int hdrvae_rows_end(hdrvae_rows* state, hdrvae_stats* stats, void* stream);
+
 /* Decoder only: latent -> SiLU(norm_out(h)), the tensor the reference's forward
  * hook captures (hdr_vae_decode.py:850-855), as device NHWC [B,8h,8w,128] of hdrvae_operand_dtype(ctx) (fp16 by default). */
 int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent_nchw, int B, int h, int w,

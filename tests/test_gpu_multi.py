@@ -44,3 +44,49 @@ def test_batch_sharded_decode_two_gpus_nccl():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] and r[2] for r in res), res
+
+
+def _rows_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from vae_decode_hdr_b200.engine import HdrVaeEngine
+    from vae_decode_hdr_b200.sharding import decode_rows_sharded
+    from vae_decode_hdr_b200.synthetic import random_decoder_state_dict, synthetic_latent
+    eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
+    res = []
+    for (h, w, mode) in [(16, 16, "moderate"), (8, 12, "adaptive_recovery")]:
+        z = synthetic_latent(1, h, w, seed=9).to(dev)
+        out, st = decode_rows_sharded(eng, z, mode, 1.0)
+        whole, st1 = eng.decode(z, mode, 1.0)               # every rank also decodes the whole image alone
+        rows = 8 * h // world
+        mine = whole[:, rank * rows:(rank + 1) * rows]
+        rel = float((out - mine).double().norm() / mine.double().norm())
+        gathered = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(gathered, out.contiguous())
+        full_rel = float((torch.cat(gathered, dim=1) - whole).double().norm() / whole.double().norm())
+        res.append((h, w, rel, full_rel, abs(st["pre_max"] - st1["pre_max"]) / abs(st1["pre_max"])))
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_tiled_decode_two_gpus_nccl():
+    """One image split into two row slabs on two GPUs (halo rows by NCCL send/recv, GroupNorm sums and HDR statistics
+    all-reduced, attention K/V all-gathered) == the single-GPU decode: identical when the slabs tile like the whole
+    image (16x16 latent), within the fp16 decorrelation bound otherwise."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, cases in res:
+        (h0, w0, rel0, full0, dmax0), (h1, w1, rel1, full1, dmax1) = cases
+        assert rel0 < 1e-6 and full0 < 1e-6 and dmax0 < 1e-6, res
+        assert rel1 < 5e-3 and full1 < 5e-3 and dmax1 < 2e-3, res

@@ -167,3 +167,63 @@ def test_batch_sharded_stats_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _rows_exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from vae_decode_hdr_b200 import _native as N
+    from vae_decode_hdr_b200.sharding import _exchange_nccl
+    # a miniature workspace: one slab of 4 interior rows of 16 bytes with a halo row each side at offset 64,
+    # 5 float64 sums at 256, a 3-rank gather region of 8 bytes per rank at 320, a raw statistics block at 384
+    ws = torch.zeros(512, dtype=torch.uint8)
+    row = 16
+    slab = ws[64:64 + 6 * row].view(6, row)
+    slab[1:5] = torch.arange(4, dtype=torch.uint8)[:, None] + 10 * (rank + 1)
+    ws[256:296].view(torch.float64).copy_(torch.arange(5, dtype=torch.float64) + rank)
+    ws[320 + 8 * rank:328 + 8 * rank] = rank + 1
+    vmin, vmax = ws[384:400].view(torch.float32), ws[400:416].view(torch.float32)
+    vsum = ws[416:480].view(torch.float64)
+    vmin.fill_(float(rank)); vmax.fill_(float(rank)); vsum.fill_(float(rank + 1))
+    ex = N.HdrvaeExchange()
+    ex.kind = N.EX_HALO | N.EX_ALLREDUCE_F64
+    ex.n_halo = 1
+    ex.halo_row_bytes[0] = row
+    ex.halo_top_off[0] = 64
+    ex.halo_first_row_off[0] = 64 + row
+    ex.halo_last_row_off[0] = 64 + 4 * row
+    ex.halo_bottom_off[0] = 64 + 5 * row
+    ex.allreduce_off, ex.allreduce_count = 256, 5
+    _exchange_nccl(ex, ws, rank, world)
+    ok = True
+    top = 0 if rank == 0 else 10 * rank + 3                   # the neighbour's last interior row (or untouched)
+    bot = 0 if rank == world - 1 else 10 * (rank + 2)          # the neighbour's first interior row
+    ok &= bool((slab[0] == top).all()) and bool((slab[5] == bot).all())
+    ok &= bool((slab[1:5] == torch.arange(4, dtype=torch.uint8)[:, None] + 10 * (rank + 1)).all())
+    ok &= torch.equal(ws[256:296].view(torch.float64), world * torch.arange(5, dtype=torch.float64) + sum(range(world)))
+    ex2 = N.HdrvaeExchange()
+    ex2.kind = N.EX_ALLGATHER | N.EX_RAW_STATS
+    ex2.n_gather = 1
+    ex2.gather_off[0], ex2.gather_bytes_per_rank[0] = 320, 8
+    ex2.raw_stats_off = 384
+    _exchange_nccl(ex2, ws, rank, world)
+    ok &= torch.equal(ws[320:320 + 8 * world], torch.arange(1, world + 1, dtype=torch.uint8).repeat_interleave(8))
+    ok &= bool((vmin == 0).all()) and bool((vmax == world - 1).all()) and bool((vsum == world * (world + 1) / 2).all())
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_row_tiling_exchange_executor_gloo_world3():
+    """The executor of the row-tiled decode's exchange descriptors (halo send/recv with both neighbours, float64
+    sum all-reduce, all-gather in rank order, MIN/MAX/SUM of the raw statistics block) on 3 CPU ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_rows_exchange_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True), (2, True)]

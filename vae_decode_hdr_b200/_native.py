@@ -41,6 +41,18 @@ class HdrvaeWeightDesc(C.Structure):
                 ("shape", C.c_int64 * 4)]
 
 
+class HdrvaeExchange(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_halo", C.c_int32),
+                ("halo_first_row_off", C.c_uint64 * 2), ("halo_last_row_off", C.c_uint64 * 2),
+                ("halo_top_off", C.c_uint64 * 2), ("halo_bottom_off", C.c_uint64 * 2), ("halo_row_bytes", C.c_uint64 * 2),
+                ("allreduce_off", C.c_uint64), ("allreduce_count", C.c_uint64),
+                ("n_gather", C.c_int32), ("reserved", C.c_int32),
+                ("gather_off", C.c_uint64 * 2), ("gather_bytes_per_rank", C.c_uint64 * 2), ("raw_stats_off", C.c_uint64)]
+
+
+EX_END, EX_HALO, EX_ALLREDUCE_F64, EX_ALLGATHER, EX_RAW_STATS = 0, 1, 2, 4, 8
+
+
 class HdrvaeRawStats(C.Structure):
     _fields_ = [("vmin", C.c_float * RAW_NMIN), ("vmax", C.c_float * RAW_NMAX), ("vsum", C.c_double * RAW_NSUM)]
 
@@ -61,6 +73,10 @@ SIGNATURES = {
     "hdrvae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.POINTER(HdrvaeStats), _vp, _sz, _vp]),
     "hdrvae_decode_begin": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, C.POINTER(_vp), _vp]),
     "hdrvae_decode_finish": (_i, [_vp, _i, _i, _i, _i, _f, _f, _vp, C.POINTER(HdrvaeStats), _vp, _sz, _vp]),
+    "hdrvae_rows_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
+    "hdrvae_rows_begin": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "hdrvae_rows_run": (_i, [_vp, C.POINTER(HdrvaeExchange), _vp]),
+    "hdrvae_rows_end": (_i, [_vp, C.POINTER(HdrvaeStats), _vp]),
     "hdrvae_decode_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "hdrvae_epilogue_scratch_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "hdrvae_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _vp, C.POINTER(HdrvaeStats),

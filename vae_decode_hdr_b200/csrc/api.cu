@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -41,6 +42,8 @@ int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStrea
 int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
                        const int* tap_mask, float scale, cudaStream_t s);
 int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C, int HW, int cpad, cudaStream_t s);
+int launch_latent_rows_to_nhwc(const float* z, void* out, int out_dtype, int C, int h, int w, int y0, int rows, int cpad,
+                               cudaStream_t s);
 int launch_softmax_rows(const float* s, void* p, int p_dtype, float* inv_sum, int n_rows, int n_valid, int n_pad,
                         long long s_ld, long long p_ld, cudaStream_t st);
 int launch_transpose_pad(const void* in, void* out, int rows, int cols, int out_ld, cudaStream_t s);
@@ -59,7 +62,12 @@ hdrvae_stats* epilogue_stats_dev_ptr(void* scratch, int B, int H, int W);
 float* epilogue_post3_ptr(void* scratch, int B, int H, int W);
 float* epilogue_pre3_ptr(void* scratch, int B, int H, int W);
 int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, const float* conv_w, const float* conv_b,
-                            int* argmax3, void* scratch, cudaStream_t s);
+                            int* argmax3, void* scratch, cudaStream_t s, int y_pad = 0, long long img_stride = 0);
+double* gn_sums_ptr(void* scratch, int B, int C, int max_chunks);
+int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n_partials, cudaStream_t s);
+int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
+                              int B, int rows_px, int C, const float* gamma, const float* beta, bool silu, void* scratch,
+                              int max_chunks, double count, cudaStream_t s);
 int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
                             void* scratch, cudaStream_t s);
 
@@ -204,6 +212,9 @@ struct ConvIO {
   float alpha = 1.f;              // accumulator scale (undoes the operand scale of a y2-fed conv)
   float* stats = nullptr;         // GroupNorm partials of y, or null
   int* stats_chunks = nullptr;    // out: partial chunks per image written
+  // row tiling: x / y (and residual, y2) are slabs with this many halo rows stored above and below the H / OH rows;
+  // the pointers address the slab start
+  int x_pad = 0, y_pad = 0;
 };
 
 static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int H, int W, int impl,
@@ -219,19 +230,29 @@ static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int
   memset(&p, 0, sizeof p);
   p.a = io.x;
   p.ab_dtype = pc.w_dtype;
-  p.a_px_stride = pc.cin_pad; p.a_row_stride = (long long)W * pc.cin_pad; p.a_img_stride = (long long)H * W * pc.cin_pad;
+  p.a_px_stride = pc.cin_pad; p.a_row_stride = (long long)W * pc.cin_pad;
+  p.a_img_stride = (long long)(H + 2 * io.x_pad) * W * pc.cin_pad;
+  p.y_pad = io.x_pad;
   p.n_img = B; p.H = H; p.W = W;
   p.k_per_tap = pc.cin_pad;
   p.n_cols = pc.cout;
-  p.out = io.y; p.out_dtype = io.y_dtype;
-  p.bias = pc.bias; p.bias_per_row = 0; p.residual = io.residual; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
+  p.out_dtype = io.y_dtype;
+  p.bias = pc.bias; p.bias_per_row = 0; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
   p.round_tf32 = io.round_tf32 ? 1 : 0;
-  p.out2 = io.y2; p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
+  p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
   p.cta_group = ctx->cta_group;
   choose_tile(H, W, &p);
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
-  p.out_px_stride = pc.cout; p.out_row_stride = (long long)OW * pc.cout; p.out_img_stride = (long long)OH * OW * pc.cout;
+  p.out_px_stride = pc.cout; p.out_row_stride = (long long)OW * pc.cout;
+  p.out_img_stride = (long long)(OH + 2 * io.y_pad) * OW * pc.cout;
+  {
+    // interior of the output slab(s): skip the y_pad halo rows
+    const size_t skip = (size_t)io.y_pad * OW * pc.cout;
+    p.out = reinterpret_cast<uint8_t*>(io.y) + skip * dt_bytes(io.y_dtype);
+    p.residual = io.residual ? reinterpret_cast<const uint8_t*>(io.residual) + skip * dt_bytes(io.res_dtype) : nullptr;
+    p.out2 = io.y2 ? reinterpret_cast<uint8_t*>(io.y2) + skip * 2 : nullptr;
+  }
   const int tiles = p.tiles_x * p.tiles_y;
   p.stats = io.stats;
   p.stats_chunks_per_img = phases * tiles;
@@ -384,56 +405,64 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
   return 0;
 }
 
+// Attention of n_q query rows (q: 16-bit, row stride 1024) against T keys (k: row stride 1024, rows >= T zero up to
+// Tp) and v^T [512][Tp]; o: 16-bit [n_q][512].  Scratch (S, P, 1/sum, split-K partials) comes from the plan.
+static int attention_rows(hdrvae_ctx* ctx, uint8_t* ws, size_t off_s, size_t off_p, size_t off_inv, size_t off_part,
+                          int s_rows, const uint16_t* q, int n_q, const uint16_t* k, const uint16_t* v, int T, int Tp,
+                          uint16_t* o, float qk_alpha, cudaStream_t s) {
+  const int impl = ctx->conv_impl, dt = ctx->op_dtype;
+  float* S = reinterpret_cast<float*>(ws + off_s);
+  uint16_t* P = reinterpret_cast<uint16_t*>(ws + off_p);
+  float* inv = reinterpret_cast<float*>(ws + off_inv);
+  for (int r0 = 0; r0 < n_q; r0 += s_rows) {
+    const int rows = std::min(s_rows, n_q - r0);
+    // S = alpha q k^T, fp32 (the decoder folds 1/sqrt(d) into the q weights: alpha = 1); padded key
+    // columns give 0 and are masked by the softmax
+    HDRVAE_TRY(run_gemm(ctx, dt, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, Tp, Tp, S, Tp, DT_F32, nullptr, false,
+                        qk_alpha, nullptr, impl, s));
+    // P = exp(S - rowmax) (16-bit), inv = 1 / rowsum; O = inv * (P V)
+    HDRVAE_TRY(launch_softmax_rows(S, P, dt, inv, rows, T, Tp, Tp, Tp, s));
+    // A row chunk gives only rows/128 x 2 tiles: when that cannot fill the GPU the K (key) dimension is split
+    // across `splits` images of one GEMM (fp32 partials) and reduced afterwards.
+    const int tiles = ((rows + 127) / 128) * 2;
+    int splits = 1;
+    while (tiles * splits < ctx->num_sms && splits < 32 && (Tp / (splits * 2)) % 128 == 0 &&
+           (long long)rows * splits * 2 <= kSplitRowsBudget)
+      splits *= 2;
+    uint16_t* o_rows = o + (size_t)r0 * 512;
+    if (splits == 1) {
+      HDRVAE_TRY(run_gemm(ctx, dt, P, Tp, rows, Tp, v, Tp, 512, 512, o_rows, 512, dt, nullptr, false, 1.0f, inv, impl, s));
+    } else {
+      float* part = reinterpret_cast<float*>(ws + off_part);
+      const int ks = Tp / splits;
+      GemmParams p;
+      memset(&p, 0, sizeof p);
+      p.a = P; p.ab_dtype = dt;
+      p.a_px_stride = Tp; p.a_row_stride = (long long)rows * Tp; p.a_img_stride = ks;   // image s = K range s
+      p.n_img = splits; p.H = 1; p.W = rows;
+      p.k_per_tap = ks; p.ntaps = 1;
+      p.b = v; p.b_row_stride = Tp; p.b_rows = 512; p.n_cols = 512; p.b_img_k_stride = ks;
+      p.out = part; p.out_dtype = DT_F32;
+      p.out_px_stride = 512; p.out_row_stride = 0; p.out_img_stride = (long long)rows * 512;
+      p.sy = p.sx = 1; p.alpha = 1.0f;
+      p.tw_log2 = 7; p.TW = 128; p.TH = 1; p.tiles_x = (rows + 127) / 128; p.tiles_y = 1;
+      p.cta_group = ctx->cta_group;
+      if (impl == HDRVAE_CONV_DIRECT) HDRVAE_TRY(launch_gemm_direct(p, s));
+      else HDRVAE_TRY(launch_gemm_tc(p, ctx->num_sms, s));
+      HDRVAE_TRY(launch_attn_reduce_splits(part, inv, o_rows, dt, rows, 512, splits, s));
+    }
+  }
+  return 0;
+}
+
 static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const void* qk /*[B][Tp][1024]*/,
                               const void* vt /*[B][512][Tp]*/, void* o /*[B][T][512]*/, float qk_alpha,
                               cudaStream_t s) {
-  const int impl = ctx->conv_impl, dt = ctx->op_dtype;
-  float* S = reinterpret_cast<float*>(ws + pl.off_s);
-  uint16_t* P = reinterpret_cast<uint16_t*>(ws + pl.off_p);
-  float* inv = reinterpret_cast<float*>(ws + pl.off_inv);
   for (int b = 0; b < pl.B; ++b) {
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk) + (size_t)b * pl.Tp * 1024;
-    const uint16_t* k = q + 512;
-    const uint16_t* v = reinterpret_cast<const uint16_t*>(vt) + (size_t)b * 512 * pl.Tp;
-    for (int r0 = 0; r0 < pl.T; r0 += pl.s_rows) {
-      const int rows = std::min(pl.s_rows, pl.T - r0);
-      // S = alpha q k^T, fp32 (the decoder folds 1/sqrt(d) into the q weights: alpha = 1); padded key
-      // columns give 0 and are masked by the softmax
-      HDRVAE_TRY(run_gemm(ctx, dt, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, pl.Tp, pl.Tp, S, pl.Tp, DT_F32,
-                          nullptr, false, qk_alpha, nullptr, impl, s));
-      // P = exp(S - rowmax) (16-bit), inv = 1 / rowsum; O = inv * (P V)
-      HDRVAE_TRY(launch_softmax_rows(S, P, dt, inv, rows, pl.T, pl.Tp, pl.Tp, pl.Tp, s));
-      // O = inv * (P V).  A row chunk gives only rows/128 x 2 tiles: when that cannot fill the GPU the K (key)
-      // dimension is split across `splits` images of one GEMM (fp32 partials) and reduced afterwards.
-      const int tiles = ((rows + 127) / 128) * 2;
-      int splits = 1;
-      while (tiles * splits < ctx->num_sms && splits < 32 && (pl.Tp / (splits * 2)) % 128 == 0 &&
-             (long long)rows * splits * 2 <= kSplitRowsBudget)
-        splits *= 2;
-      uint16_t* o_rows = reinterpret_cast<uint16_t*>(o) + ((size_t)b * pl.T + r0) * 512;
-      if (splits == 1) {
-        HDRVAE_TRY(run_gemm(ctx, dt, P, pl.Tp, rows, pl.Tp, v, pl.Tp, 512, 512, o_rows, 512, dt, nullptr, false, 1.0f,
-                            inv, impl, s));
-      } else {
-        float* part = reinterpret_cast<float*>(ws + pl.off_part);
-        const int ks = pl.Tp / splits;
-        GemmParams p;
-        memset(&p, 0, sizeof p);
-        p.a = P; p.ab_dtype = dt;
-        p.a_px_stride = pl.Tp; p.a_row_stride = (long long)rows * pl.Tp; p.a_img_stride = ks;   // image s = K range s
-        p.n_img = splits; p.H = 1; p.W = rows;
-        p.k_per_tap = ks; p.ntaps = 1;
-        p.b = v; p.b_row_stride = pl.Tp; p.b_rows = 512; p.n_cols = 512; p.b_img_k_stride = ks;
-        p.out = part; p.out_dtype = DT_F32;
-        p.out_px_stride = 512; p.out_row_stride = 0; p.out_img_stride = (long long)rows * 512;
-        p.sy = p.sx = 1; p.alpha = 1.0f;
-        p.tw_log2 = 7; p.TW = 128; p.TH = 1; p.tiles_x = (rows + 127) / 128; p.tiles_y = 1;
-        p.cta_group = ctx->cta_group;
-        if (impl == HDRVAE_CONV_DIRECT) HDRVAE_TRY(launch_gemm_direct(p, s));
-        else HDRVAE_TRY(launch_gemm_tc(p, ctx->num_sms, s));
-        HDRVAE_TRY(launch_attn_reduce_splits(part, inv, o_rows, dt, rows, 512, splits, s));
-      }
-    }
+    HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.s_rows, q, pl.T, q + 512,
+                              reinterpret_cast<const uint16_t*>(vt) + (size_t)b * 512 * pl.Tp, pl.T, pl.Tp,
+                              reinterpret_cast<uint16_t*>(o) + (size_t)b * pl.T * 512, qk_alpha, s));
   }
   return 0;
 }
@@ -513,6 +542,275 @@ static int check_ws(const Plan& pl, void* ws, size_t bytes) {
   return 0;
 }
 
+
+// =================================================================================================== row tiling
+// Step machine of the row-tiled decode (one image, latent rows split over `world` ranks).  Every activation
+// lives in a slab with one halo row above and below; conv outputs get their halo rows from the neighbours
+// (HALO exchange), GroupNorm sums are all-reduced, attention K/V are all-gathered.  See include/hdrvae.h.
+struct RowsPlan {
+  int h, w, hl, world, T, Tl, Tp, s_rows, gn_chunks;
+  size_t off_lat, off_x, off_h, off_t, off_xa, off_xb, off_gn, off_qk, off_v, off_vt, off_o, off_s, off_p, off_inv,
+      off_part, off_epi, total;
+};
+
+static RowsPlan make_rows_plan(int h, int w, int world) {
+  RowsPlan pl;
+  pl.h = h; pl.w = w; pl.world = world; pl.hl = h / world;
+  pl.T = h * w; pl.Tl = pl.hl * w;
+  pl.Tp = (pl.T + 63) / 64 * 64;
+  long long rows = kScoreBudgetElems / pl.Tp;
+  rows = rows / 128 * 128;
+  if (rows < 128) rows = 128;
+  const long long t128 = (pl.Tl + 127) / 128 * 128;
+  if (rows > t128) rows = t128;
+  pl.s_rows = (int)rows;
+  pl.gn_chunks = 1184;
+  for (int l = 1; l <= 8; l *= 2) pl.gn_chunks = std::max(pl.gn_chunks, 4 * tiles_for(l * pl.hl, l * w));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t widest = (size_t)(8 * pl.hl + 2) * 8 * w * 256;           // slab elements incl. halo rows
+  size_t xa = std::max((size_t)(pl.hl + 2) * w * 512, std::max((size_t)(2 * pl.hl + 2) * 2 * w * 512,
+                                                               (size_t)(4 * pl.hl + 2) * 4 * w * 256));
+  pl.off_lat = take((size_t)(pl.hl + 2) * w * 64 * 2);
+  pl.off_x = take(widest * 4);
+  pl.off_h = take(widest * 4);
+  pl.off_t = take(widest * 2);
+  pl.off_xa = take(xa * 2);
+  pl.off_xb = take(widest * 2);
+  pl.off_gn = take(gn_scratch_bytes(1, 512, pl.gn_chunks));
+  pl.off_qk = take((size_t)pl.Tp * 1024 * 2);          // gathered [T][q|k]
+  pl.off_v = take((size_t)pl.Tp * 512 * 2);            // gathered v [T][512]
+  pl.off_vt = take((size_t)512 * pl.Tp * 2);
+  pl.off_o = take((size_t)pl.Tl * 512 * 2);
+  pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
+  pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
+  pl.off_inv = take((size_t)pl.s_rows * 4);
+  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);
+  pl.off_epi = take(epilogue_scratch_bytes(1, 8 * pl.hl, 8 * w));
+  pl.total = off;
+  return pl;
+}
+
+}  // namespace hdrvae
+
+struct hdrvae_rows {
+  hdrvae_ctx* ctx = nullptr;
+  RowsPlan pl;
+  int rank = 0, mode = 0;
+  float factor = 1.f, ev = 1.f;
+  uint8_t* ws = nullptr;
+  const float* latent = nullptr;
+  float* out = nullptr;
+  struct Op { bool exchange; std::function<int(cudaStream_t)> fn; hdrvae_exchange ex; };
+  std::vector<Op> ops;
+  size_t pc = 0;
+  // layer-program state while the op list is being built
+  float* x = nullptr; float* hbuf = nullptr;
+  int H = 0, W = 0, pending = 0;
+};
+
+namespace hdrvae {
+
+static void rows_compute(hdrvae_rows* st, std::function<int(cudaStream_t)> fn) {
+  hdrvae_rows::Op op; op.exchange = false; op.fn = std::move(fn); memset(&op.ex, 0, sizeof op.ex);
+  st->ops.push_back(std::move(op));
+}
+static void rows_exchange(hdrvae_rows* st, const hdrvae_exchange& ex) {
+  hdrvae_rows::Op op; op.exchange = true; op.ex = ex;
+  st->ops.push_back(std::move(op));
+}
+static size_t ws_off(hdrvae_rows* st, const void* p) { return reinterpret_cast<const uint8_t*>(p) - st->ws; }
+
+// halo descriptor of a slab [H+2][W][C] with element size eb
+static void add_halo(hdrvae_rows* st, hdrvae_exchange* ex, const void* slab, int H, int W, int C, int eb) {
+  const int i = ex->n_halo++;
+  const size_t row = (size_t)W * C * eb;
+  const size_t base = ws_off(st, slab);
+  ex->kind |= HDRVAE_EX_HALO;
+  ex->halo_row_bytes[i] = row;
+  ex->halo_top_off[i] = base;
+  ex->halo_first_row_off[i] = base + row;
+  ex->halo_last_row_off[i] = base + (size_t)H * row;
+  ex->halo_bottom_off[i] = base + (size_t)(H + 1) * row;
+}
+
+// zero the halo rows that lie outside the image (true conv padding) of a 16-bit operand slab
+static int zero_border_halos(hdrvae_rows* st, void* slab, int H, int W, int C, int eb, cudaStream_t s) {
+  const size_t row = (size_t)W * C * eb;
+  if (st->rank == 0) HDRVAE_CUDA_OK(cudaMemsetAsync(slab, 0, row, s));
+  if (st->rank == st->pl.world - 1) HDRVAE_CUDA_OK(cudaMemsetAsync(reinterpret_cast<uint8_t*>(slab) + (size_t)(H + 1) * row, 0, row, s));
+  return 0;
+}
+
+// conv epilogue emitted this rank's GroupNorm partials: fold them, then (exchange) all-reduce the sums
+static void rows_stats_and_halo(hdrvae_rows* st, const void* slab_f32, int H, int W, int C, const void* slab16, int C16) {
+  hdrvae_ctx* ctx = st->ctx;
+  void* gn = st->ws + st->pl.off_gn;
+  const int gn_chunks = st->pl.gn_chunks;
+  int* pending = &st->pending;
+  rows_compute(st, [=](cudaStream_t s) { return launch_gn_reduce_partials(gn, 1, 512, gn_chunks, *pending, s); });
+  hdrvae_exchange ex;
+  memset(&ex, 0, sizeof ex);
+  add_halo(st, &ex, slab_f32, H, W, C, 4);
+  if (slab16 != nullptr) add_halo(st, &ex, slab16, H, W, C16, 2);
+  ex.kind |= HDRVAE_EX_ALLREDUCE_F64;
+  ex.allreduce_off = ws_off(st, gn_sums_ptr(gn, 1, 512, gn_chunks));
+  ex.allreduce_count = 32 * 2;
+  rows_exchange(st, ex);
+  (void)ctx;
+}
+
+// t = [silu](GroupNorm(x)) over the whole slab (halo rows included: GroupNorm is elementwise once the global
+// statistics are known), then restore the zero padding at the image borders
+static void rows_gn(hdrvae_rows* st, const float* x_slab, const NormW& nw, bool silu, int H, int W) {
+  hdrvae_ctx* ctx = st->ctx;
+  void* gn = st->ws + st->pl.off_gn;
+  void* t = st->ws + st->pl.off_t;
+  const int gn_chunks = st->pl.gn_chunks;
+  const double count = (double)H * st->pl.world * (double)W * (double)(nw.C / 32);
+  const NormW n = nw;
+  rows_compute(st, [=](cudaStream_t s) {
+    const long long slab = (long long)(H + 2) * W * n.C;
+    HDRVAE_TRY(launch_gn_apply_from_sums(x_slab, DT_F32, slab, t, ctx->op_dtype, slab, 1, (H + 2) * W, n.C, n.gamma, n.beta,
+                                         silu, gn, gn_chunks, count, s));
+    return zero_border_halos(st, t, H, W, n.C, 2, s);
+  });
+}
+
+static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
+  hdrvae_ctx* ctx = st->ctx;
+  void* t = st->ws + st->pl.off_t;
+  void* xa = st->ws + st->pl.off_xa;
+  void* xb = st->ws + st->pl.off_xb;
+  float* stats = reinterpret_cast<float*>(st->ws + st->pl.off_gn);
+  int* pending = &st->pending;
+  float* x = st->x; float* hb = st->hbuf;
+  const ResW* r = &rw;
+  rows_gn(st, x, rw.n1, true, H, W);
+  rows_compute(st, [=](cudaStream_t s) {
+    ConvIO io; io.x = t; io.y = hb; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
+    return run_conv(ctx, r->c1, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
+  });
+  rows_stats_and_halo(st, hb, H, W, rw.c1.cout, nullptr, 0);
+  rows_gn(st, hb, rw.n2, true, H, W);
+  float* out = rw.has_nin ? hb : x;
+  rows_compute(st, [=](cudaStream_t s) {
+    if (r->has_nin) {
+      ConvIO sc; sc.x = xb; sc.y = hb; sc.alpha = 1.0f / kRawOperandScale; sc.x_pad = sc.y_pad = 1;
+      HDRVAE_TRY(run_conv(ctx, r->nin, sc, 1, H, W, HDRVAE_CONV_TCGEN05, s));
+    }
+    ConvIO io; io.x = t; io.y = out; io.residual = out; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
+    if (r->dual_out) { io.y2 = xa; io.y2_dtype = ctx->op_dtype; io.y2_scale = kRawOperandScale; }
+    HDRVAE_TRY(run_conv(ctx, r->c2, io, 1, H, W, HDRVAE_CONV_TCGEN05, s));
+    if (r->dual_out) HDRVAE_TRY(zero_border_halos(st, xa, H, W, r->c2.cout, 2, s));
+    return 0;
+  });
+  rows_stats_and_halo(st, out, H, W, rw.c2.cout, rw.dual_out ? xa : nullptr, rw.c2.cout);
+  if (rw.has_nin) std::swap(st->x, st->hbuf);
+}
+
+static int build_rows_program(hdrvae_rows* st) {
+  hdrvae_ctx* ctx = st->ctx;
+  const RowsPlan& pl = st->pl;
+  const int dt = ctx->op_dtype;
+  uint8_t* ws = st->ws;
+  void* lat = ws + pl.off_lat;
+  void* t = ws + pl.off_t;
+  void* xa = ws + pl.off_xa;
+  void* xb = ws + pl.off_xb;
+  float* stats = reinterpret_cast<float*>(ws + pl.off_gn);
+  int* pending = &st->pending;
+  st->x = reinterpret_cast<float*>(ws + pl.off_x);
+  st->hbuf = reinterpret_cast<float*>(ws + pl.off_h);
+  int H = pl.hl, W = pl.w;
+  const int rank = st->rank;
+  const float* latent = st->latent;
+
+  {
+    float* x = st->x;
+    rows_compute(st, [=](cudaStream_t s) {
+      // latent rows of this rank plus one neighbour row each side (rows outside the image are zero)
+      HDRVAE_TRY(launch_latent_rows_to_nhwc(latent, lat, dt, 16, pl.h, pl.w, rank * pl.hl - 1, pl.hl + 2, 64, s));
+      ConvIO io; io.x = lat; io.y = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
+      return run_conv(ctx, ctx->conv_in, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
+    });
+    rows_stats_and_halo(st, x, H, W, 512, nullptr, 0);
+  }
+  rows_res(st, ctx->mid1, H, W);
+  {
+    // mid.attn_1 is global: q for this rank's tokens, K and V of all tokens (all-gather)
+    uint16_t* qk = reinterpret_cast<uint16_t*>(ws + pl.off_qk);
+    uint16_t* vb = reinterpret_cast<uint16_t*>(ws + pl.off_v);
+    uint16_t* vt = reinterpret_cast<uint16_t*>(ws + pl.off_vt);
+    uint16_t* o = reinterpret_cast<uint16_t*>(ws + pl.off_o);
+    float* x = st->x;
+    rows_gn(st, x, ctx->attn_norm, false, H, W);
+    rows_compute(st, [=](cudaStream_t s) {
+      const uint16_t* tl = reinterpret_cast<const uint16_t*>(t) + (size_t)W * 512;      // interior rows of the slab
+      if (pl.Tp != pl.T) {
+        HDRVAE_CUDA_OK(cudaMemsetAsync(qk, 0, (size_t)pl.Tp * 1024 * 2, s));
+        HDRVAE_CUDA_OK(cudaMemsetAsync(vt, 0, (size_t)512 * pl.Tp * 2, s));
+      }
+      HDRVAE_TRY(run_gemm(ctx, dt, tl, 512, pl.Tl, 512, ctx->qk.w[0], 512, 1024, 1024, qk + (size_t)rank * pl.Tl * 1024, 1024, dt,
+                          ctx->qk.bias, false, 1.0f, nullptr, HDRVAE_CONV_TCGEN05, s));
+      return run_gemm(ctx, dt, tl, 512, pl.Tl, 512, ctx->vproj.w[0], 512, 512, 512, vb + (size_t)rank * pl.Tl * 512, 512, dt,
+                      ctx->vproj.bias, false, 1.0f, nullptr, HDRVAE_CONV_TCGEN05, s);
+    });
+    hdrvae_exchange ex;
+    memset(&ex, 0, sizeof ex);
+    ex.kind = HDRVAE_EX_ALLGATHER;
+    ex.n_gather = 2;
+    ex.gather_off[0] = pl.off_qk; ex.gather_bytes_per_rank[0] = (size_t)pl.Tl * 1024 * 2;
+    ex.gather_off[1] = pl.off_v;  ex.gather_bytes_per_rank[1] = (size_t)pl.Tl * 512 * 2;
+    rows_exchange(st, ex);
+    rows_compute(st, [=](cudaStream_t s) {
+      HDRVAE_TRY(launch_transpose_pad(vb, vt, pl.T, 512, pl.Tp, s));
+      HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.s_rows, qk + (size_t)rank * pl.Tl * 1024,
+                                pl.Tl, qk + 512, vt, pl.T, pl.Tp, o, 1.0f, s));
+      ConvIO io; io.x = o; io.y = x; io.residual = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = 0; io.y_pad = 1;
+      return run_conv(ctx, ctx->proj_out, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
+    });
+    rows_stats_and_halo(st, x, H, W, 512, nullptr, 0);
+  }
+  rows_res(st, ctx->mid2, H, W);
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    for (int i = 0; i < 3; ++i) rows_res(st, ctx->up[lvl][i], H, W);
+    if (lvl != 0) {
+      float* hb = st->hbuf;
+      const PackedConv* up = &ctx->upsample[lvl];
+      const int Hc = H, Wc = W;
+      rows_compute(st, [=](cudaStream_t s) {
+        ConvIO io; io.x = xa; io.y = hb; io.alpha = 1.0f / kRawOperandScale; io.x_pad = io.y_pad = 1;
+        if (lvl <= 2) { io.y2 = xb; io.y2_dtype = dt; io.y2_scale = kRawOperandScale; }
+        io.stats = stats; io.stats_chunks = pending;
+        return run_conv(ctx, *up, io, 1, Hc, Wc, HDRVAE_CONV_TCGEN05, s);
+      });
+      H *= 2; W *= 2;
+      rows_stats_and_halo(st, hb, H, W, up->cout, nullptr, 0);
+      std::swap(st->x, st->hbuf);
+    }
+  }
+  {
+    float* x = st->x;
+    rows_gn(st, x, ctx->norm_out, true, H, W);
+    void* epi = ws + pl.off_epi;
+    rows_compute(st, [=](cudaStream_t s) {
+      const uint16_t* pre = reinterpret_cast<const uint16_t*>(t) + (size_t)W * 128;      // interior row 0
+      return launch_epilogue_phase_a(pre, dt, 1, H, W, ctx->conv_out_w, ctx->conv_out_b, nullptr, epi, s, 1,
+                                     (long long)(H + 2) * W * 128);
+    });
+    hdrvae_exchange ex;
+    memset(&ex, 0, sizeof ex);
+    ex.kind = HDRVAE_EX_RAW_STATS;
+    ex.raw_stats_off = ws_off(st, epilogue_raw_stats_ptr(epi, 1, H, W));
+    rows_exchange(st, ex);
+    rows_compute(st, [=](cudaStream_t s) {
+      return launch_epilogue_phase_b(1, H, W, st->mode, st->factor, st->ev, st->out, nullptr, epi, s);
+    });
+  }
+  return 0;
+}
+
 }  // namespace hdrvae
 
 // =================================================================================================== C ABI
@@ -549,7 +847,8 @@ int hdrvae_destroy(hdrvae_ctx* ctx) {
   return 0;
 }
 
-static_assert(sizeof(hdrvae_stats) == 200 && sizeof(hdrvae_raw_stats) == 96, "ABI struct layout changed");
+static_assert(sizeof(hdrvae_stats) == 200 && sizeof(hdrvae_raw_stats) == 96 && sizeof(hdrvae_exchange) == 152,
+              "ABI struct layout changed");
 
 long long hdrvae_launch_count(void) { return g_launch_count; }
 
@@ -804,6 +1103,68 @@ int hdrvae_decode(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, int
     HDRVAE_CUDA_OK(cudaStreamSynchronize(s));
   }
   return 0;
+}
+
+int hdrvae_rows_workspace_bytes(hdrvae_ctx* ctx, int h, int w, int world, size_t* bytes) {
+  HDRVAE_REQUIRE(ctx && bytes && h >= 1 && w >= 1 && world >= 1, "hdrvae_rows_workspace_bytes: bad argument");
+  HDRVAE_REQUIRE(h % world == 0, "row tiling needs the latent height (%d) to be a multiple of the rank count (%d)", h, world);
+  *bytes = make_rows_plan(h, w, world).total;
+  return 0;
+}
+
+int hdrvae_rows_begin(hdrvae_ctx* ctx, const float* latent_full, int h, int w, int rank, int world, int mode,
+                      float expansion_factor, float ev_multiplier, float* out_rows, void* workspace, size_t ws_bytes,
+                      hdrvae_rows** state) {
+  HDRVAE_REQUIRE(ctx && latent_full && out_rows && workspace && state, "hdrvae_rows_begin: null argument");
+  HDRVAE_REQUIRE(ctx->loaded, "hdrvae: weights not loaded");
+  HDRVAE_REQUIRE(h >= 1 && w >= 1 && world >= 1 && rank >= 0 && rank < world && h % world == 0,
+                 "hdrvae_rows_begin: latent height %d must split evenly over %d ranks (rank %d)", h, world, rank);
+  HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_rows_begin: bad mode %d", mode);
+  HDRVAE_REQUIRE(ctx->conv_impl == HDRVAE_CONV_TCGEN05, "row tiling runs on the tcgen05 kernels only");
+  hdrvae_rows* st = new hdrvae_rows();
+  st->ctx = ctx;
+  st->pl = make_rows_plan(h, w, world);
+  if (ws_bytes < st->pl.total || (reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) {
+    set_error("hdrvae_rows_begin: workspace too small or misaligned (%zu < %zu bytes)", ws_bytes, st->pl.total);
+    delete st;
+    return -2;
+  }
+  st->rank = rank; st->mode = mode; st->factor = expansion_factor; st->ev = ev_multiplier;
+  st->ws = reinterpret_cast<uint8_t*>(workspace);
+  st->latent = latent_full;
+  st->out = out_rows;
+  int r = build_rows_program(st);
+  if (r != 0) { delete st; return r; }
+  *state = st;
+  return 0;
+}
+
+int hdrvae_rows_run(hdrvae_rows* st, hdrvae_exchange* ex, void* stream) {
+  HDRVAE_REQUIRE(st && ex, "hdrvae_rows_run: null argument");
+  HDRVAE_CUDA_OK(cudaSetDevice(st->ctx->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  memset(ex, 0, sizeof *ex);
+  while (st->pc < st->ops.size()) {
+    hdrvae_rows::Op& op = st->ops[st->pc++];
+    if (op.exchange) { *ex = op.ex; return 0; }
+    HDRVAE_TRY(op.fn(s));
+  }
+  ex->kind = HDRVAE_EX_END;
+  return 0;
+}
+
+int hdrvae_rows_end(hdrvae_rows* st, hdrvae_stats* stats, void* stream) {
+  if (st == nullptr) return 0;
+  int r = 0;
+  if (stats != nullptr) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(stats, epilogue_stats_dev_ptr(st->ws + st->pl.off_epi, 1, 8 * st->pl.hl, 8 * st->pl.w),
+                                    sizeof(hdrvae_stats), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("hdrvae_rows_end: %s", cudaGetErrorString(e)); r = -1; }
+  }
+  delete st;
+  return r;
 }
 
 int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, void* features, void* workspace,

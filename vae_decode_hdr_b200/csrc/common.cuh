@@ -63,6 +63,8 @@ struct GemmParams {
   int b_rows;       // rows of B that exist in memory (0: same as n_cols); rows beyond are zero-filled by TMA
   int ab_dtype;
   int n_img, H, W;  // source grid of the M dimension
+  int y_pad;        // halo rows stored above/below the H rows of A (row tiling): `a` points at the slab start, the
+                    // A rows addressed are y + dy + y_pad of H + 2*y_pad stored rows (0: vertical padding by TMA zero fill)
   int k_per_tap;    // elements; multiple of one 128-byte row (64 for 16-bit operands, 32 for tf32)
   int ntaps;
   int tap_dy[9], tap_dx[9];

@@ -108,7 +108,8 @@ template <typename T, bool kArgmax>
 __global__ void __launch_bounds__(kEpiThreads, 2)
 hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /*OIHW [3][128][3][3]*/,
                    const float* __restrict__ conv_b, int H, int W, float* __restrict__ post3,
-                   float* __restrict__ pre3, int* __restrict__ argmax3, PartialA* __restrict__ partials) {
+                   float* __restrict__ pre3, int* __restrict__ argmax3, PartialA* __restrict__ partials, int y_pad,
+                   long long img_stride) {
   extern __shared__ float sm[];
   float4* wsm = reinterpret_cast<float4*>(sm);                 // [9][128] (w_r, w_g, w_b, 0)
   float* tile = sm + 9 * kC * 4;                               // [kChunk][kChanStride]: [channel][row][col]
@@ -134,7 +135,8 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
   }
   float smin = INFINITY, smax = -INFINITY, ssum = 0.f, ssq = 0.f;      // pre stats (this thread's loads)
 
-  const T* img_base = pre + (long long)img * H * W * kC;
+  // `pre` points at interior row 0; y_pad halo rows above/below hold the neighbour ranks' rows (row tiling)
+  const T* img_base = pre + (long long)img * img_stride;
   // Staging loads are software-pipelined for the 16-bit input types (the product path): the raw 8-byte pieces of
   // chunk k+1 are fetched into registers while chunk k is being computed (ncu: the convert-after-load was 28 % of
   // all stall samples); fp32 input (parity entry) loads in place.
@@ -146,7 +148,7 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
     const int tp = i - quad * kTilePx;
     const int tx = tp % kHaloW, ty = tp / kHaloW;
     const int sx = x0 + tx - 1, sy = y0 + ty - 1;
-    *ok = i < kTilePx * (kChunk / 4) && sx >= 0 && sx < W && sy >= 0 && sy < H;
+    *ok = i < kTilePx * (kChunk / 4) && sx >= 0 && sx < W && sy >= -y_pad && sy < H + y_pad;
     return img_base + ((long long)sy * W + sx) * kC + ch0 + quad * 4;
   };
   if (kPrefetch) {
@@ -170,10 +172,10 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
       const int tx = tp % kHaloW, ty = tp / kHaloW;
       const int sx = x0 + tx - 1, sy = y0 + ty - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
+      if (sx >= 0 && sx < W && sy >= -y_pad && sy < H + y_pad) {
         if (kPrefetch) v = Cvt4<T>::cvt(pf[u]);
         else v = Load4<T>::ld(img_base + ((long long)sy * W + sx) * kC + ch0 + quad * 4);
-        if (tx >= 1 && tx <= kTileW && ty >= 1 && ty <= kTileH) {      // interior pixel: owned by this block
+        if (tx >= 1 && tx <= kTileW && ty >= 1 && ty <= kTileH && sy >= 0 && sy < H) {   // pixel owned by this block
           smin = fminf(smin, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
           smax = fmaxf(smax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
           ssum += (v.x + v.y) + (v.z + v.w);
@@ -521,7 +523,7 @@ float* epilogue_pre3_ptr(void* scratch, int B, int H, int W) { return carve(scra
 
 template <typename T>
 static void launch_phase_a(const void* pre, const float* conv_w, const float* conv_b, int H, int W, float* post3, float* pre3,
-                           int* argmax3, PartialA* pa, dim3 grid, size_t smem, cudaStream_t s) {
+                           int* argmax3, PartialA* pa, dim3 grid, size_t smem, int y_pad, long long img_stride, cudaStream_t s) {
   static bool set = false;
   if (!set) {
     cudaFuncSetAttribute(hdr_phase_a_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -529,23 +531,24 @@ static void launch_phase_a(const void* pre, const float* conv_w, const float* co
     set = true;
   }
   if (argmax3 != nullptr)
-    hdr_phase_a_kernel<T, true><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, argmax3, pa);
+    hdr_phase_a_kernel<T, true><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, argmax3, pa, y_pad, img_stride);
   else
-    hdr_phase_a_kernel<T, false><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, nullptr, pa);
+    hdr_phase_a_kernel<T, false><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, nullptr, pa, y_pad, img_stride);
 }
 
 int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, const float* conv_w, const float* conv_b,
-                            int* argmax3, void* scratch, cudaStream_t s) {
+                            int* argmax3, void* scratch, cudaStream_t s, int y_pad, long long img_stride) {
+  if (img_stride == 0) img_stride = (long long)H * W * kC;
   EpilogueScratch e = carve(scratch, B, H, W);
   const dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH), B);
   HDRVAE_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "epilogue: image too large for the launch grid");
   const size_t smem = (9 * kC * 4 + kChunk * kChanStride) * sizeof(float);
   if (dtype == HDRVAE_F32) {
-    launch_phase_a<float>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, s);
+    launch_phase_a<float>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, y_pad, img_stride, s);
   } else if (dtype == HDRVAE_BF16) {
-    launch_phase_a<__nv_bfloat16>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, s);
+    launch_phase_a<__nv_bfloat16>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, y_pad, img_stride, s);
   } else if (dtype == HDRVAE_F16) {
-    launch_phase_a<__half>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, s);
+    launch_phase_a<__half>(pre, conv_w, conv_b, H, W, e.post3, e.pre3, argmax3, e.pa, grid, smem, y_pad, img_stride, s);
   } else {
     HDRVAE_REQUIRE(false, "epilogue: unsupported activation dtype %d", dtype);
   }

@@ -183,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int kb = kbl - t * kb_per_tap;
               uint8_t* sa = smem_a + (stage * KSUB + j) * kABytes;
               uint8_t* sb = smem_b + (stage * KSUB + j) * Cfg::kBBytes;
-              const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t];
+              const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t] + p.y_pad;
               if (CG == 2) {
                 ptx::tma_load_4d_pair(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, xs, ys, img);
                 ptx::tma_load_2d_pair(sb, &tmB, &full_bar[stage], bk0 + kbl * kElemsPerRow, n0);
@@ -485,7 +485,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps) {
                  "gemm_tc: strides must be multiples of 16 bytes");
   {
     // A: {C, W, H, N}; the channel extent visible to TMA is k_per_tap (columns beyond are never addressed)
-    cuuint64_t dims[4] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.n_img};
+    cuuint64_t dims[4] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * eb, (cuuint64_t)p.a_row_stride * eb,
                              (cuuint64_t)p.a_img_stride * eb};
     cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
@@ -578,7 +578,10 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
   const bool tf32 = p.ab_dtype == DT_F32;
   static int cg = -1;                                       // CTA pairs by default; HDRVAE_CTA_GROUP=1 selects single CTAs
   if (cg < 0) { const char* e = getenv("HDRVAE_CTA_GROUP"); cg = (e && atoi(e) == 1) ? 1 : 2; }
-  const int use_cg = p.cta_group > 0 ? p.cta_group : cg;
+  int use_cg = p.cta_group > 0 ? p.cta_group : cg;
+  // A CTA pair shares one B tile, so with a per-image K offset into B (split-K) both m-tiles of a pair must
+  // belong to the same image: an odd number of tiles per image runs as single CTAs.
+  if (p.b_img_k_stride != 0 && (p.tiles_x * p.tiles_y) % 2 != 0) use_cg = 1;
   const bool n128 = p.n_cols <= 128;
   if (use_cg == 2 && !tf32) {
     // specialised epilogues for what the decoder launches; anything else takes the generic build

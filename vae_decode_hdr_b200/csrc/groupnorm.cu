@@ -141,7 +141,8 @@ __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __
 template <typename TIn, typename TOut, bool kSilu>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ scale,
-                const float* __restrict__ shift, int HW, int C, int px_per_block) {
+                const float* __restrict__ shift, int HW, int C, int px_per_block, long long x_img_stride,
+                long long y_img_stride) {
   extern __shared__ float tab[];   // [2][C]
   const int img = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
@@ -158,8 +159,8 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = tab[vi * 8 + j]; b[j] = tab[C + vi * 8 + j]; }
-  const TIn* xin = x + (long long)img * HW * C;
-  TOut* yout = y + (long long)img * HW * C;
+  const TIn* xin = x + (long long)img * x_img_stride;
+  TOut* yout = y + (long long)img * y_img_stride;
   // 4 pixels per iteration: all loads are issued before the first use (memory-level parallelism)
   int p = p0 + p_off;
   for (; p + 3 * p_step < p1; p += 4 * p_step) {
@@ -188,9 +189,8 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
   }
 }
 
-// scratch layout: [partials: B * max_chunks * 64 floats][scale: B*C][shift: B*C]
 size_t gn_scratch_bytes(int B, int C, int max_chunks) {
-  return ((size_t)B * max_chunks * kGroups * 2 + (size_t)2 * B * C) * sizeof(float);
+  return ((size_t)B * max_chunks * kGroups * 2 + (size_t)2 * B * C + 2) * sizeof(float) + (size_t)B * kGroups * 2 * sizeof(double);
 }
 
 static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* px_per_block) {
@@ -206,17 +206,89 @@ static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* 
   *chunks = (HW + ppb - 1) / ppb;
 }
 
+static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* px_per_block);
+
 template <typename TIn, typename TOut>
 static void launch_apply(const void* x, void* y, const float* scale, const float* shift, int B, int HW, int C, int chunks,
-                         int ppb, bool silu, cudaStream_t s) {
+                         int ppb, bool silu, long long xs, long long ys, cudaStream_t s) {
   const dim3 grid(chunks, B);
   const size_t sm = 2 * C * sizeof(float);
   if (silu)
     gn_apply_kernel<TIn, TOut, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                  scale, shift, HW, C, ppb);
+                                                                  scale, shift, HW, C, ppb, xs, ys);
   else
     gn_apply_kernel<TIn, TOut, false><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                   scale, shift, HW, C, ppb);
+                                                                   scale, shift, HW, C, ppb, xs, ys);
+}
+
+// Row tiling: the statistics of a (image, group) are sums over ALL ranks' rows.  gn_reduce_partials folds this
+// rank's conv-emitted partials into sums[B][32][2] (double, fixed order); the host all-reduces that block (SUM);
+// gn_finalize_sums turns the global sums into per-(image, channel) scale / shift.
+__global__ void __launch_bounds__(256)
+gn_reduce_partials_kernel(const float* __restrict__ partial, int n_chunks, double* __restrict__ sums) {
+  const int g = blockIdx.x, img = blockIdx.y;
+  __shared__ double rs[256], rq[256];
+  double s = 0.0, q = 0.0;
+  for (int c = threadIdx.x; c < n_chunks; c += 256) {
+    const float2 pp = *reinterpret_cast<const float2*>(partial + ((long long)img * n_chunks + c) * (kGroups * 2) + g * 2);
+    s += (double)pp.x;
+    q += (double)pp.y;
+  }
+  rs[threadIdx.x] = s; rq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sums[((long long)img * kGroups + g) * 2] = rs[0]; sums[((long long)img * kGroups + g) * 2 + 1] = rq[0]; }
+}
+__global__ void gn_finalize_sums_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
+                                        int C, double count, float eps) {
+  const int img = blockIdx.x;
+  const int cpg = C / kGroups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = sums[((long long)img * kGroups + g) * 2] / count;
+    double var = sums[((long long)img * kGroups + g) * 2 + 1] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float a = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+    scale[(long long)img * C + c] = a;
+    shift[(long long)img * C + c] = beta[c] - (float)mean * a;
+  }
+}
+// scratch layout (gn_scratch_bytes): [partials: B*max_chunks*64 floats][sums: B*64 doubles][scale: B*C][shift: B*C]
+double* gn_sums_ptr(void* scratch, int B, int C, int max_chunks) {
+  (void)C;
+  return reinterpret_cast<double*>(reinterpret_cast<float*>(scratch) + (size_t)B * max_chunks * kGroups * 2);
+}
+static float* gn_scale_ptr(void* scratch, int B, int max_chunks) {
+  return reinterpret_cast<float*>(gn_sums_ptr(scratch, B, 0, max_chunks) + (size_t)B * kGroups * 2);
+}
+int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n_partials, cudaStream_t s) {
+  gn_reduce_partials_kernel<<<dim3(kGroups, B), 256, 0, s>>>(reinterpret_cast<const float*>(scratch), n_partials,
+                                                             gn_sums_ptr(scratch, B, C, max_chunks));
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// x / y point at the first row to normalise; rows_px = pixels per image to process; count = elements per (image, group)
+// over ALL ranks
+int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
+                              int B, int rows_px, int C, const float* gamma, const float* beta, bool silu, void* scratch,
+                              int max_chunks, double count, cudaStream_t s) {
+  HDRVAE_REQUIRE(x_dtype == DT_F32 && (y_dtype == DT_F16 || y_dtype == DT_BF16), "groupnorm (row tiling): fp32 in, 16-bit out");
+  float* scale = gn_scale_ptr(scratch, B, max_chunks);
+  float* shift = scale + (size_t)B * C;
+  gn_finalize_sums_kernel<<<B, 256, 0, s>>>(gn_sums_ptr(scratch, B, C, max_chunks), gamma, beta, scale, shift, C, count, 1e-6f);
+  HDRVAE_LAUNCHED();
+  int chunks, ppb;
+  gn_chunking(B, rows_px, C, max_chunks, &chunks, &ppb);
+  if (y_dtype == DT_F16) launch_apply<float, __half>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s);
+  else launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // partial_chunks > 0: the statistics partials [B][partial_chunks][32][2] are already in the scratch buffer
@@ -229,7 +301,7 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
   int chunks, ppb;
   gn_chunking(B, HW, C, max_chunks, &chunks, &ppb);
   float* partial = reinterpret_cast<float*>(scratch);
-  float* scale = partial + (size_t)B * max_chunks * kGroups * 2;
+  float* scale = gn_scale_ptr(scratch, B, max_chunks);
   float* shift = scale + (size_t)B * C;
   int n_partials = partial_chunks;
   if (partial_chunks <= 0) {
@@ -246,13 +318,13 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   if (y_dtype == DT_F16) {
-    if (x_dtype == DT_F32) launch_apply<float, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
-    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
-    else launch_apply<__half, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+    if (x_dtype == DT_F32) launch_apply<float, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    else launch_apply<__half, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
   } else {
-    if (x_dtype == DT_F32) launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
-    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
-    else launch_apply<__half, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, s);
+    if (x_dtype == DT_F32) launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    else launch_apply<__half, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
   }
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());

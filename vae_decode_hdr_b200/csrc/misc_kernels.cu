@@ -97,6 +97,33 @@ int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C
   return 0;
 }
 
+// ------------------------------------------------------------------ latent row slab (row tiling)
+// full latent NCHW fp32 [C][h][w] -> NHWC 16-bit slab [rows][w][cpad] holding latent rows y0 .. y0+rows-1;
+// rows outside the image and the padding channels are zero.
+__global__ void latent_rows_to_nhwc_kernel(const float* __restrict__ z, void* __restrict__ out, int out_dtype, int C,
+                                           int h, int w, int y0, int rows, int cpad) {
+  const long long total = (long long)rows * w * cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const long long p = i / cpad;
+    const int x = (int)(p % w);
+    const int y = y0 + (int)(p / w);
+    const float v = (c < C && y >= 0 && y < h) ? z[((long long)c * h + y) * w + x] : 0.f;
+    if (out_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+  }
+}
+int launch_latent_rows_to_nhwc(const float* z, void* out, int out_dtype, int C, int h, int w, int y0, int rows, int cpad,
+                               cudaStream_t s) {
+  const long long total = (long long)rows * w * cpad;
+  int grid = ceil_div(total, 256);
+  if (grid > 2368) grid = 2368;
+  latent_rows_to_nhwc_kernel<<<grid, 256, 0, s>>>(z, out, out_dtype, C, h, w, y0, rows, cpad);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ CUDA-core validation conv (same GemmParams)
 // One thread per output element; used only to validate the tcgen05 kernel on the GPU
 // (HDRVAE_CONV_DIRECT), never on the product path.
@@ -119,8 +146,8 @@ __global__ void gemm_direct_kernel(const GemmParams p) {
     float acc = 0.f;
     if (!(p.b_rows > 0 && col >= p.b_rows)) {
       for (int t = 0; t < p.ntaps; ++t) {
-        const int ys = y + p.tap_dy[t], xs = x + p.tap_dx[t];
-        if (ys < 0 || ys >= p.H || xs < 0 || xs >= p.W) continue;
+        const int ys = y + p.tap_dy[t] + p.y_pad, xs = x + p.tap_dx[t];
+        if (ys < 0 || ys >= p.H + 2 * p.y_pad || xs < 0 || xs >= p.W) continue;
         const long long ao = img * p.a_img_stride + ys * p.a_row_stride + xs * p.a_px_stride;
         const long long bo = col * p.b_row_stride + (long long)t * p.k_per_tap + img * p.b_img_k_stride;
         for (int c = 0; c < p.k_per_tap; ++c) {

@@ -178,6 +178,43 @@ class HdrVaeEngine:
                                                   ws.data_ptr(), ws.numel(), self._stream()), "hdrvae_decode_finish")
         return out, (st.as_dict() if want_stats else None)
 
+    # -- spatial row tiling (one image split over ranks): step program driven by sharding.py ----------------
+    def rows_workspace_bytes(self, h: int, w: int, world: int) -> int:
+        n = C.c_size_t()
+        N.check(self.lib.hdrvae_rows_workspace_bytes(self._ctx, h, w, world, C.byref(n)), "hdrvae_rows_workspace_bytes")
+        return int(n.value)
+
+    def rows_begin(self, latent_full: torch.Tensor, rank: int, world: int, hdr_mode: str, ev_multiplier: float,
+                   workspace: Optional[torch.Tensor] = None):
+        """-> (state handle, workspace uint8 tensor, out tensor [1, 8h/world, 8w, 3])."""
+        B, h, w = self._check_latent(latent_full)
+        if B != 1:
+            raise ValueError("row tiling decodes one image (shard batches with decode_batch_sharded)")
+        if h % world:
+            raise ValueError(f"latent height {h} must be a multiple of the number of ranks {world}")
+        mode, factor = resolve_mode(hdr_mode)
+        with torch.cuda.device(self.device):
+            z = latent_full.to(device=self.device, dtype=torch.float32).contiguous()
+            need = self.rows_workspace_bytes(h, w, world)
+            ws = workspace if workspace is not None else torch.empty(need, dtype=torch.uint8, device=self.device)
+            out = torch.empty((1, 8 * h // world, 8 * w, 3), dtype=torch.float32, device=self.device)
+            state = C.c_void_p()
+            N.check(self.lib.hdrvae_rows_begin(self._ctx, z.data_ptr(), h, w, rank, world, mode, factor, float(ev_multiplier),
+                                               out.data_ptr(), ws.data_ptr(), ws.numel(), C.byref(state)), "hdrvae_rows_begin")
+        return state, ws, out, z
+
+    def rows_run(self, state) -> "N.HdrvaeExchange":
+        ex = N.HdrvaeExchange()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.hdrvae_rows_run(state, C.byref(ex), self._stream()), "hdrvae_rows_run")
+        return ex
+
+    def rows_end(self, state, want_stats: bool = True):
+        st = N.HdrvaeStats() if want_stats else None
+        with torch.cuda.device(self.device):
+            N.check(self.lib.hdrvae_rows_end(state, C.byref(st) if want_stats else None, self._stream()), "hdrvae_rows_end")
+        return st.as_dict() if want_stats else None
+
     def decode_features(self, latent: torch.Tensor) -> torch.Tensor:
         """Decoder only -> NHWC [B,8h,8w,128] in the operand dtype (fp16 by default) = the tensor the reference's
         hook captures (:850-855)."""

@@ -54,3 +54,99 @@ def decode_batch_sharded(engine, latent_local: torch.Tensor, hdr_mode: str, ev_m
     vmin, vmax, vsum = engine.decode_begin(latent_local)
     allreduce_raw_stats(vmin, vmax, vsum, group)
     return engine.decode_finish(hdr_mode, ev_multiplier, want_stats)
+
+
+# ------------------------------------------------------------------------------------------------ row tiling
+# One image, latent rows split evenly over the ranks (BASELINE config C4).  libhdrvae runs the same step program
+# on every rank's slab and tells the host what to exchange between steps (include/hdrvae.h, hdrvae_exchange):
+# 1-row conv halos to the neighbours, GroupNorm sums all-reduced, attention K/V all-gathered, HDR statistics
+# all-reduced.  Here the exchanges are NCCL collectives / point-to-point (torch.distributed) on views of the
+# workspace; `decode_rows_emulated` performs the same exchanges with plain copies between R workspaces of ONE
+# process, which is how the path is tested on a single GPU.
+from . import _native as _N  # noqa: E402
+
+
+def _raw_views(ws: torch.Tensor, off: int):
+    blk = ws[off:off + 96]
+    return blk[0:16].view(torch.float32), blk[16:32].view(torch.float32), blk[32:96].view(torch.float64)
+
+
+def _exchange_nccl(ex, ws: torch.Tensor, rank: int, world: int, group=None) -> None:
+    if ex.kind & _N.EX_HALO:
+        ops = []
+        for i in range(ex.n_halo):
+            n = ex.halo_row_bytes[i]
+            first, last = ws[ex.halo_first_row_off[i]:ex.halo_first_row_off[i] + n], ws[ex.halo_last_row_off[i]:ex.halo_last_row_off[i] + n]
+            top, bot = ws[ex.halo_top_off[i]:ex.halo_top_off[i] + n], ws[ex.halo_bottom_off[i]:ex.halo_bottom_off[i] + n]
+            if rank > 0:
+                ops += [dist.P2POp(dist.isend, first, rank - 1, group), dist.P2POp(dist.irecv, top, rank - 1, group)]
+            if rank < world - 1:
+                ops += [dist.P2POp(dist.isend, last, rank + 1, group), dist.P2POp(dist.irecv, bot, rank + 1, group)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+    if ex.kind & _N.EX_ALLREDUCE_F64:
+        buf = ws[ex.allreduce_off:ex.allreduce_off + 8 * ex.allreduce_count].view(torch.float64)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    if ex.kind & _N.EX_ALLGATHER:
+        for i in range(ex.n_gather):
+            n = ex.gather_bytes_per_rank[i]
+            full = ws[ex.gather_off[i]:ex.gather_off[i] + n * world]
+            dist.all_gather_into_tensor(full, full[rank * n:(rank + 1) * n].clone(), group=group)
+    if ex.kind & _N.EX_RAW_STATS:
+        allreduce_raw_stats(*_raw_views(ws, ex.raw_stats_off), group=group)
+
+
+def decode_rows_sharded(engine, latent_full: torch.Tensor, hdr_mode: str, ev_multiplier: float = 1.0, group=None,
+                        want_stats: bool = True):
+    """Row-tiled decode of ONE image across the ranks of `group`: returns this rank's rows of the image
+    ([1, 8h/world, 8w, 3]) and the statistics (pre/post/conv/pre3 global, out_* of the local slab)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    state, ws, out, _keep = engine.rows_begin(latent_full, rank, world, hdr_mode, ev_multiplier)
+    while True:
+        ex = engine.rows_run(state)
+        if ex.kind == _N.EX_END:
+            break
+        _exchange_nccl(ex, ws, rank, world, group)
+    return out, engine.rows_end(state, want_stats)
+
+
+def decode_rows_emulated(engine, latent_full: torch.Tensor, world: int, hdr_mode: str, ev_multiplier: float = 1.0):
+    """The same row-tiled program with `world` virtual ranks on ONE GPU (one workspace each, run in lock step);
+    exchanges are device copies.  Returns the full image [1, 8h, 8w, 3] and rank 0's statistics."""
+    states, wss, outs, keep = [], [], [], []
+    for r in range(world):
+        st, ws, out, z = engine.rows_begin(latent_full, r, world, hdr_mode, ev_multiplier)
+        states.append(st); wss.append(ws); outs.append(out); keep.append(z)
+    while True:
+        exs = [engine.rows_run(st) for st in states]
+        ex = exs[0]
+        if ex.kind == _N.EX_END:
+            break
+        if ex.kind & _N.EX_HALO:
+            for i in range(ex.n_halo):
+                n = ex.halo_row_bytes[i]
+                for r in range(world):
+                    if r > 0:       # my first interior row -> upper neighbour's bottom halo
+                        wss[r - 1][ex.halo_bottom_off[i]:ex.halo_bottom_off[i] + n].copy_(wss[r][ex.halo_first_row_off[i]:ex.halo_first_row_off[i] + n])
+                    if r < world - 1:   # my last interior row -> lower neighbour's top halo
+                        wss[r + 1][ex.halo_top_off[i]:ex.halo_top_off[i] + n].copy_(wss[r][ex.halo_last_row_off[i]:ex.halo_last_row_off[i] + n])
+        if ex.kind & _N.EX_ALLREDUCE_F64:
+            views = [ws[ex.allreduce_off:ex.allreduce_off + 8 * ex.allreduce_count].view(torch.float64) for ws in wss]
+            total = torch.stack(views).sum(0)
+            for v in views:
+                v.copy_(total)
+        if ex.kind & _N.EX_ALLGATHER:
+            for i in range(ex.n_gather):
+                n = ex.gather_bytes_per_rank[i]
+                parts = [wss[r][ex.gather_off[i] + r * n:ex.gather_off[i] + (r + 1) * n].clone() for r in range(world)]
+                for ws in wss:
+                    for r in range(world):
+                        ws[ex.gather_off[i] + r * n:ex.gather_off[i] + (r + 1) * n].copy_(parts[r])
+        if ex.kind & _N.EX_RAW_STATS:
+            blocks = [_raw_views(ws, ex.raw_stats_off) for ws in wss]
+            vmin, vmax, vsum = merge_raw_stats(blocks)
+            for b in blocks:
+                b[0].copy_(vmin); b[1].copy_(vmax); b[2].copy_(vsum)
+    stats = [engine.rows_end(st, True) for st in states]
+    return torch.cat(outs, dim=1), stats[0]
