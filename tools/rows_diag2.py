@@ -14,7 +14,7 @@ eng = HdrVaeEngine(build_decoder(0).state_dict(), dev)
 h, w = int(sys.argv[1]), int(sys.argv[2])
 WORLD = int(sys.argv[3])
 MODE = sys.argv[4] if len(sys.argv) > 4 else "conservative"
-z = make_latent(1, h, w, seed=43).to(dev)
+z = make_latent(1, h, w, seed=int(sys.argv[5]) if len(sys.argv) > 5 else 43).to(dev)
 
 
 def run(world):
