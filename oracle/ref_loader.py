@@ -69,3 +69,59 @@ def load_reference_node():
     node = mod.HDRVAEDecode()
     node.logger.setLevel(logging.WARNING)
     return node
+
+
+def _stub_upscaler_deps(descriptor):
+    """Stand-ins for the packages hdr_upscale_with_model.py imports that are not installed here (folder_paths,
+    comfy, spandrel, kornia.color / kornia.filters): the restated algorithms of oracle.upscaler_oracle, wired so that
+    the UNMODIFIED reference node runs on CPU.  `descriptor` is what `ModelLoader().load_from_file` returns."""
+    from oracle import upscaler_oracle as uo
+    _stub_kornia()
+    k = sys.modules["kornia"]
+    if not hasattr(k, "color") or not hasattr(getattr(k, "color"), "rgb_to_ycbcr"):
+        kcol, kfil = types.ModuleType("kornia.color"), types.ModuleType("kornia.filters")
+        kcol.rgb_to_ycbcr = uo.rgb_to_ycbcr
+        kfil.median_blur = uo.median_blur
+        k.color, k.filters = kcol, kfil
+        sys.modules["kornia.color"], sys.modules["kornia.filters"] = kcol, kfil
+    fp = types.ModuleType("folder_paths")
+    fp.get_filename_list = lambda kind: ["fake_esrgan.pth"]
+    fp.get_full_path = lambda kind, name: name
+    sys.modules["folder_paths"] = fp
+    comfy = types.ModuleType("comfy")
+    mm, cu = types.ModuleType("comfy.model_management"), types.ModuleType("comfy.utils")
+    mm.get_torch_device = lambda: torch.device("cpu")
+    mm.module_size = lambda m: 0
+    mm.free_memory = lambda *a, **k: None
+    mm.OOM_EXCEPTION = torch.OutOfMemoryError if hasattr(torch, "OutOfMemoryError") else MemoryError
+
+    class _PBar:
+        def __init__(self, total):
+            self.total = total
+
+        def update(self, n):
+            pass
+    cu.ProgressBar = _PBar
+    cu.tiled_scale = uo.tiled_scale
+    cu.get_tiled_scale_steps = uo.get_tiled_scale_steps
+    cu.common_upscale = uo.common_upscale
+    comfy.model_management, comfy.utils = mm, cu
+    sys.modules["comfy"], sys.modules["comfy.model_management"], sys.modules["comfy.utils"] = comfy, mm, cu
+    sp = types.ModuleType("spandrel")
+
+    class ModelLoader:
+        def load_from_file(self, path):
+            return sp._descriptor
+    sp.ModelLoader = ModelLoader
+    sp.ImageModelDescriptor = type(descriptor)
+    sp._descriptor = descriptor
+    sys.modules["spandrel"] = sp
+
+
+def load_reference_upscaler(descriptor):
+    """Fresh `HDRUpscaleWithModel` of the unmodified reference whose model loader returns `descriptor`."""
+    _stub_upscaler_deps(descriptor)
+    sys.modules.pop("_hdrvae_reference_hdr_upscale_with_model", None)
+    mod = load_reference_module("hdr_upscale_with_model")
+    sys.modules["spandrel"]._descriptor = descriptor
+    return mod.HDRUpscaleWithModel()

@@ -13,7 +13,8 @@ from oracle.make_golden import apply_variant
 from oracle.ref_loader import load_reference_node, reference_available
 
 MODES = list(ho.HDR_MODES)
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+               if not os.path.basename(p).startswith("up_"))
 
 
 def _load(golden_dir, name):
