@@ -60,6 +60,10 @@ enum { HDRVAE_PRECISION_BF16 = 0, HDRVAE_PRECISION_F16 = 1 };
  * kernel is the product path; the CUDA-core direct kernel exists to validate it
  * on the GPU and is never selected implicitly. */
 enum { HDRVAE_CONV_TCGEN05 = 0, HDRVAE_CONV_DIRECT = 1 };
+/* Upscaler: reversal hook kinds (hdr_upscale_with_model.py:79-107, :266-279) and the resampling methods of
+ * local_fix that are implemented (:241; "area", "bicubic" and ComfyUI's "bislerp" are rejected with an error). */
+enum { HDRVAE_REVERSAL_NONE = 0, HDRVAE_REVERSAL_ATANH = 1, HDRVAE_REVERSAL_LOGIT = 2 };
+enum { HDRVAE_UPSCALE_NEAREST_EXACT = 0, HDRVAE_UPSCALE_BILINEAR = 1 };
 
 /*
  * Scalars the reference computes with ~25 full-tensor reductions + host syncs
@@ -198,6 +202,30 @@ int hdrvae_rows_begin(hdrvae_ctx* ctx, const float* latent_full_nchw, int h, int
 int hdrvae_rows_run(hdrvae_rows* state, hdrvae_exchange* ex, void* stream);
 /* After HDRVAE_EX_END: copy the statistics (global: pre/post/conv/pre3; local slab: out_*, pixel counts) and free. */
 int hdrvae_rows_end(hdrvae_rows* state, hdrvae_stats* stats, void* stream);
+
+/* ---- HDR upscaler: replaces HDRUpscaleWithModel.upscale (hdr_upscale_with_model.py:148-263) for ESRGAN /
+ * RRDBNet 4x models (nf 64, gc 32, any block count; what spandrel loads for "ESRGAN" checkpoints, :73-77).
+ * The model object is created against a decode context (device, SM count, conv implementation).
+ *   load_weights : the model's state dict in either key layout (Real-ESRGAN "conv_first / body.N.rdbK.convJ / ..."
+ *                  or BasicSR-spandrel "model.0 / model.1.sub.N.RDBK.convJ.0 / ..."), host or device pointers;
+ *   forward      : the network (+ reversal hook) on n equal tiles, x [n,h,w,3] -> y [n,4h,4w,3], float32 device
+ *                  (kernel-level parity entry: what `upscale_model(a)` with the forward hook returns, :92-105);
+ *   upscale      : the whole node: image [B,H,W,3] float32 -> out [B,4H,4W,3]; two passes (input as is / clamped to
+ *                  [-1,1], :181-186) through 512-pixel tiles with 64 overlap and feather blending (:110-146,
+ *                  comfy.utils.tiled_scale), Y from the first and Cb/Cr from the second pass, clamp(Y,0,8), 3x3 median
+ *                  (:189-218), optional output median (small_blur, :219-224) and local hot-spot fix (:229-258). */
+typedef struct hdrvae_upscaler hdrvae_upscaler;
+int hdrvae_upscaler_create(hdrvae_ctx* ctx, hdrvae_upscaler** out);
+int hdrvae_upscaler_destroy(hdrvae_upscaler* up);
+int hdrvae_upscaler_load_weights(hdrvae_upscaler* up, const hdrvae_weight_desc* descs, int n);
+int hdrvae_upscaler_blocks(hdrvae_upscaler* up);
+int hdrvae_upscaler_forward_bytes(hdrvae_upscaler* up, int n, int h, int w, size_t* bytes);
+int hdrvae_upscaler_forward(hdrvae_upscaler* up, const float* x_bhwc, int n, int h, int w, int reversal,
+                            float* y_bhwc, void* workspace, size_t workspace_bytes, void* stream);
+int hdrvae_upscale_workspace_bytes(hdrvae_upscaler* up, int B, int H, int W, size_t* bytes);
+int hdrvae_upscale(hdrvae_upscaler* up, const float* image_bhwc, int B, int H, int W, int reversal, int small_blur,
+                   int local_fix, int upscale_method, float* out_bhwc, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* Decoder only: latent -> SiLU(norm_out(h)), the tensor the reference's forward
  * hook captures (hdr_vae_decode.py:850-855), as device NHWC [B,8h,8w,128] of hdrvae_operand_dtype(ctx) (fp16 by default). */

@@ -1,13 +1,16 @@
 """vae_decode_hdr_b200 — B200-native (sm_100a) drop-in for the HDRVAEDecode node of
 netocg/vae-decode-hdr.  Registered exactly like the reference package (__init__.py:43-53)."""
+from .hdr_upscale_with_model import HDRUpscaleWithModel
 from .hdr_vae_decode import HDRVAEDecode
 
 NODE_CLASS_MAPPINGS = {
     "HDRVAEDecode": HDRVAEDecode,
+    "HDRUpscaleWithModel": HDRUpscaleWithModel,
 }
 
 NODE_DISPLAY_NAME_MAPPINGS = {
     "HDRVAEDecode": "HDR VAE Decode",
+    "HDRUpscaleWithModel": "HDR Upscale with Model",
 }
 
-__all__ = ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS", "HDRVAEDecode"]
+__all__ = ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS", "HDRVAEDecode", "HDRUpscaleWithModel"]

@@ -90,7 +90,17 @@ SIGNATURES = {
     "hdrvae_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "hdrvae_quantiles": (_i, [_vp, C.c_longlong, C.POINTER(C.c_double), _i, C.POINTER(C.c_float), _vp]),
     "hdrvae_pack_half": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "hdrvae_upscaler_create": (_i, [_vp, C.POINTER(_vp)]),
+    "hdrvae_upscaler_destroy": (_i, [_vp]),
+    "hdrvae_upscaler_load_weights": (_i, [_vp, C.POINTER(HdrvaeWeightDesc), _i]),
+    "hdrvae_upscaler_blocks": (_i, [_vp]),
+    "hdrvae_upscaler_forward_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
+    "hdrvae_upscaler_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "hdrvae_upscale_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
+    "hdrvae_upscale": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
 }
+REVERSAL_NONE, REVERSAL_ATANH, REVERSAL_LOGIT = 0, 1, 2
+UPSCALE_METHODS = {"nearest-exact": 0, "bilinear": 1}
 
 _lib = None
 

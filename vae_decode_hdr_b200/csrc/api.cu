@@ -17,8 +17,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/hdrvae.h"
-#include "common.cuh"
+#include "engine.cuh"
 
 namespace hdrvae {
 
@@ -34,110 +33,16 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
-// ---- kernels implemented in the other translation units -------------------------------------------
-int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream);
-int launch_gemm_direct(const GemmParams& p, cudaStream_t s);
-void choose_tile(int H, int W, GemmParams* p);
-int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStream_t s);
-int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
-                       const int* tap_mask, float scale, cudaStream_t s);
-int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C, int HW, int cpad, cudaStream_t s);
-int launch_latent_rows_to_nhwc(const float* z, void* out, int out_dtype, int C, int h, int w, int y0, int rows, int cpad,
-                               cudaStream_t s);
-int launch_softmax_rows(const float* s, void* p, int p_dtype, float* inv_sum, int n_rows, int n_valid, int n_pad,
-                        long long s_ld, long long p_ld, cudaStream_t st);
-int launch_transpose_pad(const void* in, void* out, int rows, int cols, int out_ld, cudaStream_t s);
-int launch_attn_reduce_splits(const float* part, const float* inv_sum, void* out, int out_dtype, int rows, int cols,
-                              int splits, cudaStream_t st);
-int launch_pack_half(const float* img, uint16_t* out, int B, int H, int W, int layout, cudaStream_t s);
-size_t quantile_scratch_bytes();
-int launch_quantiles(const float* x, long long n, const unsigned long long* ranks_host, int nq, float* out, void* scratch,
-                     cudaStream_t s);
-size_t gn_scratch_bytes(int B, int C, int max_chunks);
-int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
-                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s);
-size_t epilogue_scratch_bytes(int B, int H, int W);
-void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W);
-hdrvae_stats* epilogue_stats_dev_ptr(void* scratch, int B, int H, int W);
-float* epilogue_post3_ptr(void* scratch, int B, int H, int W);
-float* epilogue_pre3_ptr(void* scratch, int B, int H, int W);
-int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, const float* conv_w, const float* conv_b,
-                            int* argmax3, void* scratch, cudaStream_t s, int y_pad = 0, long long img_stride = 0);
-double* gn_sums_ptr(void* scratch, int B, int C, int max_chunks);
-int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n_partials, cudaStream_t s);
-int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
-                              int B, int rows_px, int C, const float* gamma, const float* beta, bool silu, void* scratch,
-                              int max_chunks, double count, cudaStream_t s);
-int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
-                            void* scratch, cudaStream_t s);
-
-// ---- per-op device timing (diagnostics; enabled by hdrvae_profile_begin) -----------------------------
-struct ProfEntry { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
-static bool g_prof_on = false;
-static std::vector<ProfEntry> g_prof;
-struct ProfScope {
-  cudaStream_t s; bool on;
-  ProfScope(const char* name, double flops, double bytes, cudaStream_t st) : s(st), on(g_prof_on) {
-    if (!on) return;
-    ProfEntry e; e.name = name; e.flops = flops; e.bytes = bytes;
-    cudaEventCreate(&e.e0); cudaEventCreate(&e.e1);
-    cudaEventRecord(e.e0, s);
-    g_prof.push_back(e);
-    idx = g_prof.size() - 1;
-  }
-  ~ProfScope() { if (on) cudaEventRecord(g_prof[idx].e1, s); }
-  size_t idx = 0;
-};
-
-// ---- packed operands --------------------------------------------------------------------------
-struct PackedConv {
-  void* w[4] = {nullptr, nullptr, nullptr, nullptr};  // [Cout][ntaps*cin_pad] K-major; 4 phase matrices when upsample
-  float* bias = nullptr;
-  int cin = 0, cin_pad = 0, cout = 0, ks = 0;
-  int w_dtype = DT_F16;      // operand type of this conv (DT_F32 = tf32 MMA on the raw fp32 stream)
-  bool upsample = false;
-};
-struct NormW {
-  float* gamma = nullptr;
-  float* beta = nullptr;
-  int C = 0;
-};
-struct ResW {
-  NormW n1, n2;
-  PackedConv c1, c2, nin;
-  bool has_nin = false;
-  bool dual_out = false;     // the block's output is also the operand of the next (upsample) conv: emit the scaled 16-bit copy
-};
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
 
 }  // namespace hdrvae
 
 using namespace hdrvae;
 
-struct hdrvae_ctx {
-  int device = 0;
-  int num_sms = 148;
-  bool loaded = false;
-  int conv_impl = HDRVAE_CONV_TCGEN05;
-  int op_dtype = DT_F16;                          // 16-bit tensor-core operand type (HDRVAE_PRECISION_*)
-  int cta_group = 0;                              // 0 = default (CTA pairs), 1 / 2 forced
-  struct GraphEntry { int B, h, w, mode, conv_impl, cta_group; float factor, ev; void* ws; cudaGraphExec_t exec; long long n_kernels; };
-  std::vector<GraphEntry> graphs;                 // captured whole-decode CUDA graphs (hdrvae_decode)
-  std::vector<GraphEntry> seen;                   // keys decoded once already (capture happens on the second use)
-  bool use_graphs = true;
-  std::vector<void*> owned;                       // every device allocation of the context
-  std::map<std::string, float*> raw;              // fp32 device copies of the state dict
-  std::map<std::string, std::vector<int64_t>> shapes;
-  PackedConv conv_in, qk, vproj, proj_out;
-  NormW attn_norm, norm_out;
-  ResW mid1, mid2, up[4][3];
-  PackedConv upsample[4];
-  float* conv_out_w = nullptr;                    // fp32 OIHW [3][128][3][3]
-  float* conv_out_b = nullptr;
-};
-
 namespace hdrvae {
 
-static int dev_alloc(hdrvae_ctx* ctx, size_t bytes, void** out) {
+int dev_alloc(hdrvae_ctx* ctx, size_t bytes, void** out) {
   HDRVAE_CUDA_OK(cudaMalloc(out, bytes ? bytes : 16));
   ctx->owned.push_back(*out);
   return 0;
@@ -166,13 +71,15 @@ static void phase_taps(int py, int px, int* dy, int* dx, int* mask) {
     }
 }
 
-static int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int cin, int ks, bool upsample,
+int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int cin, int ks, bool upsample,
                      float scale, int w_dtype, PackedConv* pc, cudaStream_t s) {
   pc->cin = cin; pc->cout = cout; pc->ks = ks; pc->upsample = upsample; pc->w_dtype = w_dtype;
   pc->cin_pad = (cin + 63) / 64 * 64;
+  pc->cout_pad = (cout + 31) / 32 * 32;
   const size_t eb = dt_bytes(w_dtype);
   if (bias != nullptr) {
-    HDRVAE_TRY(dev_alloc(ctx, cout * sizeof(float), (void**)&pc->bias));
+    HDRVAE_TRY(dev_alloc(ctx, pc->cout_pad * sizeof(float), (void**)&pc->bias));
+    HDRVAE_CUDA_OK(cudaMemsetAsync(pc->bias, 0, pc->cout_pad * sizeof(float), s));
     HDRVAE_CUDA_OK(cudaMemcpyAsync(pc->bias, bias, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   if (!upsample) {
@@ -199,25 +106,8 @@ static int tiles_for(int H, int W) {
   return p.tiles_x * p.tiles_y;
 }
 
-struct ConvIO {
-  const void* x = nullptr;        // [B,H,W,cin_pad], element type = pc.w_dtype
-  void* y = nullptr;              // [B,OH,OW,cout]
-  int y_dtype = DT_F32;
-  const void* residual = nullptr; // y's layout
-  int res_dtype = DT_F32;
-  bool round_tf32 = false;
-  void* y2 = nullptr;             // optional scaled 16-bit copy of y (operand of a conv that reads y un-normalised)
-  int y2_dtype = DT_F16;
-  float y2_scale = 1.f;
-  float alpha = 1.f;              // accumulator scale (undoes the operand scale of a y2-fed conv)
-  float* stats = nullptr;         // GroupNorm partials of y, or null
-  int* stats_chunks = nullptr;    // out: partial chunks per image written
-  // row tiling: x / y (and residual, y2) are slabs with this many halo rows stored above and below the H / OH rows;
-  // the pointers address the slab start
-  int x_pad = 0, y_pad = 0;
-};
 
-static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int H, int W, int impl,
+int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int H, int W, int impl,
                     cudaStream_t s) {
   char pname[96];
   snprintf(pname, sizeof pname, "conv%dx%d%s%s %d->%d @%dx%dx%d", pc.ks, pc.ks, pc.upsample ? "up" : "",
@@ -230,12 +120,16 @@ static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int
   memset(&p, 0, sizeof p);
   p.a = io.x;
   p.ab_dtype = pc.w_dtype;
-  p.a_px_stride = pc.cin_pad; p.a_row_stride = (long long)W * pc.cin_pad;
-  p.a_img_stride = (long long)(H + 2 * io.x_pad) * W * pc.cin_pad;
+  const int xch = io.x_channels > 0 ? io.x_channels : pc.cin_pad;
+  p.a_px_stride = xch; p.a_row_stride = (long long)W * xch;
+  p.a_img_stride = (long long)(H + 2 * io.x_pad) * W * xch;
+  p.a_k_valid = io.x_channels > 0 ? pc.cin : 0;
   p.y_pad = io.x_pad;
   p.n_img = B; p.H = H; p.W = W;
   p.k_per_tap = pc.cin_pad;
-  p.n_cols = pc.cout;
+  p.n_cols = pc.cout_pad;
+  p.n_store = io.n_store > 0 ? io.n_store : (pc.cout_pad != pc.cout ? (pc.cout + 3) / 4 * 4 : 0);
+  p.res_scale = io.res_scale; p.lrelu = io.lrelu;
   p.out_dtype = io.y_dtype;
   p.bias = pc.bias; p.bias_per_row = 0; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
   p.round_tf32 = io.round_tf32 ? 1 : 0;
@@ -244,14 +138,22 @@ static int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int
   choose_tile(H, W, &p);
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
-  p.out_px_stride = pc.cout; p.out_row_stride = (long long)OW * pc.cout;
-  p.out_img_stride = (long long)(OH + 2 * io.y_pad) * OW * pc.cout;
+  const int ych = io.y_channels > 0 ? io.y_channels : pc.cout;
+  p.out_px_stride = ych; p.out_row_stride = (long long)OW * ych;
+  p.out_img_stride = (long long)(OH + 2 * io.y_pad) * OW * ych;
   {
     // interior of the output slab(s): skip the y_pad halo rows
-    const size_t skip = (size_t)io.y_pad * OW * pc.cout;
+    const size_t skip = (size_t)io.y_pad * OW * ych + io.y_chan_off;
     p.out = reinterpret_cast<uint8_t*>(io.y) + skip * dt_bytes(io.y_dtype);
     p.residual = io.residual ? reinterpret_cast<const uint8_t*>(io.residual) + skip * dt_bytes(io.res_dtype) : nullptr;
-    p.out2 = io.y2 ? reinterpret_cast<uint8_t*>(io.y2) + skip * 2 : nullptr;
+    p.residual2 = io.residual2 ? io.residual2 + skip : nullptr;
+    if (io.y2 != nullptr && io.y2_channels > 0) {
+      p.out2_px_stride = io.y2_channels; p.out2_row_stride = (long long)OW * io.y2_channels;
+      p.out2_img_stride = (long long)(OH + 2 * io.y_pad) * OW * io.y2_channels;
+      p.out2 = reinterpret_cast<uint8_t*>(io.y2) + ((size_t)io.y_pad * OW * io.y2_channels + io.y2_chan_off) * 2;
+    } else {
+      p.out2 = io.y2 ? reinterpret_cast<uint8_t*>(io.y2) + skip * 2 : nullptr;
+    }
   }
   const int tiles = p.tiles_x * p.tiles_y;
   p.stats = io.stats;

@@ -66,6 +66,9 @@ struct GemmParams {
   int y_pad;        // halo rows stored above/below the H rows of A (row tiling): `a` points at the slab start, the
                     // A rows addressed are y + dy + y_pad of H + 2*y_pad stored rows (0: vertical padding by TMA zero fill)
   int k_per_tap;    // elements; multiple of one 128-byte row (64 for 16-bit operands, 32 for tf32)
+  int a_k_valid;    // channels of A that exist per pixel (0: k_per_tap).  Smaller than k_per_tap when a conv reads a
+                    // channel prefix that is not a multiple of the 128-byte row (dense-block concat buffers): TMA
+                    // zero-fills the tail of the last K block, the packed weights hold zeros there
   int ntaps;
   int tap_dy[9], tap_dx[9];
   int n_cols;       // valid output columns (Cout)
@@ -80,11 +83,16 @@ struct GemmParams {
   int bias_per_row;  // bias indexed by the M row (x coordinate) instead of the column
   const void* residual;  // same addressing as out, or null
   int res_dtype;
+  float res_scale;   // multiplier of `residual` (0 is read as 1)
+  const float* residual2;  // second fp32 residual, same addressing as out, added unscaled; or null
+  float lrelu;       // LeakyReLU negative slope applied last (0: none)
+  int n_store;       // columns actually stored (multiple of 4; 0: n_cols) — a Cout padded up to 32 stores less
   const float* row_scale;  // per M row (x coordinate) multiplier of the accumulator, or null
   float alpha;       // accumulator scale applied before bias (1.0 for convs)
   void* out2;        // optional second output: out * out2_scale as a 16-bit tensor (same addressing), or null
   int out2_dtype;
   float out2_scale;
+  long long out2_img_stride, out2_row_stride, out2_px_stride;  // elements; all 0: same addressing as out
   int round_tf32;    // round fp32 outputs to tf32 (RN) so a following kind::tf32 MMA reads them exactly
   // GroupNorm statistics of the output, emitted per (image, m-tile) as (sum, sum of squares) of each of the
   // 32 channel groups: stats[((img * tiles_per_img + m_tile) * 32 + group) * 2 + {0,1}], or null

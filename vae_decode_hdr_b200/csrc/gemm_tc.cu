@@ -90,6 +90,8 @@ enum : int {
   EPI_OUT2 = 8,      // + scaled 16-bit second output
   EPI_STATS = 16,    // + GroupNorm partial statistics
   EPI_ROWOPS = 32,   // per-row bias / per-row scale (attention GEMMs)
+  EPI_LRELU = 64,    // LeakyReLU applied last (upscaler convs)
+  EPI_RES2 = 128,    // + second fp32 residual (end of an RRDB: 0.04 acc + 0.2 x2 + x0)
 };
 
 template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB>
@@ -99,6 +101,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcConfig<BLOCK_N, CG, KSUB>;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position in the CTA pair (0 = leader)
   constexpr int kStages = Cfg::kStages;
+  // 32-column tiles are drained by the 4 warps that cover the 4 TMEM lane quarters; the other 4 stay idle
+  constexpr int kActiveEpiWarps = BLOCK_N >= 64 ? 8 : 4;
   constexpr int kElemsPerRow = kTf32 ? 32 : 64;   // K elements per stage
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage buffers.
@@ -126,7 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], CG * kEpilogueThreads / 32);   // epilogue warps of every CTA of the pair
+      ptx::mbar_init(&tmem_empty_bar[i], CG * kActiveEpiWarps);   // draining epilogue warps of every CTA of the pair
     }
     ptx::fence_barrier_init();
   }
@@ -244,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && (warp - 2) < kActiveEpiWarps) {
     // ------------------------------------------------------------ epilogue (8 warps; 128 TMEM lanes x 2 column halves)
     // TMEM hands every thread one accumulator ROW (pixel).  Writing rows straight to global memory makes each
     // warp-level access touch 32 different 128-byte lines (ncu: 31 sectors/request, LSU wavefront bound), so
@@ -261,6 +265,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_stats = kGen ? (p.stats != nullptr) : ((EPI & EPI_STATS) != 0);
     const bool row_ops = kGen ? (p.bias_per_row != 0 || p.row_scale != nullptr) : ((EPI & EPI_ROWOPS) != 0);
     const bool do_round = kGen && p.round_tf32 != 0;
+    const bool has_lrelu = kGen ? (p.lrelu != 0.f) : ((EPI & EPI_LRELU) != 0);
+    const bool has_res2 = kGen ? (p.residual2 != nullptr) : ((EPI & EPI_RES2) != 0);
+    const float lrelu = p.lrelu, res_scale = p.res_scale;
+    const int n_store = p.n_store > 0 ? p.n_store : p.n_cols;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int we = warp - 2;                // 0..7
     const int half = we >> 2;               // which half of the tile's columns this warp drains
@@ -269,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int slot = lane & 7;              // 4-channel slot inside the 32-column chunk
     const int sr = lane >> 3;               // pixel sub-row 0..3 handled by this lane in each iteration
     float4* patch = reinterpret_cast<float4*>(stage_s) + we * 256;      // [32 rows][8 float4], XOR-swizzled
-    constexpr int kChunksPerWarp = BLOCK_N / 64;
+    constexpr int kChunksPerWarp = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
     const float alpha = p.alpha;
     const bool out16_bf = p.out_dtype == DT_BF16, out2_bf = p.out2_dtype == DT_BF16;
     const float s2 = p.out2_scale;
@@ -278,6 +286,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint16_t* const out2h = reinterpret_cast<uint16_t*>(p.out2);
     const float* const resf = reinterpret_cast<const float*>(p.residual);
     const long long px_step = (long long)p.sx * p.out_px_stride;
+    // the second output may live in a tensor with different strides (a channel slice of a concat buffer)
+    const bool out2_own = p.out2_px_stride != 0;
+    const long long o2_img = out2_own ? p.out2_img_stride : p.out_img_stride;
+    const long long o2_row = out2_own ? p.out2_row_stride : p.out_row_stride;
+    const long long o2_px = out2_own ? p.out2_px_stride : p.out_px_stride;
     const bool wide = p.tw_log2 >= 5;       // a warp's 32 pixels are consecutive in x (all but tiny images)
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -326,13 +339,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ci = 0; ci < kChunksPerWarp; ++ci) {
         const int c0 = cbase + ci * 32;
         const int col = c0 + slot * 4;                    // first of this lane's 4 columns (tile-relative)
-        const uint32_t cmask = (n0 + c0) < p.n_cols ? pmask : 0u;   // n_cols is a multiple of 32 on every call site
+        const uint32_t cmask = (n0 + col) < n_store ? pmask : 0u;   // n_cols % 32 == 0 and n_store % 4 == 0 on every call site
         // residual: coalesced loads issued first so they overlap the accumulator wait / TMEM load / transpose
         float4 rres[8];
         if (has_res_f32) {
 #pragma unroll
           for (int it = 0; it < 8; ++it)
             if (cmask >> it & 1) rres[it] = *reinterpret_cast<const float4*>(resf + poff[it] + col);   // plain load: may alias out
+        }
+        float4 rres2[8];
+        if (has_res2) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (cmask >> it & 1) rres2[it] = *reinterpret_cast<const float4*>(p.residual2 + poff[it] + col);
         }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!(row_ops && p.bias_per_row) && p.bias != nullptr && cmask != 0u) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
@@ -368,7 +387,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             a.x = fmaf(a.x, scale, bias4.x); a.y = fmaf(a.y, scale, bias4.y);
             a.z = fmaf(a.z, scale, bias4.z); a.w = fmaf(a.w, scale, bias4.w);
-            if (has_res_f32) { a.x += rres[it].x; a.y += rres[it].y; a.z += rres[it].z; a.w += rres[it].w; }
+            if (has_res_f32) {
+              a.x = fmaf(rres[it].x, res_scale, a.x); a.y = fmaf(rres[it].y, res_scale, a.y);
+              a.z = fmaf(rres[it].z, res_scale, a.z); a.w = fmaf(rres[it].w, res_scale, a.w);
+            }
+            if (has_res2) { a.x += rres2[it].x; a.y += rres2[it].y; a.z += rres2[it].z; a.w += rres2[it].w; }
             if (has_res_16) {
               // 16-bit residual (test entry only); plain load: the residual may alias the output
               const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + poff[it] + col);
@@ -382,13 +405,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
             }
+            if (has_lrelu) {
+              a.x = a.x < 0.f ? a.x * lrelu : a.x; a.y = a.y < 0.f ? a.y * lrelu : a.y;
+              a.z = a.z < 0.f ? a.z * lrelu : a.z; a.w = a.w < 0.f ? a.w * lrelu : a.w;
+            }
             if (has_out2) {
               // second, scaled 16-bit copy of the output: the tensor-core operand of a conv that consumes this
               // (un-normalised) tensor directly; the power-of-two scale keeps fp16 far from overflow
               uint2 o2;
               if (out2_bf) { o2.x = pack_bf16x2(a.x * s2, a.y * s2); o2.y = pack_bf16x2(a.z * s2, a.w * s2); }
               else { o2.x = pack_f16x2(a.x * s2, a.y * s2); o2.y = pack_f16x2(a.z * s2, a.w * s2); }
-              *reinterpret_cast<uint2*>(out2h + poff[it] + col) = o2;
+              long long off2 = poff[it];
+              if (out2_own) {
+                const int row = wide ? q * 32 + sr + it * 4 : q * 32 + it * 4 + sr;
+                const int y2 = ty * p.TH + (row >> p.tw_log2), x2 = tx * p.TW + (row & (p.TW - 1));
+                off2 = (long long)img * o2_img + n0 + (long long)(y2 * p.sy + p.py) * o2_row + (long long)(x2 * p.sx + p.px) * o2_px;
+              }
+              *reinterpret_cast<uint2*>(out2h + off2 + col) = o2;
             }
             if (out_f32) {
               if (do_round) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
@@ -485,7 +518,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps) {
                  "gemm_tc: strides must be multiples of 16 bytes");
   {
     // A: {C, W, H, N}; the channel extent visible to TMA is k_per_tap (columns beyond are never addressed)
-    cuuint64_t dims[4] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
+    cuuint64_t dims[4] = {(cuuint64_t)(p.a_k_valid > 0 ? p.a_k_valid : p.k_per_tap), (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * eb, (cuuint64_t)p.a_row_stride * eb,
                              (cuuint64_t)p.a_img_stride * eb};
     cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
@@ -529,6 +562,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
   constexpr int KSUB = (BLOCK_N <= 128) ? 2 : 1;
   GemmParams p = p_in;
+  if (p.res_scale == 0.f) p.res_scale = 1.f;
   using Cfg = TcConfig<BLOCK_N, CG, KSUB>;
   {
     const char* d = getenv("HDRVAE_GEMM_DBG");
@@ -583,7 +617,30 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
   // belong to the same image: an odd number of tiles per image runs as single CTAs.
   if (p.b_img_k_stride != 0 && (p.tiles_x * p.tiles_y) % 2 != 0) use_cg = 1;
   const bool n128 = p.n_cols <= 128;
-  if (use_cg == 2 && !tf32) {
+  if (p.n_cols <= 64 && !tf32) {
+    // narrow tiles (the upscaler's 32- and 64-channel convs): 32 / 64 accumulator columns instead of 128, so the
+    // MMAs do no work on padding columns
+    const bool n32 = p.n_cols <= 32;
+    int epi = -1;
+    if (use_cg == 2 && !p.round_tf32 && p.stats == nullptr && !p.bias_per_row && p.row_scale == nullptr &&
+        (p.residual == nullptr || p.res_dtype == DT_F32)) {
+      epi = (p.out_dtype != DT_F32 ? EPI_OUT16 : 0) | (p.residual ? EPI_RES : 0) | (p.residual2 ? EPI_RES2 : 0) |
+            (p.out2 ? EPI_OUT2 : 0) | (p.lrelu != 0.f ? EPI_LRELU : 0);
+    }
+    if (n32) {
+      if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<32, false, 2, EPI_OUT16 | EPI_LRELU>(p, num_sms, stream);
+      if (epi == 0) return launch_tc<32, false, 2, 0>(p, num_sms, stream);
+      return use_cg == 2 ? launch_tc<32, false, 2, EPI_GENERIC>(p, num_sms, stream)
+                         : launch_tc<32, false, 1, EPI_GENERIC>(p, num_sms, stream);
+    }
+    if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<64, false, 2, EPI_OUT16 | EPI_LRELU>(p, num_sms, stream);
+    if (epi == (EPI_RES | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_OUT2>(p, num_sms, stream);
+    if (epi == (EPI_RES | EPI_RES2 | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_RES2 | EPI_OUT2>(p, num_sms, stream);
+    if (epi == EPI_OUT2) return launch_tc<64, false, 2, EPI_OUT2>(p, num_sms, stream);
+    return use_cg == 2 ? launch_tc<64, false, 2, EPI_GENERIC>(p, num_sms, stream)
+                       : launch_tc<64, false, 1, EPI_GENERIC>(p, num_sms, stream);
+  }
+  if (use_cg == 2 && !tf32 && p.lrelu == 0.f && p.residual2 == nullptr && p.n_store == 0 && p.res_scale == 0.f) {
     // specialised epilogues for what the decoder launches; anything else takes the generic build
     int epi = 0;
     const bool simple_res = p.residual == nullptr || p.res_dtype == DT_F32;

@@ -150,7 +150,8 @@ __global__ void gemm_direct_kernel(const GemmParams p) {
         if (ys < 0 || ys >= p.H + 2 * p.y_pad || xs < 0 || xs >= p.W) continue;
         const long long ao = img * p.a_img_stride + ys * p.a_row_stride + xs * p.a_px_stride;
         const long long bo = col * p.b_row_stride + (long long)t * p.k_per_tap + img * p.b_img_k_stride;
-        for (int c = 0; c < p.k_per_tap; ++c) {
+        const int kv = p.a_k_valid > 0 ? p.a_k_valid : p.k_per_tap;
+        for (int c = 0; c < kv; ++c) {
           float av = load_as(p.a, ao + c, p.ab_dtype), bv = load_as(p.b, bo + c, p.ab_dtype);
           if (tf32) { av = trunc_tf32(av); bv = trunc_tf32(bv); }     // the tensor core ignores the low 13 bits
           acc = fmaf(av, bv, acc);
@@ -161,10 +162,16 @@ __global__ void gemm_direct_kernel(const GemmParams p) {
     if (p.bias != nullptr) v += p.bias_per_row ? p.bias[x] : p.bias[col];
     const long long off = (long long)img * p.out_img_stride + (long long)(y * p.sy + p.py) * p.out_row_stride +
                           (long long)(x * p.sx + p.px) * p.out_px_stride + col;
-    if (p.residual != nullptr) v += load_as(p.residual, off, p.res_dtype);
+    if (p.residual != nullptr) v += (p.res_scale != 0.f ? p.res_scale : 1.f) * load_as(p.residual, off, p.res_dtype);
+    if (p.residual2 != nullptr) v += p.residual2[off];
+    if (p.lrelu != 0.f && v < 0.f) v *= p.lrelu;
+    if (p.n_store > 0 && col >= p.n_store) continue;
     if (p.out2 != nullptr) {
-      if (p.out2_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out2)[off] = __float2bfloat16_rn(v * p.out2_scale);
-      else reinterpret_cast<__half*>(p.out2)[off] = __float2half_rn(v * p.out2_scale);
+      const long long off2 = p.out2_px_stride == 0 ? off
+          : (long long)img * p.out2_img_stride + (long long)(y * p.sy + p.py) * p.out2_row_stride +
+            (long long)(x * p.sx + p.px) * p.out2_px_stride + col;
+      if (p.out2_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out2)[off2] = __float2bfloat16_rn(v * p.out2_scale);
+      else reinterpret_cast<__half*>(p.out2)[off2] = __float2half_rn(v * p.out2_scale);
     }
     if (p.out_dtype == DT_F32) {
       if (p.round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
