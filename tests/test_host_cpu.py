@@ -88,7 +88,7 @@ def test_node_surface_equals_reference():
     from vae_decode_hdr_b200 import NODE_CLASS_MAPPINGS, NODE_DISPLAY_NAME_MAPPINGS
     cls = NODE_CLASS_MAPPINGS["HDRVAEDecode"]
     it = cls.INPUT_TYPES()
-    assert NODE_DISPLAY_NAME_MAPPINGS == {"HDRVAEDecode": "HDR VAE Decode"}
+    assert NODE_DISPLAY_NAME_MAPPINGS == {"HDRVAEDecode": "HDR VAE Decode", "HDRUpscaleWithModel": "HDR Upscale with Model"}
     assert (cls.RETURN_TYPES, cls.RETURN_NAMES, cls.FUNCTION, cls.CATEGORY) == (("IMAGE",), ("image",), "simple_hdr_decode", "latent")
     from oracle.ref_loader import load_reference_module, reference_available
     if reference_available():      # build container: compare with the unmodified reference class
@@ -227,3 +227,26 @@ def test_row_tiling_exchange_executor_gloo_world3():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True), (2, True)]
+
+
+def test_upscaler_node_surface_equals_reference():
+    """HDRUpscaleWithModel: same INPUT_TYPES / RETURN_TYPES / FUNCTION / CATEGORY / upscale() parameters as the
+    unmodified reference class (hdr_upscale_with_model.py:50-71,148) when the reference tree is mounted."""
+    import inspect
+    from vae_decode_hdr_b200 import NODE_CLASS_MAPPINGS
+    cls = NODE_CLASS_MAPPINGS["HDRUpscaleWithModel"]
+    assert (cls.RETURN_TYPES, cls.FUNCTION, cls.CATEGORY) == (("IMAGE",), "upscale", "HDR/Upscale")
+    from oracle.ref_loader import reference_available
+    if reference_available():
+        from oracle import upscaler_oracle as uo
+        from oracle.ref_loader import load_reference_upscaler
+        ref = type(load_reference_upscaler(uo.FakeDescriptor(torch.nn.Identity())))
+        want, got = ref.INPUT_TYPES()["required"], cls.INPUT_TYPES()["required"]
+        assert list(want) == list(got)
+        for k in want:
+            if k != "model_name":                 # the file list comes from ComfyUI's folder_paths
+                assert want[k] == got[k], k
+        assert (cls.RETURN_TYPES, cls.FUNCTION, cls.CATEGORY) == (ref.RETURN_TYPES, ref.FUNCTION, ref.CATEGORY)
+        assert list(inspect.signature(cls.upscale).parameters) == list(inspect.signature(ref.upscale).parameters)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cls._compute_device(torch.zeros(1, 4, 4, 3))

@@ -99,3 +99,34 @@ class SyntheticVAE:
 def synthetic_latent(b: int, h: int, w: int, seed: int = 1234) -> torch.Tensor:
     g = torch.Generator(device="cpu").manual_seed(seed)
     return torch.randn(b, Z, h, w, generator=g, dtype=torch.float32)
+
+
+def upscaler_param_shapes(nb: int = 23) -> List[Tuple[str, Tuple[int, ...]]]:
+    """RRDBNet (ESRGAN 4x: nf 64, gc 32) parameters in Real-ESRGAN key order."""
+    out: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def conv(name, cout, cin):
+        out.append((name + ".weight", (cout, cin, 3, 3)))
+        out.append((name + ".bias", (cout,)))
+    conv("conv_first", 64, 3)
+    for i in range(nb):
+        for r in (1, 2, 3):
+            for j in range(4):
+                conv(f"body.{i}.rdb{r}.conv{j + 1}", 32, 64 + 32 * j)
+            conv(f"body.{i}.rdb{r}.conv5", 64, 192)
+    for name in ("conv_body", "conv_up1", "conv_up2", "conv_hr"):
+        conv(name, 64, 64)
+    conv("conv_last", 3, 64)
+    return out
+
+
+def random_upscaler_state_dict(seed: int = 0, nb: int = 23) -> Dict[str, torch.Tensor]:
+    """PyTorch-default-style init of an RRDBNet (config C5: random-init ESRGAN), fp32, CPU."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    bound = 1.0
+    for name, shape in upscaler_param_shapes(nb):
+        if len(shape) == 4:
+            bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])
+        sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return sd
