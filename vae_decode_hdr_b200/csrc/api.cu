@@ -136,6 +136,18 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
   p.cta_group = ctx->cta_group;
   choose_tile(H, W, &p);
+  {
+    // narrow 3x3 convs (the upscaler's): L2 -> SM operand traffic of the 9 taps is the bound, so the activation slab
+    // is loaded once per tile (gemm_tc.cu slab variant); HDRVAE_SLAB=0 keeps the tap-reload form for A/B comparison
+    static int slab_on = -1;
+    if (slab_on < 0) { const char* e = getenv("HDRVAE_SLAB"); slab_on = (e && atoi(e) == 0) ? 0 : 1; }
+    if (slab_on && pc.ks == 3 && !pc.upsample && pc.cout_pad <= 64 && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT &&
+        io.stats == nullptr && H * W >= 128) {
+      p.slab = 1;
+      p.tw_log2 = 3; p.TW = 8; p.TH = 16;
+      p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;
+    }
+  }
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
   const int ych = io.y_channels > 0 ? io.y_channels : pc.cout;

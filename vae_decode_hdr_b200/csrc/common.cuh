@@ -98,6 +98,8 @@ struct GemmParams {
   // 32 channel groups: stats[((img * tiles_per_img + m_tile) * 32 + group) * 2 + {0,1}], or null
   float* stats;
   int stats_chunks_per_img, stats_chunk0;
+  int slab;          // 3x3 conv with narrow output (<= 64 columns): 8x16-pixel tiles whose 10x18 activation slab is loaded
+                     // ONCE per K block and read by the 9 taps as shifted descriptors (gemm_tc.cu "slab" variant)
   int cta_group;     // 0 = library default (CTA pairs), 1 = single CTA, 2 = CTA pair (tcgen05 cta_group::2)
   int dbg;           // diagnostics (env HDRVAE_GEMM_DBG): bit0 = producer skips the TMA loads, bit1 = issuer skips the MMAs
 };

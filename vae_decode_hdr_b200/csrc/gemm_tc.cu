@@ -17,6 +17,7 @@
 //
 // Tile: 128 pixels (TH x TW patch) x BLOCK_N output channels, K step = one 128-byte swizzle row.
 #include "common.cuh"
+#pragma nv_diag_suppress 128   // "loop is not reachable": the tap-reload loops after the slab branch of an if-constexpr
 #include "ptx.cuh"
 
 namespace hdrvae {
@@ -34,16 +35,23 @@ constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 4 * 64 * 4 
 // CG = CTAs cooperating on one MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256-pixel x BLOCK_N
 // tile with M = 256 instructions; each CTA then stages only half of the B (weight) tile, which cuts the
 // L2->SM operand traffic by a third, deepens the pipeline and halves the per-MMA issue/barrier overhead.
-template <int BLOCK_N, int CG, int KSUB>
+// SLAB (3x3 convs with <= 64 output columns, where the 9 taps re-reading the activation tile from L2 is the bound):
+// the tile is 8 x 16 pixels; per K block ONE TMA box of 18 rows x 16 pixels (the 10 x 18 halo slab at a 16-line
+// pitch) and ONE box with the 9 taps' weights are staged, and the 9 taps are shifted UMMA descriptors into the slab.
+constexpr int kSlabRows = 18, kSlabPitch = 16;
+constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 36 KB
+template <int BLOCK_N, int CG, int KSUB, bool SLAB = false>
 struct TcConfig {
-  static constexpr int kBBytes = (BLOCK_N / CG) * kRowBytes;       // one k-sub-block of B staged by this CTA
-  static constexpr int kSubBytes = kABytes + kBBytes;              // bytes one CTA loads per k-sub-block
+  static constexpr int kATile = SLAB ? kSlabBytes : kABytes;
+  static constexpr int kBBytes = (SLAB ? 9 : 1) * (BLOCK_N / CG) * kRowBytes;   // one k-sub-block of B staged by this CTA
+  static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block
   static constexpr int kStageBytes = KSUB * kSubBytes;
   static constexpr int kStagesFit = (kSmemLimit - kSmemFixed) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 256 / 512)
   static constexpr int kSmemBytes = kStages * kStageBytes + kSmemFixed;
-  static_assert(kStages >= 3 && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
+  static_assert(kStages >= (SLAB ? 2 : 3) && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
+  static_assert(!SLAB || KSUB == 1, "the slab variant stages one K block per pipeline slot");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -94,11 +102,12 @@ enum : int {
   EPI_RES2 = 128,    // + second fp32 residual (end of an RRDB: 0.04 acc + 0.2 x2 + x0)
 };
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, bool SLAB = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
-  using Cfg = TcConfig<BLOCK_N, CG, KSUB>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
+  constexpr int kAT = Cfg::kATile;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position in the CTA pair (0 = leader)
   constexpr int kStages = Cfg::kStages;
   // 32-column tiles are drained by the 4 warps that cover the 4 TMEM lane quarters; the other 4 stay idle
@@ -108,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // SWIZZLE_128B needs 1024-byte aligned stage buffers.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * KSUB * kABytes;
+  uint8_t* smem_b = smem + kStages * KSUB * kAT;
   float* stage_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);     // [8 warps][32 rows][32 floats]
   float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
@@ -171,6 +180,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = rem - ty * p.tiles_x;
       const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / CG);
       const int bk0 = (int)(img * p.b_img_k_stride);       // split-K: this image's K range of B
+      if constexpr (SLAB) {
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * Cfg::kSubBytes));
+            uint8_t* sa = smem_a + stage * kAT;
+            uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+            // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
+            if (CG == 2) {
+              ptx::tma_load_4d_pair(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+              ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, 0);
+            } else {
+              ptx::tma_load_4d(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+              ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, 0);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int g = 0; g < num_groups; ++g) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         const int kb0 = g * KSUB;
@@ -185,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int kbl = kb0 + j;
               const int t = kbl / kb_per_tap;
               const int kb = kbl - t * kb_per_tap;
-              uint8_t* sa = smem_a + (stage * KSUB + j) * kABytes;
+              uint8_t* sa = smem_a + (stage * KSUB + j) * kAT;
               uint8_t* sb = smem_b + (stage * KSUB + j) * Cfg::kBBytes;
               const int xs = x0 + p.tap_dx[t], ys = y0 + p.tap_dy[t] + p.y_pad;
               if (CG == 2) {
@@ -214,6 +244,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      if constexpr (SLAB) {
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
+            const uint32_t sa = ptx::smem_u32(smem_a + stage * kAT);
+            const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
+              const uint32_t a_off = (uint32_t)(((t / 3) * kSlabPitch + (t % 3)) * kRowBytes);
+              const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, kSlabPitch * kRowBytes);
+              const uint64_t db = ptx::make_sw128_kmajor_desc(sb + t * (BLOCK_N / CG) * kRowBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t accum = (kb | t | k) != 0 ? 1u : 0u;
+                if (CG == 2) ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              }
+            }
+            if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+            if (kb == kb_per_tap - 1) {
+              if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int g = 0; g < num_groups; ++g) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after_sync();
@@ -221,7 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (ptx::elect_one()) {
           for (int j = 0; j < nsub; ++j) {
             if (p.dbg & 2) break;                          // diagnostics: barriers only
-            const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + (stage * KSUB + j) * kABytes));
+            const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_a + (stage * KSUB + j) * kAT));
             const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + (stage * KSUB + j) * Cfg::kBBytes));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -504,7 +565,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps) {
+static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, bool slab = false) {
   PFN_encodeTiled enc = get_encode_fn();
   HDRVAE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   const int eb = dt_bytes(p.ab_dtype);
@@ -522,13 +583,23 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps) {
     cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * eb, (cuuint64_t)p.a_row_stride * eb,
                              (cuuint64_t)p.a_img_stride * eb};
     cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    if (slab) { box[1] = kSlabPitch; box[2] = kSlabRows; }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&maps->a, dt, 4, const_cast<void*>(p.a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (W=%d H=%d N=%d K=%d)", (int)r, p.W, p.H,
                    p.n_img, p.k_per_tap);
   }
-  {
+  if (slab) {
+    // B as {K of one tap, Cout rows, 9 taps}: one box brings the 9 taps' [rows][64] tiles of a K block, tap-major
+    cuuint64_t dims[3] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols), 9};
+    cuuint64_t strides[2] = {(cuuint64_t)p.b_row_stride * eb, (cuuint64_t)p.k_per_tap * eb};
+    cuuint32_t box[3] = {(cuuint32_t)row_elems, (cuuint32_t)block_n, 9};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&maps->b, dt, 3, const_cast<void*>(p.b), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, slab) failed: %d (K=%d cols=%d)", (int)r, p.k_per_tap, p.n_cols);
+  } else {
     cuuint64_t dims[2] = {(cuuint64_t)(p.b_img_k_stride > 0 ? p.b_img_k_stride * p.n_img : (long long)p.k_per_tap * p.ntaps),
                           (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols)};
     cuuint64_t strides[1] = {(cuuint64_t)p.b_row_stride * eb};
@@ -557,23 +628,23 @@ void choose_tile(int H, int W, GemmParams* p) {
   p->tiles_y = (H + p->TH - 1) / p->TH;
 }
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, bool SLAB = false>
 static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
-  constexpr int KSUB = (BLOCK_N <= 128) ? 2 : 1;
+  constexpr int KSUB = SLAB ? 1 : (BLOCK_N <= 128) ? 2 : 1;
   GemmParams p = p_in;
   if (p.res_scale == 0.f) p.res_scale = 1.f;
-  using Cfg = TcConfig<BLOCK_N, CG, KSUB>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
   {
     const char* d = getenv("HDRVAE_GEMM_DBG");
     p.dbg = d ? atoi(d) : 0;
   }
   p.n_tiles_n = (p.n_cols + BLOCK_N - 1) / BLOCK_N;
   TensorMapPair maps;
-  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps));            // a CTA of a pair stages half of the B rows
+  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB));      // a CTA of a pair stages half of the B rows
   static bool attr_set = false;
   if (!attr_set) {
-    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -594,7 +665,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB>, maps.a, maps.b, p));
+  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, maps.a, maps.b, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -626,6 +697,25 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
         (p.residual == nullptr || p.res_dtype == DT_F32)) {
       epi = (p.out_dtype != DT_F32 ? EPI_OUT16 : 0) | (p.residual ? EPI_RES : 0) | (p.residual2 ? EPI_RES2 : 0) |
             (p.out2 ? EPI_OUT2 : 0) | (p.lrelu != 0.f ? EPI_LRELU : 0);
+    }
+    if (p.slab) {
+      HDRVAE_REQUIRE(p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0,
+                     "gemm_tc: the slab variant is a 3x3 conv on 8x16-pixel tiles");
+      if (use_cg == 2) {
+        if (n32) {
+          if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<32, false, 2, EPI_OUT16 | EPI_LRELU, true>(p, num_sms, stream);
+          if (epi == 0) return launch_tc<32, false, 2, 0, true>(p, num_sms, stream);
+          return launch_tc<32, false, 2, EPI_GENERIC, true>(p, num_sms, stream);
+        }
+        if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<64, false, 2, EPI_OUT16 | EPI_LRELU, true>(p, num_sms, stream);
+        if (epi == (EPI_RES | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_OUT2, true>(p, num_sms, stream);
+        if (epi == (EPI_RES | EPI_RES2 | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_RES2 | EPI_OUT2, true>(p, num_sms, stream);
+        if (epi == EPI_OUT2) return launch_tc<64, false, 2, EPI_OUT2, true>(p, num_sms, stream);
+        return launch_tc<64, false, 2, EPI_GENERIC, true>(p, num_sms, stream);
+      }
+      // single CTAs: 64 columns x 9 taps of B do not leave room for two slab stages; 8x16 tiles also work tap by tap
+      return n32 ? launch_tc<32, false, 1, EPI_GENERIC, true>(p, num_sms, stream)
+                 : launch_tc<64, false, 1, EPI_GENERIC>(p, num_sms, stream);
     }
     if (n32) {
       if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<32, false, 2, EPI_OUT16 | EPI_LRELU>(p, num_sms, stream);
