@@ -149,3 +149,25 @@ def test_node_surface_and_call(nets, golden_dir, monkeypatch):
     assert _rel(out, torch.from_numpy(g["output"])) < 1e-2
     with pytest.raises(NotImplementedError):
         node.upscale(torch.from_numpy(g["image"]), "fake.pth", False, True, "bislerp")
+
+
+def test_c5_pipeline_decode_upscale_pack(nets):
+    """Config C5 in small: HDR decode -> 4x HDR upscale -> half packing, all on the GPU through the node-level calls,
+    against the oracle chain (reference decode math, reference upscaler math, numpy astype(float16))."""
+    from oracle import hdr_oracle as ho
+    from oracle.flux_decoder import build_decoder, make_latent
+    from vae_decode_hdr_b200.engine import HdrVaeEngine, pack_half
+    dec = build_decoder(0)
+    eng = HdrVaeEngine(dec.state_dict(), DEV)
+    net, up = nets[(2, 1.0)]
+    z = make_latent(1, 8, 8, seed=77)
+    img, _ = eng.decode(z.to(DEV), "moderate")
+    big = up.upscale(img, "atanh")
+    half = pack_half(big)
+    assert half.dtype == torch.float16 and half.shape == (1, 256, 256, 3)
+    assert np.array_equal(half.cpu().numpy(), big.cpu().numpy().astype(np.float16))        # the cast itself is bit-exact
+    ref_img, _, _ = ho.simple_hdr_decode(dec, z, "moderate", 1.0)
+    ref_big = uo.upscale(ref_img, uo.FakeDescriptor(net))
+    ref_half = torch.from_numpy(ref_big.numpy().astype(np.float16)).float()
+    assert _rel(half.float().cpu(), ref_half) < 1e-2, _rel(half.float().cpu(), ref_half)
+    eng.close()
