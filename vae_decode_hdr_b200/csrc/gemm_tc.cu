@@ -730,7 +730,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
     return use_cg == 2 ? launch_tc<64, false, 2, EPI_GENERIC>(p, num_sms, stream)
                        : launch_tc<64, false, 1, EPI_GENERIC>(p, num_sms, stream);
   }
-  if (use_cg == 2 && !tf32 && p.lrelu == 0.f && p.residual2 == nullptr && p.n_store == 0 && p.res_scale == 0.f) {
+  if (use_cg == 2 && !tf32 && p.lrelu == 0.f && p.residual2 == nullptr && (p.res_scale == 0.f || p.res_scale == 1.f)) {
     // specialised epilogues for what the decoder launches; anything else takes the generic build
     int epi = 0;
     const bool simple_res = p.residual == nullptr || p.res_dtype == DT_F32;
