@@ -11,7 +11,8 @@ from oracle import hdr_oracle as ho
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 MODES = list(ho.HDR_MODES)
-GOLD = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+              if not os.path.basename(p).startswith("up_"))          # up_*: upscaler goldens (test_gpu_upscaler.py)
 
 
 @pytest.fixture(scope="module")
