@@ -191,3 +191,34 @@ def test_row_tiled_decode_equals_single_gpu(setup, world, h, w, mode):
     assert st["pre_max"] == pytest.approx(st1["pre_max"], rel=2e-3) and st["norm_function"] == st1["norm_function"]
     if (world, h, w) == (2, 16, 16):
         assert _rel(tiled, whole) < 1e-6, _rel(tiled, whole)
+
+
+def test_full_size_c2_properties_and_gpu_oracle(setup):
+    """BASELINE config C2 at full size (4 x 16x128x128 -> 4 x 1024^2, "moderate"): properties that do not need a CPU
+    oracle run, plus the fp32 PyTorch oracle executed on the same GPU (TF32 off) for the whole batch.
+      * the multiplier is applied last (hdr_vae_decode.py:180-182): decode(ev=2) == 2 * decode(ev=1) exactly;
+      * batch order: decoding a permuted batch permutes the images (statistics are batch-global sums / extrema);
+        identical up to the order of the fp64 partial sums;
+      * rel-L2 <= 1e-2 against the fp32 oracle on all 4 images, statistics in agreement."""
+    dec, eng = setup
+    z = make_latent(4, 128, 128, seed=1234).to(DEV)
+    out1, st1 = eng.decode(z, "moderate", 1.0)
+    out2, _ = eng.decode(z, "moderate", 2.0)
+    assert out1.shape == (4, 1024, 1024, 3)
+    assert torch.equal(out2, out1 * 2.0)
+    perm = torch.tensor([2, 0, 3, 1], device=DEV)
+    outp, _ = eng.decode(z[perm].contiguous(), "moderate", 1.0)
+    assert torch.allclose(outp, out1[perm], rtol=1e-6, atol=1e-7)
+    del out2, outp
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dec_gpu = dec.to(DEV)
+    try:
+        ref, rst, _ = ho.simple_hdr_decode(dec_gpu, z, "moderate", 1.0)
+    finally:
+        dec.to("cpu")
+    assert _rel(out1, ref) < 1e-2, _rel(out1, ref)
+    for b in range(4):
+        assert _rel(out1[b], ref[b]) < 1e-2
+    assert st1["hdr_pixels"] == pytest.approx(rst["hdr_pixels"], rel=2e-3)
+    assert st1["out_max"] == pytest.approx(rst["out_max"], rel=2e-2)

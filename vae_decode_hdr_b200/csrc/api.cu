@@ -100,10 +100,12 @@ int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int 
   return 0;
 }
 
+// Upper bound of the m-tiles (= GroupNorm partial chunks) a conv over an H x W image is split into: the 128-pixel
+// patch choose_tile picks, or the 8 x 16 tiles of the slab variant.
 static int tiles_for(int H, int W) {
   GemmParams p;
   choose_tile(H, W, &p);
-  return p.tiles_x * p.tiles_y;
+  return std::max(p.tiles_x * p.tiles_y, ((W + 7) / 8) * ((H + 15) / 16));
 }
 
 
@@ -137,12 +139,14 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   p.cta_group = ctx->cta_group;
   choose_tile(H, W, &p);
   {
-    // narrow 3x3 convs (the upscaler's): L2 -> SM operand traffic of the 9 taps is the bound, so the activation slab
-    // is loaded once per tile (gemm_tc.cu slab variant); HDRVAE_SLAB=0 keeps the tap-reload form for A/B comparison
+    // 3x3 convs with <= 128 output columns (the upscaler's, and the decoder's 128-channel level): the operand traffic
+    // of the 9 taps and the pipeline depth a byte of smem buys are the bound, so the activation slab is staged once per
+    // K block (gemm_tc.cu slab variant); HDRVAE_SLAB=0 keeps the tap-reload form for A/B comparison
     static int slab_on = -1;
     if (slab_on < 0) { const char* e = getenv("HDRVAE_SLAB"); slab_on = (e && atoi(e) == 0) ? 0 : 1; }
-    if (slab_on && pc.ks == 3 && !pc.upsample && pc.cout_pad <= 64 && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT &&
-        io.stats == nullptr && H * W >= 128) {
+    // (measured: with 128 columns the in-place residual convs are faster on row-shaped 128x1 tiles: 1.57 vs 1.76 ms)
+    if (slab_on && pc.ks == 3 && !pc.upsample && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
+        (pc.cout_pad <= 64 || (pc.cout_pad <= 128 && io.residual == nullptr))) {
       p.slab = 1;
       p.tw_log2 = 3; p.TW = 8; p.TH = 16;
       p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;

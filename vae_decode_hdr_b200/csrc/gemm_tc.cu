@@ -35,23 +35,27 @@ constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 4 * 64 * 4 
 // CG = CTAs cooperating on one MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256-pixel x BLOCK_N
 // tile with M = 256 instructions; each CTA then stages only half of the B (weight) tile, which cuts the
 // L2->SM operand traffic by a third, deepens the pipeline and halves the per-MMA issue/barrier overhead.
-// SLAB (3x3 convs with <= 64 output columns, where the 9 taps re-reading the activation tile from L2 is the bound):
-// the tile is 8 x 16 pixels; per K block ONE TMA box of 18 rows x 16 pixels (the 10 x 18 halo slab at a 16-line
-// pitch) and ONE box with the 9 taps' weights are staged, and the 9 taps are shifted UMMA descriptors into the slab.
+// SLAB > 0 (3x3 convs): the tile is 8 x 16 pixels and its activation slab is staged ONCE per K block instead of once
+// per tap: one TMA box of 18 rows x 16 pixels (the 10 x 18 halo slab at a 16-line pitch) goes into a ring of
+// kSlabStages buffers, the weights go into their own ring in groups of SLAB taps (9, 3 or 1: one 3-D TMA box each),
+// and the 9 taps are shifted UMMA descriptors into the slab.  L2 -> SM operand traffic drops 4x and the MMA time a
+// byte of shared memory keeps in flight doubles, which is what bounds the layers with <= 128 output columns.
 constexpr int kSlabRows = 18, kSlabPitch = 16;
 constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 36 KB
-template <int BLOCK_N, int CG, int KSUB, bool SLAB = false>
+template <int BLOCK_N, int CG, int KSUB, int SLAB = 0>
 struct TcConfig {
-  static constexpr int kATile = SLAB ? kSlabBytes : kABytes;
-  static constexpr int kBBytes = (SLAB ? 9 : 1) * (BLOCK_N / CG) * kRowBytes;   // one k-sub-block of B staged by this CTA
-  static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block
-  static constexpr int kStageBytes = KSUB * kSubBytes;
-  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed) / kStageBytes;
+  static constexpr int kATile = kABytes;
+  static constexpr int kBBytes = (SLAB ? SLAB : 1) * (BLOCK_N / CG) * kRowBytes;   // one B stage staged by this CTA
+  static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block (tap-reload form)
+  static constexpr int kStageBytes = SLAB ? kBBytes : KSUB * kSubBytes;
+  // narrow tiles have short MMAs (a slab feeds 36 MMAs of 32 cycles): three slabs in flight cover the TMA latency
+  static constexpr int kSlabStages = SLAB ? (BLOCK_N <= 64 ? 3 : 2) : 0;
+  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-  static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 256 / 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSmemFixed;
+  static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 64 ... 512)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBytes + kSmemFixed;
   static_assert(kStages >= (SLAB ? 2 : 3) && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
-  static_assert(!SLAB || KSUB == 1, "the slab variant stages one K block per pipeline slot");
+  static_assert(SLAB == 0 || ((SLAB == 9 || SLAB == 3 || SLAB == 1) && KSUB == 1), "the slab variant stages 9, 3 or 1 taps of B per pipeline slot");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -102,7 +106,7 @@ enum : int {
   EPI_RES2 = 128,    // + second fp32 residual (end of an RRDB: 0.04 acc + 0.2 x2 + x0)
 };
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, bool SLAB = false>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
@@ -117,15 +121,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // SWIZZLE_128B needs 1024-byte aligned stage buffers.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * KSUB * kAT;
-  float* stage_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);     // [8 warps][32 rows][32 floats]
+  // tap-reload form: [A stages][B stages]; slab form: [B stages][slab ring]
+  uint8_t* smem_b = SLAB ? smem : smem + kStages * KSUB * kAT;
+  uint8_t* smem_slab = smem + kStages * Cfg::kStageBytes;
+  float* stage_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kSlabStages * kSlabBytes);   // [8 warps][32 rows][32 floats]
   float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
   uint64_t* full_bar = bars;                      // [kStages]
   uint64_t* empty_bar = bars + kStages;           // [kStages]
   uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* slab_full_bar = bars + 2 * kStages + 4;   // [3]
+  uint64_t* slab_empty_bar = bars + 2 * kStages + 7;  // [3]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,6 +144,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      ptx::mbar_init(&slab_full_bar[i], 1);
+      ptx::mbar_init(&slab_empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
@@ -169,8 +181,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_groups = (num_kb + KSUB - 1) / KSUB;
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, ss = 0;
+    uint32_t phase = 0, sphase = 0;
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
       const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
@@ -180,24 +192,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = rem - ty * p.tiles_x;
       const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / CG);
       const int bk0 = (int)(img * p.b_img_k_stride);       // split-K: this image's K range of B
-      if constexpr (SLAB) {
+      if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
           if (ptx::elect_one()) {
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * Cfg::kSubBytes));
-            uint8_t* sa = smem_a + stage * kAT;
-            uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
+            uint8_t* sa = smem_slab + ss * kSlabBytes;
             // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
-            if (CG == 2) {
-              ptx::tma_load_4d_pair(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-              ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, 0);
-            } else {
-              ptx::tma_load_4d(sa, &tmA, &full_bar[stage], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-              ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, 0);
-            }
+            if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+            else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+          for (int tg = 0; tg < 9 / SLAB; ++tg) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (ptx::elect_one()) {
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * Cfg::kBBytes));
+              uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+              if (CG == 2) ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, tg * SLAB);
+              else ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, tg * SLAB);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
         continue;
       }
@@ -236,41 +253,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ MMA issuer (one warp of the leader CTA)
     const uint32_t idesc = kTf32 ? ptx::make_idesc(2u, kBlockM * CG, BLOCK_N)
                                  : ptx::make_idesc(p.ab_dtype == DT_BF16 ? 1u : 0u, kBlockM * CG, BLOCK_N);
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, ss = 0;
+    uint32_t phase = 0, sphase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      if constexpr (SLAB) {
+      if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after_sync();
-          if (ptx::elect_one()) {
-            const uint32_t sa = ptx::smem_u32(smem_a + stage * kAT);
-            const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
+          ptx::mbar_wait(&slab_full_bar[ss], sphase);
+          const uint32_t sa = ptx::smem_u32(smem_slab + ss * kSlabBytes);
+          for (int tg = 0; tg < 9 / SLAB; ++tg) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+              const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
-              const uint32_t a_off = (uint32_t)(((t / 3) * kSlabPitch + (t % 3)) * kRowBytes);
-              const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, kSlabPitch * kRowBytes);
-              const uint64_t db = ptx::make_sw128_kmajor_desc(sb + t * (BLOCK_N / CG) * kRowBytes);
+              for (int tt = 0; tt < SLAB; ++tt) {
+                // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
+                const int t = tg * SLAB + tt;
+                const uint32_t a_off = (uint32_t)(((t / 3) * kSlabPitch + (t % 3)) * kRowBytes);
+                const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, kSlabPitch * kRowBytes);
+                const uint64_t db = ptx::make_sw128_kmajor_desc(sb + tt * (BLOCK_N / CG) * kRowBytes);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t accum = (kb | t | k) != 0 ? 1u : 0u;
-                if (CG == 2) ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
-                else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t accum = (kb | t | k) != 0 ? 1u : 0u;
+                  if (CG == 2) ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                  else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                }
+              }
+              if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+              if (tg == 9 / SLAB - 1) {
+                if (CG == 2) ptx::umma_commit_pair(&slab_empty_bar[ss]); else ptx::umma_commit(&slab_empty_bar[ss]);
+                if (kb == kb_per_tap - 1) {
+                  if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
+                }
               }
             }
-            if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
-            if (kb == kb_per_tap - 1) {
-              if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
-            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
@@ -394,20 +419,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      bool waited = false;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      // Software pipeline over the warp's chunks: the TMEM load of chunk ci+1 is issued as soon as the registers of
+      // chunk ci have gone to the transpose patch, so it overlaps the store phase.  (Prefetching the next chunk's
+      // residual the same way was measured 13 % SLOWER on the 128-channel layers: it competes with the stores.)
+      float4 rres[8];
+      auto load_res = [&](int ci, float4 (&dst)[8]) {
+        if (!has_res_f32) return;
+        const int colx = cbase + ci * 32 + slot * 4;
+        const uint32_t cm = (n0 + colx) < n_store ? pmask : 0u;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (cm >> it & 1) dst[it] = *reinterpret_cast<const float4*>(resf + poff[it] + colx);   // plain load: may alias out
+      };
+      load_res(0, rres);
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(t_row + cbase, v);
 #pragma unroll 1
       for (int ci = 0; ci < kChunksPerWarp; ++ci) {
         const int c0 = cbase + ci * 32;
         const int col = c0 + slot * 4;                    // first of this lane's 4 columns (tile-relative)
         const uint32_t cmask = (n0 + col) < n_store ? pmask : 0u;   // n_cols % 32 == 0 and n_store % 4 == 0 on every call site
-        // residual: coalesced loads issued first so they overlap the accumulator wait / TMEM load / transpose
-        float4 rres[8];
-        if (has_res_f32) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it)
-            if (cmask >> it & 1) rres[it] = *reinterpret_cast<const float4*>(resf + poff[it] + col);   // plain load: may alias out
-        }
+        if (ci > 0) load_res(ci, rres);                   // residual: issued first, overlaps the TMEM wait / transpose
+        if (ci > 0 && (p.dbg & 4)) ptx::tmem_ld_32x32(t_row + c0, v);   // diagnostics: un-pipelined TMEM load
         float4 rres2[8];
         if (has_res2) {
 #pragma unroll
@@ -416,19 +452,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!(row_ops && p.bias_per_row) && p.bias != nullptr && cmask != 0u) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
-        if (!waited) {
-          ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-          ptx::tc_fence_after_sync();
-          waited = true;
-        }
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_row + c0, v);
         ptx::tmem_ld_wait(v);
         __syncwarp();                                     // previous chunk's readers are done with the patch
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           patch[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        if (ci + 1 < kChunksPerWarp && !(p.dbg & 4)) {    // v has been consumed: start the next chunk's loads now
+          ptx::tmem_ld_32x32(t_row + c0 + 32, v);
+        }
         __syncwarp();
         float s_acc = 0.f, q_acc = 0.f;
 #pragma unroll
@@ -565,7 +597,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, bool slab = false) {
+static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int slab = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   HDRVAE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   const int eb = dt_bytes(p.ab_dtype);
@@ -594,7 +626,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, bool
     // B as {K of one tap, Cout rows, 9 taps}: one box brings the 9 taps' [rows][64] tiles of a K block, tap-major
     cuuint64_t dims[3] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols), 9};
     cuuint64_t strides[2] = {(cuuint64_t)p.b_row_stride * eb, (cuuint64_t)p.k_per_tap * eb};
-    cuuint32_t box[3] = {(cuuint32_t)row_elems, (cuuint32_t)block_n, 9};
+    cuuint32_t box[3] = {(cuuint32_t)row_elems, (cuuint32_t)block_n, (cuuint32_t)slab};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&maps->b, dt, 3, const_cast<void*>(p.b), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -628,7 +660,7 @@ void choose_tile(int H, int W, GemmParams* p) {
   p->tiles_y = (H + p->TH - 1) / p->TH;
 }
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, bool SLAB = false>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0>
 static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
   constexpr int KSUB = SLAB ? 1 : (BLOCK_N <= 128) ? 2 : 1;
@@ -703,18 +735,18 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
                      "gemm_tc: the slab variant is a 3x3 conv on 8x16-pixel tiles");
       if (use_cg == 2) {
         if (n32) {
-          if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<32, false, 2, EPI_OUT16 | EPI_LRELU, true>(p, num_sms, stream);
-          if (epi == 0) return launch_tc<32, false, 2, 0, true>(p, num_sms, stream);
-          return launch_tc<32, false, 2, EPI_GENERIC, true>(p, num_sms, stream);
+          if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<32, false, 2, EPI_OUT16 | EPI_LRELU, 9>(p, num_sms, stream);
+          if (epi == 0) return launch_tc<32, false, 2, 0, 9>(p, num_sms, stream);
+          return launch_tc<32, false, 2, EPI_GENERIC, 9>(p, num_sms, stream);
         }
-        if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<64, false, 2, EPI_OUT16 | EPI_LRELU, true>(p, num_sms, stream);
-        if (epi == (EPI_RES | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_OUT2, true>(p, num_sms, stream);
-        if (epi == (EPI_RES | EPI_RES2 | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_RES2 | EPI_OUT2, true>(p, num_sms, stream);
-        if (epi == EPI_OUT2) return launch_tc<64, false, 2, EPI_OUT2, true>(p, num_sms, stream);
-        return launch_tc<64, false, 2, EPI_GENERIC, true>(p, num_sms, stream);
+        if (epi == (EPI_OUT16 | EPI_LRELU)) return launch_tc<64, false, 2, EPI_OUT16 | EPI_LRELU, 9>(p, num_sms, stream);
+        if (epi == (EPI_RES | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_OUT2, 9>(p, num_sms, stream);
+        if (epi == (EPI_RES | EPI_RES2 | EPI_OUT2)) return launch_tc<64, false, 2, EPI_RES | EPI_RES2 | EPI_OUT2, 9>(p, num_sms, stream);
+        if (epi == EPI_OUT2) return launch_tc<64, false, 2, EPI_OUT2, 9>(p, num_sms, stream);
+        return launch_tc<64, false, 2, EPI_GENERIC, 9>(p, num_sms, stream);
       }
       // single CTAs: 64 columns x 9 taps of B do not leave room for two slab stages; 8x16 tiles also work tap by tap
-      return n32 ? launch_tc<32, false, 1, EPI_GENERIC, true>(p, num_sms, stream)
+      return n32 ? launch_tc<32, false, 1, EPI_GENERIC, 9>(p, num_sms, stream)
                  : launch_tc<64, false, 1, EPI_GENERIC>(p, num_sms, stream);
     }
     if (n32) {
@@ -746,6 +778,13 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       }
     } else {
       epi = -1;
+    }
+    if (p.slab && n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
+      // the decoder's 128-channel 3x3 convs: slab variant, weights in groups of 3 taps
+      if (epi == EPI_STATS) return launch_tc<128, false, 2, EPI_STATS, 3>(p, num_sms, stream);
+      if (epi == (EPI_RES | EPI_STATS)) return launch_tc<128, false, 2, EPI_RES | EPI_STATS, 3>(p, num_sms, stream);
+      if (epi == 0) return launch_tc<128, false, 2, 0, 3>(p, num_sms, stream);
+      if (epi == EPI_RES) return launch_tc<128, false, 2, EPI_RES, 3>(p, num_sms, stream);
     }
 #define HDRVAE_EPI_CASE(E)                                                                       \
     case E:                                                                                      \

@@ -285,6 +285,8 @@ class HdrVaeEngine:
                 rs.data_ptr() if rs is not None else None, _DTYPE_ID[rs.dtype] if rs is not None else 0, y.data_ptr(),
                 _DTYPE_ID[out_dtype], int(round_tf32), part.data_ptr() if want_stats else None, C.byref(nch), impl,
                 self._stream()), "hdrvae_conv2d")
+        if want_stats:      # the library packs the partials with the chunk count it actually used (<= the capacity asked for)
+            part = part.flatten()[:B * nch.value * 64].view(B, nch.value, 32, 2)
         return (y, part) if want_stats else y
 
     def groupnorm_silu(self, x_nhwc: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, silu: bool = True,
