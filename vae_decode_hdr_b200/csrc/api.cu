@@ -373,6 +373,23 @@ static int attention_rows(hdrvae_ctx* ctx, uint8_t* ws, size_t off_s, size_t off
   return 0;
 }
 
+// Epilogue phase A on the decoder's features (slab start `feat`, `pad` halo rows above / below each image's H rows).
+// fp16 operands: conv_out runs on the tensor cores into `conv8` (dense [B][H][W][8] fp32 scratch), then one streaming
+// pass does the MAX-pool and the statistics; otherwise (bf16 operands, validation kernel, HDRVAE_TC_CONVOUT=0) the
+// all-in-one CUDA-core kernel.
+static int run_phase_a(hdrvae_ctx* ctx, const void* feat, int B, int H, int W, int pad, float* conv8, void* epi, cudaStream_t s) {
+  static int tc_on = -1;
+  if (tc_on < 0) { const char* e = getenv("HDRVAE_TC_CONVOUT"); tc_on = (e && atoi(e) == 0) ? 0 : 1; }
+  const long long img_stride = (long long)(H + 2 * pad) * W * 128;
+  const uint16_t* interior = reinterpret_cast<const uint16_t*>(feat) + (size_t)pad * W * 128;
+  if (tc_on && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && ctx->conv_out_tc.w[0] != nullptr) {
+    ConvIO io; io.x = feat; io.x_pad = pad; io.y = conv8; io.y_dtype = DT_F32; io.y_channels = 8; io.n_store = 8;
+    HDRVAE_TRY(run_conv(ctx, ctx->conv_out_tc, io, B, H, W, HDRVAE_CONV_TCGEN05, s));
+    return launch_epilogue_phase_a_pre(interior, ctx->op_dtype, B, H, W, conv8, ctx->conv_out_b, nullptr, epi, s, img_stride);
+  }
+  return launch_epilogue_phase_a(interior, ctx->op_dtype, B, H, W, ctx->conv_out_w, ctx->conv_out_b, nullptr, epi, s, pad, img_stride);
+}
+
 static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const void* qk /*[B][Tp][1024]*/,
                               const void* vt /*[B][512][Tp]*/, void* o /*[B][T][512]*/, float qk_alpha,
                               cudaStream_t s) {
@@ -712,10 +729,9 @@ static int build_rows_program(hdrvae_rows* st) {
     float* x = st->x;
     rows_gn(st, x, ctx->norm_out, true, H, W);
     void* epi = ws + pl.off_epi;
+    float* hscratch = st->hbuf;                       // the other fp32 stream buffer is free by now
     rows_compute(st, [=](cudaStream_t s) {
-      const uint16_t* pre = reinterpret_cast<const uint16_t*>(t) + (size_t)W * 128;      // interior row 0
-      return launch_epilogue_phase_a(pre, dt, 1, H, W, ctx->conv_out_w, ctx->conv_out_b, nullptr, epi, s, 1,
-                                     (long long)(H + 2) * W * 128);
+      return run_phase_a(ctx, t, 1, H, W, 1, hscratch, epi, s);
     });
     hdrvae_exchange ex;
     memset(&ex, 0, sizeof ex);
@@ -909,6 +925,14 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
   HDRVAE_TRY(need_conv("conv_out", 3, 128, 3));
   ctx->conv_out_w = W("conv_out.weight");
   ctx->conv_out_b = W("conv_out.bias");
+  if (op == DT_F16) {
+    // conv_out on the tensor cores for the product path: fp32 weights as fp16 hi + lo rows (exact to ~2^-21)
+    float* w8 = nullptr;
+    HDRVAE_CUDA_OK(cudaMalloc((void**)&w8, 8 * 1152 * sizeof(float)));
+    staging.push_back(w8);
+    HDRVAE_TRY(launch_split_hi_lo(ctx->conv_out_w, w8, 1152, s));
+    HDRVAE_TRY(pack_conv(ctx, w8, nullptr, 8, 128, 3, false, 1.f, DT_F16, &ctx->conv_out_tc, s));
+  }
   HDRVAE_CUDA_OK(cudaStreamSynchronize(s));
   for (void* p : staging) cudaFree(p);
   ctx->loaded = true;
@@ -935,8 +959,7 @@ int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int 
   HDRVAE_TRY(run_decoder(ctx, latent, pl, ws, &feat, s));
   {
     ProfScope prof("epilogue phase A (conv_out, max-pool, stats)", 2.0 * B * 64.0 * h * w * 3 * 1152, B * 64.0 * h * w * (256 + 24), s);
-    HDRVAE_TRY(launch_epilogue_phase_a(feat, ctx->op_dtype, B, 8 * h, 8 * w, ctx->conv_out_w, ctx->conv_out_b, nullptr,
-                                       ws + pl.off_epi, s));
+    HDRVAE_TRY(run_phase_a(ctx, feat, B, 8 * h, 8 * w, 0, reinterpret_cast<float*>(ws + pl.off_h), ws + pl.off_epi, s));
   }
   if (raw_stats_dev != nullptr) *raw_stats_dev = epilogue_raw_stats_ptr(ws + pl.off_epi, B, 8 * h, 8 * w);
   return 0;

@@ -43,6 +43,9 @@ int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n
 int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
                               int B, int rows_px, int C, const float* gamma, const float* beta, bool silu, void* scratch,
                               int max_chunks, double count, cudaStream_t s);
+int launch_epilogue_phase_a_pre(const void* pre, int dtype, int B, int H, int W, const float* conv8, const float* conv_b,
+                                int* argmax3, void* scratch, cudaStream_t s, long long img_stride);
+int launch_split_hi_lo(const float* w, float* w8, int k, cudaStream_t s);
 int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
                             void* scratch, cudaStream_t s);
 
@@ -108,6 +111,7 @@ struct hdrvae_ctx {
   NormW attn_norm, norm_out;
   ResW mid1, mid2, up[4][3];
   PackedConv upsample[4];
+  PackedConv conv_out_tc;                         // conv_out as an 8-row fp16 operand: rows 0-2 hi, 4-6 lo of the fp32 weights
   float* conv_out_w = nullptr;                    // fp32 OIHW [3][128][3][3]
   float* conv_out_b = nullptr;
 };

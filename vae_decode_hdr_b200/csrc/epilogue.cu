@@ -294,6 +294,145 @@ hdr_phase_a_kernel(const T* __restrict__ pre, const float* __restrict__ conv_w /
   }
 }
 
+// ------------------------------------------------------------------------------------ phase A, conv_out precomputed
+// Product path for 16-bit features: conv_out (128 -> 3, 3x3) has already run on the tensor cores (gemm_tc.cu slab
+// variant) with the fp32 weights split into fp16 hi + lo rows, so conv8[px] = {hi r,g,b,0, lo r,g,b,0} and
+// conv = hi + lo + bias reproduces the fp32 convolution of the 16-bit features to ~1e-7.  What is left is one
+// streaming pass over `pre`: the 128 -> 3 channel MAX-pool with first-max index and the statistics.  Same 64 x 16
+// pixel block per CTA and the same PartialA layout as hdr_phase_a_kernel; 8 lanes share a pixel (16 channels each:
+// a warp load covers 4 pixels x 128 contiguous bytes).
+template <typename T, bool kArgmax>
+__global__ void __launch_bounds__(kEpiThreads)
+hdr_phase_a_pre_kernel(const T* __restrict__ pre, const float4* __restrict__ conv8, const float* __restrict__ conv_b, int H,
+                       int W, float* __restrict__ post3, float* __restrict__ pre3, int* __restrict__ argmax3,
+                       PartialA* __restrict__ partials, long long img_stride) {
+  const int img = blockIdx.z;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane & 7;                 // which 16 channels of the pixel
+  const int pq = lane >> 3;                 // which of the warp's 4 pixels
+  const T* img_base = pre + (long long)img * img_stride;
+  const float cb[3] = {conv_b[0], conv_b[1], conv_b[2]};
+  float smin = INFINITY, smax = -INFINITY, ssum = 0.f, ssq = 0.f;
+  float cmin = INFINITY, cmax = -INFINITY, csum = 0.f;
+  float pmin = INFINITY, pmax = -INFINITY, psum = 0.f, psq = 0.f;
+  float p3min = INFINITY, p3max = -INFINITY;
+  float hl = 0.f, nlive = 0.f;
+  // block pixels in row-major order, 32 per iteration (8 warps x 4).  Lane `sub` holds channels 8 sub .. 8 sub + 7 and
+  // 64 + 8 sub .. 64 + 8 sub + 7: each of the two 16-byte loads of a warp covers 4 pixels x 128 contiguous bytes.  The
+  // loads of iteration it+1 are issued before iteration it is processed (the pass is latency bound otherwise).
+  constexpr int kIters = kTileW * kTileH / 32;
+  auto px_of = [&](int it, int* gx, int* gy) {
+    const int bp = it * 32 + warp * 4 + pq;
+    *gx = x0 + (bp % kTileW); *gy = y0 + (bp / kTileW);
+    return *gx < W && *gy < H;
+  };
+  uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+  {
+    int gx, gy;
+    if (px_of(0, &gx, &gy)) {
+      const uint4* src = reinterpret_cast<const uint4*>(img_base + ((long long)gy * W + gx) * kC + sub * 8);
+      n0 = __ldg(src); n1 = __ldg(src + 8);
+    }
+  }
+  for (int it = 0; it < kIters; ++it) {
+    int gx, gy;
+    const bool live = px_of(it, &gx, &gy);
+    const uint4 r0 = n0, r1 = n1;
+    if (it + 1 < kIters) {
+      int nx, ny;
+      if (px_of(it + 1, &nx, &ny)) {
+        const uint4* src = reinterpret_cast<const uint4*>(img_base + ((long long)ny * W + nx) * kC + sub * 8);
+        n0 = __ldg(src); n1 = __ldg(src + 8);
+      }
+    }
+    float v[16];
+    {
+      const float4 a = Cvt4<T>::cvt(make_uint2(r0.x, r0.y)), b = Cvt4<T>::cvt(make_uint2(r0.z, r0.w));
+      const float4 c = Cvt4<T>::cvt(make_uint2(r1.x, r1.y)), d = Cvt4<T>::cvt(make_uint2(r1.z, r1.w));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+    }
+    float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int am[3] = {0, 42, 84};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = (j < 8 ? 0 : 64) + sub * 8 + (j & 7);
+      if (live) {
+        smin = fminf(smin, v[j]); smax = fmaxf(smax, v[j]); ssum += v[j]; ssq = fmaf(v[j], v[j], ssq);
+      }
+      // channel MAX-pool 0-41 / 42-83 / 84-125 (hdr_vae_decode.py:1044-1051); strict > keeps the first max.
+      // Predicated, not branched: the 8 lanes of a pixel sit in different groups.
+      const bool in0 = c < 42, in1 = c >= 42 && c < 84, in2 = c >= 84 && c < 126;
+      if (kArgmax) {
+        if (in0 && v[j] > mx[0]) { mx[0] = v[j]; am[0] = c; }
+        if (in1 && v[j] > mx[1]) { mx[1] = v[j]; am[1] = c; }
+        if (in2 && v[j] > mx[2]) { mx[2] = v[j]; am[2] = c; }
+      } else {
+        mx[0] = in0 ? fmaxf(mx[0], v[j]) : mx[0];
+        mx[1] = in1 ? fmaxf(mx[1], v[j]) : mx[1];
+        mx[2] = in2 ? fmaxf(mx[2], v[j]) : mx[2];
+      }
+    }
+    // combine the 8 lanes of the pixel: larger value wins, equal values keep the smaller channel index
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float ov = __shfl_xor_sync(~0u, mx[k], o);
+        const int oi = __shfl_xor_sync(~0u, am[k], o);
+        if (ov > mx[k] || (kArgmax && ov == mx[k] && oi < am[k])) { mx[k] = ov; am[k] = oi; }
+      }
+    }
+    if (live && sub == 0) {
+      const long long px = ((long long)img * H + gy) * W + gx;
+      const float4 hi = conv8[px * 2], lo = conv8[px * 2 + 1];
+      const float cvv[3] = {(hi.x + lo.x) + cb[0], (hi.y + lo.y) + cb[1], (hi.z + lo.z) + cb[2]};
+      nlive += 3.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float cv = cvv[k];
+        // comfy.sd.VAE.decode process_output: clamp((x + 1) / 2, 0, 1)
+        const float sv = fminf(fmaxf(__fdiv_rn(__fadd_rn(cv, 1.0f), 2.0f), 0.f), 1.f);
+        post3[px * 3 + k] = sv;
+        pre3[px * 3 + k] = mx[k];
+        if (kArgmax) argmax3[px * 3 + k] = am[k];
+        cmin = fminf(cmin, cv); cmax = fmaxf(cmax, cv); csum += cv;
+        pmin = fminf(pmin, sv); pmax = fmaxf(pmax, sv); psum += sv; psq += sv * sv;
+        p3min = fminf(p3min, mx[k]); p3max = fmaxf(p3max, mx[k]);
+        hl += mx[k] > 1.0f ? 1.f : 0.f;
+      }
+    }
+  }
+  __shared__ float rmin[4][8], rmax[4][8];
+  __shared__ double rsum[8][8];
+  const float mins[4] = {warp_min(smin), warp_min(pmin), warp_min(cmin), warp_min(p3min)};
+  const float maxs[4] = {warp_max(smax), warp_max(pmax), warp_max(cmax), warp_max(p3max)};
+  const double sums[8] = {warp_sum((double)ssum), warp_sum((double)ssq), warp_sum((double)psum), warp_sum((double)psq),
+                          warp_sum((double)csum), 0.0, warp_sum((double)nlive), warp_sum((double)hl)};
+  if (lane == 0) {
+    for (int k = 0; k < 4; ++k) { rmin[k][warp] = mins[k]; rmax[k][warp] = maxs[k]; }
+    for (int k = 0; k < 8; ++k) rsum[k][warp] = sums[k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    PartialA pa;
+    for (int k = 0; k < 4; ++k) {
+      float a = rmin[k][0], b = rmax[k][0];
+      for (int w2 = 1; w2 < 8; ++w2) { a = fminf(a, rmin[k][w2]); b = fmaxf(b, rmax[k][w2]); }
+      pa.vmin[k] = a; pa.vmax[k] = b;
+    }
+    for (int k = 0; k < 8; ++k) {
+      double a = 0.0;
+      for (int w2 = 0; w2 < 8; ++w2) a += rsum[k][w2];
+      pa.vsum[k] = a;
+    }
+    const int ix = min(kTileW, W - x0), iy = min(kTileH, H - y0);
+    pa.vsum[5] = (double)ix * iy * kC;        // number of pre elements owned by this block
+    partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = pa;
+  }
+}
+
 // ------------------------------------------------------------------------------------ reduce partials
 __global__ void __launch_bounds__(256)
 hdr_reduce_a_kernel(const PartialA* __restrict__ partials, int n, hdrvae_raw_stats* __restrict__ raw) {
@@ -552,6 +691,29 @@ int launch_epilogue_phase_a(const void* pre, int dtype, int B, int H, int W, con
   } else {
     HDRVAE_REQUIRE(false, "epilogue: unsupported activation dtype %d", dtype);
   }
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  hdr_reduce_a_kernel<<<1, 256, 0, s>>>(e.pa, n_blocks_a(B, H, W), e.raw);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Phase A with conv_out precomputed on the tensor cores (16-bit features only; see hdr_phase_a_pre_kernel).
+// `pre` points at interior row 0 of each image (img_stride elements apart), conv8 is dense [B][H][W][8] fp32.
+int launch_epilogue_phase_a_pre(const void* pre, int dtype, int B, int H, int W, const float* conv8, const float* conv_b,
+                                int* argmax3, void* scratch, cudaStream_t s, long long img_stride) {
+  HDRVAE_REQUIRE(dtype == HDRVAE_F16 || dtype == HDRVAE_BF16, "epilogue (precomputed conv): 16-bit features only");
+  if (img_stride == 0) img_stride = (long long)H * W * kC;
+  EpilogueScratch e = carve(scratch, B, H, W);
+  const dim3 grid(ceil_div(W, kTileW), ceil_div(H, kTileH), B);
+  HDRVAE_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "epilogue: image too large for the launch grid");
+  const float4* c8 = reinterpret_cast<const float4*>(conv8);
+#define HDRVAE_PA_PRE(T, AM) hdr_phase_a_pre_kernel<T, AM><<<grid, kEpiThreads, 0, s>>>(reinterpret_cast<const T*>(pre), c8, conv_b, \
+                                                                                       H, W, e.post3, e.pre3, argmax3, e.pa, img_stride)
+  if (dtype == HDRVAE_F16) { if (argmax3) HDRVAE_PA_PRE(__half, true); else HDRVAE_PA_PRE(__half, false); }
+  else { if (argmax3) HDRVAE_PA_PRE(__nv_bfloat16, true); else HDRVAE_PA_PRE(__nv_bfloat16, false); }
+#undef HDRVAE_PA_PRE
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   hdr_reduce_a_kernel<<<1, 256, 0, s>>>(e.pa, n_blocks_a(B, H, W), e.raw);

@@ -190,6 +190,27 @@ int launch_gemm_direct(const GemmParams& p, cudaStream_t s) {
   return 0;
 }
 
+// ------------------------------------------------------------------ fp32 weights -> fp16 hi / lo rows
+// w [rows][k] fp32 -> w8 [8][k] fp32: rows 0..2 = w (packs to hi = fp16(w)), rows 4..6 = w - float(fp16(w)) (packs to
+// lo), rows 3 and 7 zero; rows must be 3 (conv_out).  hi + lo carries ~21 mantissa bits of w.
+__global__ void split_hi_lo_kernel(const float* __restrict__ w, float* __restrict__ w8, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 8 * k) return;
+  const int r = i / k, c = i - r * k;
+  float v = 0.f;
+  if ((r & 3) < 3) {
+    const float x = w[(r & 3) * k + c];
+    v = r < 4 ? x : x - __half2float(__float2half_rn(x));
+  }
+  w8[i] = v;
+}
+int launch_split_hi_lo(const float* w, float* w8, int k, cudaStream_t s) {
+  split_hi_lo_kernel<<<ceil_div(8 * k, 256), 256, 0, s>>>(w, w8, k);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ attention row softmax, split form
 // fp32 scores -> e = exp(s - rowmax) as 16-bit operand (max element is exactly 1: no fp16 range problem
 // for long rows) + inv_sum[row] = 1 / sum(exp), applied later as the PV GEMM's per-row scale.
