@@ -51,18 +51,58 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region (B200_PROFILING.md recipe).
+    NVML in-process (microseconds per query, so even a 0.2 s region yields dozens of samples on an 8-GPU box where
+    spawning nvidia-smi takes longer than the region); `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.stop, self.t, self.src = [], None, index, False, None, None
+
+    def _nvml_loop(self, nv, h):
+        bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.src = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.src = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -74,27 +114,29 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif self.t is not None:
+            self.t.join(timeout=1)
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[2:6]):
+                for n, v in zip(self.NAMES, r[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.src}
 
 
 def cpu_reference_run(steps: int, warmup: int, sample_latent: int = 32):
