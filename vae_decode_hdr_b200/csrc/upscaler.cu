@@ -34,10 +34,10 @@ __global__ void up_extract_tiles_kernel(const float* __restrict__ img, int H, in
     const int x = (int)(i % w);
     const int y = (int)((i / w) % h);
     const int t = (int)(i / ((long long)w * h));
-    const int4 tl = tiles[t];
+    const int4 tl = tiles[t];                     // image, y0, x0, clamp flag
     const float* src = img + (((long long)tl.x * H + tl.y + y) * W + tl.z + x) * 3;
     float r = src[0], g = src[1], b = src[2];
-    if (clamp1) { r = fminf(fmaxf(r, -1.f), 1.f); g = fminf(fmaxf(g, -1.f), 1.f); b = fminf(fmaxf(b, -1.f), 1.f); }
+    if (clamp1 || tl.w) { r = fminf(fmaxf(r, -1.f), 1.f); g = fminf(fmaxf(g, -1.f), 1.f); b = fminf(fmaxf(b, -1.f), 1.f); }
     const __half2 rg = __floats2half2_rn(r, g), b0 = __floats2half2_rn(b, 0.f);
     uint4 o;
     o.x = *reinterpret_cast<const uint32_t*>(&rg);
@@ -76,7 +76,7 @@ __global__ void up_finish_tiles_kernel(const float4* __restrict__ in, long long 
 
 struct UpTile {             // one tile of comfy.utils.tiled_scale, output coordinates
   int b, oy, ox, oh, ow;    // image index, origin and size on the upscaled grid
-  long long off;            // float4 offset of the tile's model output
+  long long off, off2;      // float4 offsets of the tile's model output: pass 1 (input as is), pass 2 (input clamped)
 };
 
 // feather weight of output row/col `i` of a tile of length `len` (restated tiled_scale: ramps (t+1)/feather applied
@@ -91,10 +91,10 @@ __device__ __forceinline__ float up_feather(float m, int i, int len, int feather
 // Blend of one pass: for every output pixel the tiles covering it, in the reference's accumulation order
 // (itertools.product: y outer, x inner): out += reversal(ps) * mask; div += mask; result out / div.
 __device__ __forceinline__ void up_blend_px(const float4* __restrict__ tiles_out, const UpTile* __restrict__ tl, int t0, int t1,
-                                            int single, int b, int y, int x, int feather, int kind, float* rgb) {
+                                            int single, int second, int b, int y, int x, int feather, int kind, float* rgb) {
   if (single) {
     const UpTile t = tl[t0 + b];
-    const float4 v = tiles_out[t.off + (long long)y * t.ow + x];
+    const float4 v = tiles_out[(second ? t.off2 : t.off) + (long long)y * t.ow + x];
     rgb[0] = up_reversal(v.x, kind); rgb[1] = up_reversal(v.y, kind); rgb[2] = up_reversal(v.z, kind);
     return;
   }
@@ -106,7 +106,7 @@ __device__ __forceinline__ void up_blend_px(const float4* __restrict__ tiles_out
     float m = 1.f;
     m = up_feather(m, ly, t.oh, feather);
     m = up_feather(m, lx, t.ow, feather);
-    const float4 v = tiles_out[t.off + (long long)ly * t.ow + lx];
+    const float4 v = tiles_out[(second ? t.off2 : t.off) + (long long)ly * t.ow + lx];
     acc[0] = __fadd_rn(acc[0], __fmul_rn(up_reversal(v.x, kind), m));
     acc[1] = __fadd_rn(acc[1], __fmul_rn(up_reversal(v.y, kind), m));
     acc[2] = __fadd_rn(acc[2], __fmul_rn(up_reversal(v.z, kind), m));
@@ -124,7 +124,7 @@ __device__ __forceinline__ void up_rgb_to_ycbcr(const float* rgb, float* ycc) {
 }
 
 // Both passes blended -> (clamp(Y_unclamped, 0, 8), Cb_clamped, Cr_clamped) per pixel   (:189-213)
-__global__ void up_blend_ycc_kernel(const float4* __restrict__ out_u, const float4* __restrict__ out_c,
+__global__ void up_blend_ycc_kernel(const float4* __restrict__ tiles_out,
                                     const UpTile* __restrict__ tl, int n_tiles, int single, int B, int OH, int OW,
                                     int feather, int kind, float* __restrict__ ycc /*[B][OH][OW][3]*/) {
   const long long total = (long long)B * OH * OW;
@@ -133,8 +133,8 @@ __global__ void up_blend_ycc_kernel(const float4* __restrict__ out_u, const floa
     const int y = (int)((i / OW) % OH);
     const int b = (int)(i / ((long long)OW * OH));
     float ru[3], rc[3], yu[3], yc[3];
-    up_blend_px(out_u, tl, 0, n_tiles, single, b, y, x, feather, kind, ru);
-    up_blend_px(out_c, tl, 0, n_tiles, single, b, y, x, feather, kind, rc);
+    up_blend_px(tiles_out, tl, 0, n_tiles, single, 0, b, y, x, feather, kind, ru);
+    up_blend_px(tiles_out, tl, 0, n_tiles, single, 1, b, y, x, feather, kind, rc);
     up_rgb_to_ycbcr(ru, yu);
     up_rgb_to_ycbcr(rc, yc);
     ycc[i * 3 + 0] = fminf(fmaxf(yu[0], 0.f), 8.f);
@@ -344,10 +344,13 @@ static int up_forward(hdrvae_upscaler* up, int n, int h, int w, uint8_t* ws, con
 namespace hdrvae {
 
 static const int kUpTile = 512, kUpOverlap = 64, kUpScale = 4;     // hdr_upscale_with_model.py:115-116, 4x ESRGAN
-static const long long kUpMaxChunkPx = 4LL * 512 * 512;            // pixels of one forward batch (bounds the workspace)
+static const long long kUpMaxChunkPx = 8LL * 512 * 512;            // pixels of one forward batch (bounds the workspace: ~14 GB)
 
-struct UpHostTile { int b, y0, x0, h, w; long long off; };
+struct UpHostTile { int b, y0, x0, h, w; long long off, off2; };
 struct UpGroup { int h, w; std::vector<int> tiles; };
+// One forward batch: n tiles of a group, both passes at once ([n as-is inputs | n clamped inputs]: the two passes of
+// hdr_upscale_with_model.py:181-186 share every launch, which halves the launch count and doubles the small grids)
+struct UpChunk { int h, w, first, n; long long out_base; size_t origin0; };
 
 static std::vector<int> up_positions(int size) {
   std::vector<int> p;
@@ -359,8 +362,10 @@ static std::vector<int> up_positions(int size) {
 struct UpTiling {
   bool single = false;
   std::vector<UpHostTile> tiles;      // reference accumulation order
-  std::vector<UpGroup> groups;        // equal-shape tiles, forward batches
-  long long out_px = 0;               // float4 elements of one pass's tile outputs
+  std::vector<UpGroup> groups;        // equal-shape tiles
+  std::vector<UpChunk> chunks;        // forward batches
+  std::vector<int> order;             // tile indices in chunk order
+  long long out_px = 0;               // float4 elements of all tile outputs (both passes)
 };
 
 static UpTiling up_make_tiling(int B, int H, int W) {
@@ -375,7 +380,7 @@ static UpTiling up_make_tiling(int B, int H, int W) {
         u.y0 = std::max(0, std::min(H - kUpOverlap, y)); u.h = std::min(kUpTile, H - u.y0);
         u.x0 = std::max(0, std::min(W - kUpOverlap, x)); u.w = std::min(kUpTile, W - u.x0);
         if (t.single) { u.y0 = u.x0 = 0; u.h = H; u.w = W; }
-        u.off = 0;
+        u.off = u.off2 = 0;
         t.tiles.push_back(u);
       }
   for (size_t i = 0; i < t.tiles.size(); ++i) {
@@ -387,29 +392,38 @@ static UpTiling up_make_tiling(int B, int H, int W) {
     t.groups[g].tiles.push_back((int)i);
   }
   long long off = 0;
-  for (UpGroup& g : t.groups)
-    for (int i : g.tiles) { t.tiles[i].off = off; off += 16LL * g.h * g.w; }
+  for (UpGroup& g : t.groups) {
+    const long long per = (long long)g.h * g.w, sz = 16 * per;
+    const int cap = (int)std::max<long long>(1, std::min<long long>((long long)g.tiles.size(), kUpMaxChunkPx / (2 * per)));
+    for (size_t i0 = 0; i0 < g.tiles.size(); i0 += cap) {
+      UpChunk c;
+      c.h = g.h; c.w = g.w; c.first = (int)t.order.size(); c.n = (int)std::min<size_t>(cap, g.tiles.size() - i0);
+      c.out_base = off; c.origin0 = 2 * (size_t)t.order.size();
+      for (int j = 0; j < c.n; ++j) {
+        UpHostTile& u = t.tiles[g.tiles[i0 + j]];
+        u.off = off + j * sz; u.off2 = off + (c.n + j) * sz;
+        t.order.push_back(g.tiles[i0 + j]);
+      }
+      off += 2 * c.n * sz;
+      t.chunks.push_back(c);
+    }
+  }
   t.out_px = off;
   return t;
 }
 
-struct UpWs { size_t descs, origins, out_u, out_c, ycc, tmp, fwd, total; int max_n_h_w[3]; };
+struct UpWs { size_t descs, origins, out, ycc, tmp, fwd, total; };
 static UpWs up_make_ws(const UpTiling& t, int B, int H, int W) {
   UpWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   w.descs = take(t.tiles.size() * sizeof(UpTile));
-  w.origins = take(t.tiles.size() * sizeof(int4));
-  w.out_u = take((size_t)t.out_px * 16);
-  w.out_c = take((size_t)t.out_px * 16);
+  w.origins = take(2 * t.tiles.size() * sizeof(int4));
+  w.out = take((size_t)t.out_px * 16);
   w.ycc = take((size_t)B * 16 * H * W * 3 * 4);
   w.tmp = take((size_t)B * 16 * H * W * 3 * 4);
   size_t fwd = 0;
-  for (const UpGroup& g : t.groups) {
-    const long long per = (long long)g.h * g.w;
-    const int n = (int)std::max<long long>(1, std::min<long long>((long long)g.tiles.size(), kUpMaxChunkPx / per));
-    fwd = std::max(fwd, up_make_plan(n, g.h, g.w).total);
-  }
+  for (const UpChunk& c : t.chunks) fwd = std::max(fwd, up_make_plan(2 * c.n, c.h, c.w).total);
   w.fwd = take(fwd);
   w.total = off;
   return w;
@@ -595,43 +609,35 @@ int hdrvae_upscale(hdrvae_upscaler* up, const float* image_bhwc, int B, int H, i
   for (size_t i = 0; i < t.tiles.size(); ++i) {
     const UpHostTile& u = t.tiles[i];
     descs[i].b = u.b; descs[i].oy = u.y0 * kUpScale; descs[i].ox = u.x0 * kUpScale;
-    descs[i].oh = u.h * kUpScale; descs[i].ow = u.w * kUpScale; descs[i].off = u.off;
+    descs[i].oh = u.h * kUpScale; descs[i].ow = u.w * kUpScale; descs[i].off = u.off; descs[i].off2 = u.off2;
   }
   HDRVAE_CUDA_OK(cudaMemcpyAsync(ws + wsl.descs, descs.data(), descs.size() * sizeof(UpTile), cudaMemcpyHostToDevice, s));
   // small_blur's input filter (:176-178) is torchvision gaussian_blur(kernel 3, sigma 0.1): taps exp(-50) = 1.9e-22
   // around a centre tap that rounds to 1.0f, i.e. the identity on fp32 images; nothing to launch.
   int4* origins = reinterpret_cast<int4*>(ws + wsl.origins);
-  std::vector<int4> host_or(t.tiles.size());
-  {
-    size_t k = 0;
-    for (const UpGroup& g : t.groups)
-      for (int i : g.tiles) host_or[k++] = make_int4(t.tiles[i].b, t.tiles[i].y0, t.tiles[i].x0, 0);
-  }
-  HDRVAE_CUDA_OK(cudaMemcpyAsync(origins, host_or.data(), host_or.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
-  for (int pass = 0; pass < 2; ++pass) {
-    float* out_pass = reinterpret_cast<float*>(ws + (pass == 0 ? wsl.out_u : wsl.out_c));
-    size_t k = 0;                                             // index into the group-ordered origin list
-    for (const UpGroup& g : t.groups) {
-      const long long per = (long long)g.h * g.w;
-      const int chunk = (int)std::max<long long>(1, std::min<long long>((long long)g.tiles.size(), kUpMaxChunkPx / per));
-      for (size_t i0 = 0; i0 < g.tiles.size(); i0 += chunk) {
-        const int n = (int)std::min<size_t>(chunk, g.tiles.size() - i0);
-        const UpPlan pl = up_make_plan(n, g.h, g.w);
-        uint8_t* fws = ws + wsl.fwd;
-        up_extract_tiles_kernel<<<up_grid((long long)n * per), 256, 0, s>>>(image_bhwc, H, W, origins + k + i0, n, g.h, g.w,
-                                                                           pass == 1 ? 1 : 0, reinterpret_cast<uint4*>(fws + pl.img8));
-        HDRVAE_LAUNCHED();
-        float* out4 = out_pass + t.tiles[g.tiles[i0]].off * 4;
-        HDRVAE_TRY(up_forward(up, n, g.h, g.w, fws, pl, out4, s));
+  std::vector<int4> host_or(2 * t.tiles.size());
+  for (const UpChunk& c : t.chunks)
+    for (int pass = 0; pass < 2; ++pass)
+      for (int j = 0; j < c.n; ++j) {
+        const UpHostTile& u = t.tiles[t.order[c.first + j]];
+        host_or[c.origin0 + pass * c.n + j] = make_int4(u.b, u.y0, u.x0, pass);     // .w: clamp the input to [-1, 1]
       }
-      k += g.tiles.size();
-    }
+  HDRVAE_CUDA_OK(cudaMemcpyAsync(origins, host_or.data(), host_or.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+  float* out_all = reinterpret_cast<float*>(ws + wsl.out);
+  for (const UpChunk& c : t.chunks) {
+    const int n2 = 2 * c.n;
+    const long long per = (long long)c.h * c.w;
+    const UpPlan pl = up_make_plan(n2, c.h, c.w);
+    uint8_t* fws = ws + wsl.fwd;
+    up_extract_tiles_kernel<<<up_grid((long long)n2 * per), 256, 0, s>>>(image_bhwc, H, W, origins + c.origin0, n2, c.h, c.w, 0,
+                                                                        reinterpret_cast<uint4*>(fws + pl.img8));
+    HDRVAE_LAUNCHED();
+    HDRVAE_TRY(up_forward(up, n2, c.h, c.w, fws, pl, out_all + c.out_base * 4, s));
   }
   const long long opx = (long long)B * OH * OW;
   float* ycc = reinterpret_cast<float*>(ws + wsl.ycc);
   float* tmp = reinterpret_cast<float*>(ws + wsl.tmp);
-  up_blend_ycc_kernel<<<up_grid(opx), 256, 0, s>>>(reinterpret_cast<const float4*>(ws + wsl.out_u),
-                                                    reinterpret_cast<const float4*>(ws + wsl.out_c),
+  up_blend_ycc_kernel<<<up_grid(opx), 256, 0, s>>>(reinterpret_cast<const float4*>(ws + wsl.out),
                                                     reinterpret_cast<const UpTile*>(ws + wsl.descs), (int)t.tiles.size(),
                                                     t.single ? 1 : 0, B, OH, OW, kUpOverlap * kUpScale, reversal, ycc);
   HDRVAE_LAUNCHED();
