@@ -57,7 +57,7 @@ def _rows_worker(rank, world, port, q):
     from vae_decode_hdr_b200.synthetic import random_decoder_state_dict, synthetic_latent
     eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
     res = []
-    for (h, w, mode) in [(16, 16, "moderate"), (8, 12, "adaptive_recovery")]:
+    for (h, w, mode) in [(32, 8, "moderate"), (8, 12, "adaptive_recovery")]:
         z = synthetic_latent(1, h, w, seed=9).to(dev)
         out, st = decode_rows_sharded(eng, z, mode, 1.0)
         whole, st1 = eng.decode(z, mode, 1.0)               # every rank also decodes the whole image alone
@@ -76,7 +76,7 @@ def _rows_worker(rank, world, port, q):
 def test_row_tiled_decode_two_gpus_nccl():
     """One image split into two row slabs on two GPUs (halo rows by NCCL send/recv, GroupNorm sums and HDR statistics
     all-reduced, attention K/V all-gathered) == the single-GPU decode: identical when the slabs tile like the whole
-    image (16x16 latent), within the fp16 decorrelation bound otherwise."""
+    image (32x8 latent: 16 latent rows per rank), within the fp16 decorrelation bound otherwise."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 30600 + os.getpid() % 1000

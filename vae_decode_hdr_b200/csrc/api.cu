@@ -145,8 +145,17 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
     static int slab_on = -1;
     if (slab_on < 0) { const char* e = getenv("HDRVAE_SLAB"); slab_on = (e && atoi(e) == 0) ? 0 : 1; }
     // (measured: with 128 columns the in-place residual convs are faster on row-shaped 128x1 tiles: 1.57 vs 1.76 ms)
+    // Which convs: every narrow one (<= 64 columns: the upscaler, conv_out); the decoder's 128-column convs unless they
+    // add the residual in place (measured slower on 8 x 16 tiles: 1.76 vs 1.57 ms); the 256-column tiles of the 256- and
+    // 512-channel levels with or without residual (same-box A/B of the C2 step: 44.3 -> 43.4 ms; the chip runs at its
+    // power cap, so the 4x lower L2 -> SM operand traffic also buys clock).  HDRVAE_SLAB_MAXN / HDRVAE_SLAB_RES move
+    // the two thresholds for experiments.
+    static int slab_maxn = -1, slab_res = -1;
+    if (slab_maxn < 0) { const char* e = getenv("HDRVAE_SLAB_MAXN"); slab_maxn = e ? atoi(e) : 512; }
+    if (slab_res < 0) { const char* e = getenv("HDRVAE_SLAB_RES"); slab_res = e ? atoi(e) : 0; }
+    const bool res_ok = io.residual == nullptr || pc.cout_pad > 128 || slab_res != 0;
     if (slab_on && pc.ks == 3 && !pc.upsample && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
-        (pc.cout_pad <= 64 || (pc.cout_pad <= 128 && io.residual == nullptr))) {
+        (pc.cout_pad <= 64 || (pc.cout_pad <= slab_maxn && res_ok))) {
       p.slab = 1;
       p.tw_log2 = 3; p.TW = 8; p.TH = 16;
       p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;

@@ -609,15 +609,21 @@ hdr_phase_b_kernel(const float* __restrict__ post3, const float* __restrict__ pr
   }
 }
 
+// one warp: lanes stride over the partials (min / max / integer sums: order-independent, so still deterministic)
 __global__ void hdr_reduce_b_kernel(const PartialB* __restrict__ partials, int n, hdrvae_stats* __restrict__ st) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   float omin = INFINITY, omax = -INFINITY, imax = -INFINITY;
   unsigned long long hdr = 0, neg = 0, ihdr = 0;
-  for (int i = 0; i < n; ++i) {
+  for (int i = threadIdx.x; i < n; i += 32) {
     const PartialB pb = partials[i];
     omin = fminf(omin, pb.omin); omax = fmaxf(omax, pb.omax); imax = fmaxf(imax, pb.imax);
     hdr += pb.hdr; neg += pb.neg; ihdr += pb.ihdr;
   }
+  omin = warp_min(omin); omax = warp_max(omax); imax = warp_max(imax);
+  for (int o = 16; o; o >>= 1) {
+    hdr += __shfl_xor_sync(~0u, hdr, o); neg += __shfl_xor_sync(~0u, neg, o); ihdr += __shfl_xor_sync(~0u, ihdr, o);
+  }
+  if (threadIdx.x != 0) return;
   st->out_min = omin; st->out_max = omax; st->intelligent_max = imax;
   st->hdr_pixels = (long long)hdr; st->negative_pixels = (long long)neg; st->intelligent_hdr_pixels = (long long)ihdr;
   st->accepted = (ihdr > 0 || imax > 1.1f) ? 1 : 0;                      // :106

@@ -786,6 +786,11 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (epi == 0) return launch_tc<128, false, 2, 0, 3>(p, num_sms, stream);
       if (epi == EPI_RES) return launch_tc<128, false, 2, EPI_RES, 3>(p, num_sms, stream);
     }
+    if (p.slab && !n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
+      // 256-column tiles: slab variant with one tap of weights per stage (experiment switch HDRVAE_SLAB_MAXN)
+      if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1>(p, num_sms, stream);
+      if (epi == (EPI_RES | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_STATS, 1>(p, num_sms, stream);
+    }
 #define HDRVAE_EPI_CASE(E)                                                                       \
     case E:                                                                                      \
       return n128 ? launch_tc<128, false, 2, E>(p, num_sms, stream) : launch_tc<256, false, 2, E>(p, num_sms, stream);
