@@ -235,7 +235,7 @@ struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
   size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_part, off_epi, off_lat_in, off_img, total;
 };
-static constexpr long long kScoreBudgetElems = 256ll << 20;   // fp32 score chunk <= 1 GiB
+static constexpr long long kScoreBudgetElems = 1024ll << 20;  // fp32 score chunk <= 4 GiB (K and V^T are re-read once per chunk)
 static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
 
 static Plan make_plan(int B, int h, int w, bool attn_only = false) {
