@@ -224,3 +224,29 @@ def test_full_size_c2_properties_and_gpu_oracle(setup):
         assert _rel(out1[b], ref[b]) < 1e-2
     assert st1["hdr_pixels"] == pytest.approx(rst["hdr_pixels"], rel=2e-3)
     assert st1["out_max"] == pytest.approx(rst["out_max"], rel=2e-2)
+
+
+def test_large_2048_decode_vs_gpu_oracle_and_row_tiling(setup):
+    """Towards config C4 (the largest size whose fp32 oracle still runs in seconds on the GPU): 1x16x256x256 latent ->
+    2048^2, "aggressive" (= mathematical_recovery).  T = 65 536 tokens exercises the chunked / split-K attention.
+      * rel-L2 <= 1e-2 against the fp32 PyTorch oracle on the same GPU (TF32 off);
+      * the same image row-tiled over 4 virtual ranks (64 latent rows each: conv tiles coincide) is identical."""
+    from vae_decode_hdr_b200.sharding import decode_rows_emulated
+    dec, eng = setup
+    z = make_latent(1, 256, 256, seed=1234).to(DEV)
+    out, st = eng.decode(z, "aggressive", 1.0)
+    assert out.shape == (1, 2048, 2048, 3) and bool(torch.isfinite(out).all())
+    tiled, _ = decode_rows_emulated(eng, z, 4, "aggressive")
+    assert _rel(tiled, out) < 1e-6, _rel(tiled, out)
+    del tiled
+    eng._workspace = None
+    torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dec_gpu = dec.to(DEV)
+    try:
+        ref, rst, _ = ho.simple_hdr_decode(dec_gpu, z, "aggressive", 1.0)
+    finally:
+        dec.to("cpu")
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    assert st["pre_max"] == pytest.approx(rst["pre_max"], rel=5e-3)
