@@ -211,9 +211,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stdout: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its debug output (the "NCCL version ..." banner on boxes that set NCCL_DEBUG) to stdout by
+        # default: send it to stderr so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.load_library()
 

@@ -27,6 +27,7 @@ rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=dev)
 eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
 z = synthetic_latent(1, a.h, a.w, seed=3).to(dev)
