@@ -179,10 +179,31 @@ def run_reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def guard_stdout() -> None:
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner with printf when
+    NCCL_DEBUG is set on the box, regardless of NCCL_DEBUG_FILE), so file descriptor 1 is pointed at stderr for the whole
+    run and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -349,7 +370,7 @@ def main():
         except Exception as exc:      # never lose the headline line to the auxiliary measurement
             line["aux_c4_4096"] = {"error": repr(exc)[:200]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
