@@ -171,3 +171,18 @@ def test_c5_pipeline_decode_upscale_pack(nets):
     ref_half = torch.from_numpy(ref_big.numpy().astype(np.float16)).float()
     assert _rel(half.float().cpu(), ref_half) < 1e-2, _rel(half.float().cpu(), ref_half)
     eng.close()
+
+
+def test_rrdbnet_full_depth_nb23_vs_oracle():
+    """The C5 model size (23 RRDBs = 69 dense blocks, 347 convs): error accumulation of the fp16-operand / fp32-stream
+    plan through the full depth, on a small image so that the fp32 CPU oracle runs in seconds."""
+    from vae_decode_hdr_b200.upscaler import HdrUpscalerEngine
+    net = uo.build_upscaler(0, nb=23)
+    eng = HdrUpscalerEngine(net.state_dict(), DEV)
+    assert eng.blocks == 23
+    x = make_image(1, 48, 40, 17, 3.0)
+    with torch.no_grad():
+        ref = net(x.movedim(-1, 1)).movedim(1, -1)
+    got = eng.forward(x.to(DEV), "none").cpu()
+    assert _rel(got, ref) < 1e-2, _rel(got, ref)
+    eng.close()
