@@ -40,7 +40,7 @@ def test_batch_sharded_decode_two_gpus_nccl():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in procs)
+    res = sorted(q.get(timeout=150) for _ in procs)
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] and r[2] for r in res), res
@@ -67,7 +67,16 @@ def _rows_worker(rank, world, port, q):
         gathered = [torch.empty_like(out) for _ in range(world)]
         dist.all_gather(gathered, out.contiguous())
         full_rel = float((torch.cat(gathered, dim=1) - whole).double().norm() / whole.double().norm())
-        res.append((h, w, rel, full_rel, abs(st["pre_max"] - st1["pre_max"]) / abs(st1["pre_max"])))
+        # same decode with the halos pushed over NVLink peer-to-peer (CUDA IPC) instead of NCCL send/recv: the kernels
+        # and their inputs are the same, so the result is bit-identical; three back-to-back decodes reuse the
+        # persistent workspace (write-after-read safety of the pushes)
+        from vae_decode_hdr_b200.sharding import RowsP2P
+        p2p = RowsP2P(eng, h, w)
+        same = True
+        for _ in range(3):
+            out2, st2 = p2p.decode(z, mode, 1.0)
+            same = same and bool(torch.equal(out2, out)) and st2["hdr_pixels"] == st["hdr_pixels"]
+        res.append((h, w, rel, full_rel, abs(st["pre_max"] - st1["pre_max"]) / abs(st1["pre_max"]), same))
     q.put((rank, res))
     dist.destroy_process_group()
 
@@ -83,10 +92,11 @@ def test_row_tiled_decode_two_gpus_nccl():
     procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in procs)
+    res = sorted(q.get(timeout=150) for _ in procs)
     for p in procs:
         p.join(timeout=60)
     for rank, cases in res:
-        (h0, w0, rel0, full0, dmax0), (h1, w1, rel1, full1, dmax1) = cases
+        (h0, w0, rel0, full0, dmax0, p2p0), (h1, w1, rel1, full1, dmax1, p2p1) = cases
+        assert p2p0 and p2p1, res
         assert rel0 < 1e-6 and full0 < 1e-6 and dmax0 < 1e-6, res
         assert rel1 < 5e-3 and full1 < 5e-3 and dmax1 < 2e-3, res

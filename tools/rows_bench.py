@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vae_decode_hdr_b200.engine import HdrVaeEngine  # noqa: E402
-from vae_decode_hdr_b200.sharding import decode_rows_sharded  # noqa: E402
+from vae_decode_hdr_b200.sharding import RowsP2P, decode_rows_sharded  # noqa: E402
 from vae_decode_hdr_b200.synthetic import random_decoder_state_dict, synthetic_latent  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -21,6 +21,7 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--mode", default="moderate")
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"])
 a = ap.parse_args()
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -32,19 +33,28 @@ dist.init_process_group("nccl", device_id=dev)
 eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
 z = synthetic_latent(1, a.h, a.w, seed=3).to(dev)
 
+p2p = RowsP2P(eng, a.h, a.w) if a.transport == "p2p" else None
+
+
+def run(want_stats):
+    if p2p is not None:
+        return p2p.decode(z, a.mode, 1.0, want_stats=want_stats)
+    return decode_rows_sharded(eng, z, a.mode, 1.0, want_stats=want_stats)
+
+
 for _ in range(a.warmup):
-    out, st = decode_rows_sharded(eng, z, a.mode, 1.0)
+    out, st = run(True)
 torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
-    out, st = decode_rows_sharded(eng, z, a.mode, 1.0, want_stats=False)
+    out, st = run(False)
 e1.record()
 torch.cuda.synchronize(); dist.barrier()
 ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 res = {"workload": f"1x16x{a.h}x{a.w} latent -> {8*a.h}x{8*a.w}, {a.mode}, row-tiled over {world} GPUs", "n_gpus": world,
-       "ms_per_image": float(ms), "megapixels_per_s": 64.0 * a.h * a.w / 1e6 / (float(ms) / 1e3),
+       "transport": a.transport, "ms_per_image": float(ms), "megapixels_per_s": 64.0 * a.h * a.w / 1e6 / (float(ms) / 1e3),
        "peak_mem_gib_per_gpu": torch.cuda.max_memory_allocated() / 2**30}
 if a.check:
     rows = 8 * a.h // world

@@ -551,6 +551,9 @@ struct hdrvae_rows {
   // layer-program state while the op list is being built
   float* x = nullptr; float* hbuf = nullptr;
   int H = 0, W = 0, pending = 0;
+  // neighbour ranks' workspaces mapped into this process (CUDA IPC / peer access), or null: hdrvae_rows_set_peers
+  uint8_t* peer_up = nullptr; uint8_t* peer_down = nullptr;
+  bool peers_set = false;
 };
 
 namespace hdrvae {
@@ -1096,10 +1099,42 @@ int hdrvae_rows_run(hdrvae_rows* st, hdrvae_exchange* ex, void* stream) {
   memset(ex, 0, sizeof *ex);
   while (st->pc < st->ops.size()) {
     hdrvae_rows::Op& op = st->ops[st->pc++];
-    if (op.exchange) { *ex = op.ex; return 0; }
+    if (op.exchange) {
+      *ex = op.ex;
+      if ((ex->kind & HDRVAE_EX_HALO) && st->peers_set) {
+        // push the halo rows straight into the neighbours' workspaces over NVLink (peer copies, stream-ordered after the
+        // conv that produced the rows); the host is left with the all-reduce.  The copy engine is used on purpose: SM
+        // stores to a CUDA-IPC mapping opened by another framework faulted here (peer access for kernels is not
+        // guaranteed by the lazy IPC open), while peer copies work on any mapping.
+        for (int i = 0; i < ex->n_halo; ++i) {
+          const size_t n = ex->halo_row_bytes[i];
+          if (st->rank > 0)
+            HDRVAE_CUDA_OK(cudaMemcpyAsync(st->peer_up + ex->halo_bottom_off[i], st->ws + ex->halo_first_row_off[i], n,
+                                           cudaMemcpyDefault, s));
+          if (st->rank < st->pl.world - 1)
+            HDRVAE_CUDA_OK(cudaMemcpyAsync(st->peer_down + ex->halo_top_off[i], st->ws + ex->halo_last_row_off[i], n,
+                                           cudaMemcpyDefault, s));
+        }
+        ex->kind &= ~HDRVAE_EX_HALO;
+        ex->kind |= HDRVAE_EX_HALO_PUSHED;
+      }
+      return 0;
+    }
     HDRVAE_TRY(op.fn(s));
   }
   ex->kind = HDRVAE_EX_END;
+  return 0;
+}
+
+int hdrvae_rows_set_peers(hdrvae_rows* st, void* upper_rank_workspace, void* lower_rank_workspace) {
+  HDRVAE_REQUIRE(st != nullptr, "hdrvae_rows_set_peers: null state");
+  HDRVAE_REQUIRE((st->rank == 0) == (upper_rank_workspace == nullptr) &&
+                 (st->rank == st->pl.world - 1) == (lower_rank_workspace == nullptr),
+                 "hdrvae_rows_set_peers: rank %d of %d needs exactly the workspaces of its existing neighbours", st->rank,
+                 st->pl.world);
+  st->peer_up = reinterpret_cast<uint8_t*>(upper_rank_workspace);
+  st->peer_down = reinterpret_cast<uint8_t*>(lower_rank_workspace);
+  st->peers_set = true;
   return 0;
 }
 

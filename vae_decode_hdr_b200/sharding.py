@@ -150,3 +150,67 @@ def decode_rows_emulated(engine, latent_full: torch.Tensor, world: int, hdr_mode
                 b[0].copy_(vmin); b[1].copy_(vmax); b[2].copy_(vsum)
     stats = [engine.rows_end(st, True) for st in states]
     return torch.cat(outs, dim=1), stats[0]
+
+
+class RowsP2P:
+    """Row-tiled decode with the conv halos pushed straight into the neighbours' workspaces over NVLink peer-to-peer
+    (CUDA IPC mappings of the neighbour ranks' workspace; the library issues one stream-ordered peer copy per halo row
+    right after the conv that produced it: hdrvae_rows_set_peers) instead of NCCL send/recv.  The GroupNorm all-reduce that accompanies every halo exchange doubles as the synchronisation: a
+    rank's all-reduce kernel is stream-ordered after its pushes, so when the all-reduce completes on a rank every
+    neighbour's push into that rank has landed; two writes of the same halo row are always separated by at least one
+    all-reduce, so a push can never overtake the neighbour's last read of the previous contents.  One NCCL call per
+    exchange point instead of three.  K/V all-gather and the HDR statistics stay on NCCL.
+
+    The workspace is persistent (the IPC handles are exchanged once, in the constructor); `decode` may be called any
+    number of times for latents of the shape given at construction."""
+
+    def __init__(self, engine, h: int, w: int, group=None):
+        self.engine, self.group, self.h, self.w = engine, group, h, w
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        need = engine.rows_workspace_bytes(h, w, self.world)
+        with torch.cuda.device(engine.device):
+            self.ws = torch.empty(need, dtype=torch.uint8, device=engine.device)
+            torch.cuda.synchronize(engine.device)
+        info = (self.ws.untyped_storage()._share_cuda_(), self.ws.storage_offset(), need)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, info, group=group)
+        self.peers = {}
+        for r in (self.rank - 1, self.rank + 1):
+            if 0 <= r < self.world:
+                share, offset, size = infos[r]
+                storage = torch.UntypedStorage._new_shared_cuda(*share)
+                t = torch.empty(0, dtype=torch.uint8, device=torch.device("cuda", share[0])).set_(storage)
+                self.peers[r] = t[offset:offset + size]
+        dist.barrier(group=group)       # nobody frees or reuses its workspace before every mapping exists
+
+    def _exchange(self, ex) -> None:
+        ws, rank, world = self.ws, self.rank, self.world
+        if ex.kind & _N.EX_HALO:
+            raise RuntimeError("the library did not push the halo rows (hdrvae_rows_set_peers not in effect)")
+        if ex.kind & _N.EX_ALLREDUCE_F64:
+            buf = ws[ex.allreduce_off:ex.allreduce_off + 8 * ex.allreduce_count].view(torch.float64)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        elif ex.kind & _N.EX_HALO_PUSHED:
+            dist.barrier(group=self.group)      # no all-reduce at this point: explicit synchronisation
+        if ex.kind & _N.EX_ALLGATHER:
+            for i in range(ex.n_gather):
+                n = ex.gather_bytes_per_rank[i]
+                full = ws[ex.gather_off[i]:ex.gather_off[i] + n * world]
+                dist.all_gather_into_tensor(full, full[rank * n:(rank + 1) * n].clone(), group=self.group)
+        if ex.kind & _N.EX_RAW_STATS:
+            allreduce_raw_stats(*_raw_views(ws, ex.raw_stats_off), group=self.group)
+
+    def decode(self, latent_full: torch.Tensor, hdr_mode: str, ev_multiplier: float = 1.0, want_stats: bool = True):
+        if tuple(latent_full.shape[-2:]) != (self.h, self.w):
+            raise ValueError(f"this RowsP2P was built for {self.h}x{self.w} latents, got {tuple(latent_full.shape)}")
+        eng = self.engine
+        state, _ws, out, _keep = eng.rows_begin(latent_full, self.rank, self.world, hdr_mode, ev_multiplier, workspace=self.ws)
+        up = self.peers[self.rank - 1].data_ptr() if self.rank > 0 else None
+        down = self.peers[self.rank + 1].data_ptr() if self.rank < self.world - 1 else None
+        _N.check(eng.lib.hdrvae_rows_set_peers(state, up, down), "hdrvae_rows_set_peers")
+        while True:
+            ex = eng.rows_run(state)
+            if ex.kind == _N.EX_END:
+                break
+            self._exchange(ex)
+        return out, eng.rows_end(state, want_stats)
