@@ -591,6 +591,7 @@ static int zero_border_halos(hdrvae_rows* st, void* slab, int H, int W, int C, i
 
 // conv epilogue emitted this rank's GroupNorm partials: fold them, then (exchange) all-reduce the sums
 static void rows_stats_and_halo(hdrvae_rows* st, const void* slab_f32, int H, int W, int C, const void* slab16, int C16) {
+  hdrvae_ctx* ctx = st->ctx;
   void* gn = st->ws + st->pl.off_gn;
   const int gn_chunks = st->pl.gn_chunks;
   int* pending = &st->pending;
