@@ -138,28 +138,18 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
   p.cta_group = ctx->cta_group;
   choose_tile(H, W, &p);
-  {
-    // 3x3 convs with <= 128 output columns (the upscaler's, and the decoder's 128-channel level): the operand traffic
-    // of the 9 taps and the pipeline depth a byte of smem buys are the bound, so the activation slab is staged once per
-    // K block (gemm_tc.cu slab variant); HDRVAE_SLAB=0 keeps the tap-reload form for A/B comparison
-    static int slab_on = -1;
-    if (slab_on < 0) { const char* e = getenv("HDRVAE_SLAB"); slab_on = (e && atoi(e) == 0) ? 0 : 1; }
-    // (measured: with 128 columns the in-place residual convs are faster on row-shaped 128x1 tiles: 1.57 vs 1.76 ms)
-    // Which convs: every narrow one (<= 64 columns: the upscaler, conv_out); the decoder's 128-column convs unless they
-    // add the residual in place (measured slower on 8 x 16 tiles: 1.76 vs 1.57 ms); the 256-column tiles of the 256- and
-    // 512-channel levels with or without residual (same-box A/B of the C2 step: 44.3 -> 43.4 ms; the chip runs at its
-    // power cap, so the 4x lower L2 -> SM operand traffic also buys clock).  HDRVAE_SLAB_MAXN / HDRVAE_SLAB_RES move
-    // the two thresholds for experiments.
-    static int slab_maxn = -1, slab_res = -1;
-    if (slab_maxn < 0) { const char* e = getenv("HDRVAE_SLAB_MAXN"); slab_maxn = e ? atoi(e) : 512; }
-    if (slab_res < 0) { const char* e = getenv("HDRVAE_SLAB_RES"); slab_res = e ? atoi(e) : 0; }
-    const bool res_ok = io.residual == nullptr || pc.cout_pad > 128 || slab_res != 0;
-    if (slab_on && pc.ks == 3 && !pc.upsample && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
-        (pc.cout_pad <= 64 || (pc.cout_pad <= slab_maxn && res_ok))) {
-      p.slab = 1;
-      p.tw_log2 = 3; p.TW = 8; p.TH = 16;
-      p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;
-    }
+  if (conv_takes_slab(pc, io, H, W, impl)) {
+    p.slab = 1;
+    p.tw_log2 = 3; p.TW = 8; p.TH = 16;
+    p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;
+  }
+  if (io.xf_scale != nullptr) {
+    HDRVAE_REQUIRE(p.slab && pc.w_dtype == DT_F16 && io.x_pad == 0 && io.x_channels == 0,
+                   "run_conv: the fused GroupNorm operand needs the fp16 slab form");
+    p.xf_scale = io.xf_scale; p.xf_shift = io.xf_shift; p.xf_C = pc.cin; p.xf_silu = io.xf_silu ? 1 : 0;
+    // the raw fp32 tensor is dense [B,H,W,cin]
+    p.a_px_stride = pc.cin; p.a_row_stride = (long long)W * pc.cin; p.a_img_stride = (long long)H * W * pc.cin;
+    p.a_k_valid = pc.cin;
   }
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
@@ -207,6 +197,21 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
     }
   }
   return 0;
+}
+
+// Which convs take the slab form (gemm_tc.cu): every narrow one (<= 64 columns: the upscaler, conv_out); the decoder's
+// 128-column convs unless they add the residual in place (measured slower on 8 x 16 tiles: 1.76 vs 1.57 ms); the
+// 256-column tiles of the 256- and 512-channel levels with or without residual (same-box A/B of the C2 step: 44.3 ->
+// 43.4 ms; the chip runs at its power cap, so the 4x lower L2 -> SM operand traffic also buys clock).  HDRVAE_SLAB=0
+// keeps the tap-reload form everywhere; HDRVAE_SLAB_MAXN / HDRVAE_SLAB_RES move the two thresholds for experiments.
+bool conv_takes_slab(const PackedConv& pc, const ConvIO& io, int H, int W, int impl) {
+  static int slab_on = -1, slab_maxn = -1, slab_res = -1;
+  if (slab_on < 0) { const char* e = getenv("HDRVAE_SLAB"); slab_on = (e && atoi(e) == 0) ? 0 : 1; }
+  if (slab_maxn < 0) { const char* e = getenv("HDRVAE_SLAB_MAXN"); slab_maxn = e ? atoi(e) : 512; }
+  if (slab_res < 0) { const char* e = getenv("HDRVAE_SLAB_RES"); slab_res = e ? atoi(e) : 0; }
+  const bool res_ok = io.residual == nullptr || pc.cout_pad > 128 || slab_res != 0;
+  return slab_on && pc.ks == 3 && !pc.upsample && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
+         (pc.cout_pad <= 64 || (pc.cout_pad <= slab_maxn && res_ok));
 }
 
 // Plain K-major GEMM: out[M][n_cols] = row_scale[m] * alpha * A[M][K] * Bm[n_cols][K]^T (+ bias) on the same kernel.
@@ -308,18 +313,51 @@ static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
   return ctx->conv_impl == HDRVAE_CONV_TCGEN05 ? reinterpret_cast<float*>(st->gn) : nullptr;
 }
 
+// GroupNorm + SiLU in front of a conv: either the separate streaming kernel (x -> t, 16-bit) or, when the conv takes
+// the slab form and HDRVAE_FUSE_GN is on, only the statistics -> scale / shift step: the conv then reads the raw fp32
+// tensor and normalises while staging its operand (io->xf_*), and the 16-bit tensor never exists in HBM.
+static int gn_before_conv(hdrvae_ctx* ctx, const float* x, const NormW& nw, const PackedConv& pc, ConvIO* io, DecState* st,
+                          int B, int H, int W, cudaStream_t s) {
+  static int fuse = -1;
+  static int fuse_min_n = 256;      // 128-column convs: the transform (MUFU bound) takes longer than their MMAs
+  if (fuse < 0) {
+    const char* e = getenv("HDRVAE_FUSE_GN"); fuse = (e && atoi(e) != 0) ? 1 : 0;
+    const char* m = getenv("HDRVAE_FUSE_GN_MINN"); if (m) fuse_min_n = atoi(m);
+  }
+  const bool fusable = fuse && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && st->pending > 0 &&
+                       pc.cout_pad >= fuse_min_n && io->y2 == nullptr && conv_takes_slab(pc, *io, H, W, ctx->conv_impl) &&
+                       !(pc.cout_pad == 128 && io->residual != nullptr);
+  if (!fusable) {
+    HDRVAE_TRY(run_gn(ctx, x, DT_F32, st->t, B, H * W, nw, true, st, s));
+    io->x = st->t;
+    return 0;
+  }
+  char pname[64];
+  snprintf(pname, sizeof pname, "groupnorm statistics C=%d @%dx%d", nw.C, B, H * W);
+  ProfScope prof(pname, 0.0, 0.0, s);
+  const int partials = st->pending;
+  st->pending = 0;
+  HDRVAE_TRY(launch_gn_finalize_only(B, H * W, nw.C, nw.gamma, nw.beta, st->gn, st->gn_chunks, partials, &io->xf_scale,
+                                     &io->xf_shift, s));
+  io->x = x;
+  io->xf_silu = true;
+  return 0;
+}
+
 static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, int W, cudaStream_t s) {
   const int impl = ctx->conv_impl;
-  HDRVAE_TRY(run_gn(ctx, st->x, DT_F32, st->t, B, H * W, rw.n1, true, st, s));
   {
-    ConvIO io; io.x = st->t; io.y = st->hbuf; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+    ConvIO io; io.y = st->hbuf; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+    HDRVAE_TRY(gn_before_conv(ctx, st->x, rw.n1, rw.c1, &io, st, B, H, W, s));
     HDRVAE_TRY(run_conv(ctx, rw.c1, io, B, H, W, impl, s));
   }
-  HDRVAE_TRY(run_gn(ctx, st->hbuf, DT_F32, st->t, B, H * W, rw.n2, true, st, s));
-  ConvIO io; io.x = st->t; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+  ConvIO io; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
   if (rw.dual_out) { io.y2 = st->xa16; io.y2_dtype = ctx->op_dtype; io.y2_scale = kRawOperandScale; }
   if (rw.has_nin) {
-    // shortcut on the scaled 16-bit copy of x into hbuf (free after norm2), then conv2 accumulates onto it in place
+    // norm2 as a separate pass (conv1's output lives in hbuf, which the shortcut is about to overwrite); then the
+    // shortcut on the scaled 16-bit copy of x into hbuf, and conv2 accumulates onto it in place
+    HDRVAE_TRY(run_gn(ctx, st->hbuf, DT_F32, st->t, B, H * W, rw.n2, true, st, s));
+    io.x = st->t;
     ConvIO sc; sc.x = st->xb16; sc.y = st->hbuf; sc.alpha = 1.0f / kRawOperandScale;
     HDRVAE_TRY(run_conv(ctx, rw.nin, sc, B, H, W, impl, s));
     io.y = st->hbuf; io.residual = st->hbuf;
@@ -327,6 +365,7 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
     std::swap(st->x, st->hbuf);
   } else {
     io.y = st->x; io.residual = st->x;                  // x += conv2(t), in place
+    HDRVAE_TRY(gn_before_conv(ctx, st->hbuf, rw.n2, rw.c2, &io, st, B, H, W, s));
     HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
   }
   return 0;

@@ -42,18 +42,25 @@ constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 4 * 64 * 4 
 // byte of shared memory keeps in flight doubles, which is what bounds the layers with <= 128 output columns.
 constexpr int kSlabRows = 18, kSlabPitch = 16;
 constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 36 KB
-template <int BLOCK_N, int CG, int KSUB, int SLAB = 0>
+// XF (slab form only): the A operand is the RAW fp32 tensor; 4 extra warps apply y = silu(x * scale + shift)
+// (GroupNorm + SiLU with the per-(image, channel) scale / shift of gn_finalize) while converting the slab to the fp16
+// swizzled layout the MMAs read, so the normalised 16-bit tensor never goes through HBM.
+constexpr int kXfThreads = 128;
+constexpr int kRawSlabBytes = kSlabRows * 10 * 64 * 4;            // 18 rows x 10 pixels x 64 channels fp32 = 45 KB
+template <int BLOCK_N, int CG, int KSUB, int SLAB = 0, bool XF = false>
 struct TcConfig {
   static constexpr int kATile = kABytes;
   static constexpr int kBBytes = (SLAB ? SLAB : 1) * (BLOCK_N / CG) * kRowBytes;   // one B stage staged by this CTA
   static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block (tap-reload form)
   static constexpr int kStageBytes = SLAB ? kBBytes : KSUB * kSubBytes;
   // narrow tiles have short MMAs (a slab feeds 36 MMAs of 32 cycles): three slabs in flight cover the TMA latency
-  static constexpr int kSlabStages = SLAB ? (BLOCK_N <= 64 ? 3 : 2) : 0;
-  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBytes) / kStageBytes;
+  static constexpr int kSlabStages = SLAB ? ((BLOCK_N <= 64 && !XF) ? 3 : 2) : 0;
+  static constexpr int kRawBytes = XF ? kRawSlabBytes : 0;
+  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBytes - kRawBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 64 ... 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBytes + kSmemFixed;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBytes + kRawBytes + kSmemFixed;
+  static_assert(!XF || SLAB > 0, "the operand transform exists in the slab form only");
   static_assert(kStages >= (SLAB ? 2 : 3) && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
   static_assert(SLAB == 0 || ((SLAB == 9 || SLAB == 3 || SLAB == 1) && KSUB == 1), "the slab variant stages 9, 3 or 1 taps of B per pipeline slot");
 };
@@ -106,11 +113,11 @@ enum : int {
   EPI_RES2 = 128,    // + second fp32 residual (end of an RRDB: 0.04 acc + 0.2 x2 + x0)
 };
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0, bool XF = false>
+__global__ void __launch_bounds__(kNumThreads + (XF ? kXfThreads : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
-  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB, XF>;
   constexpr int kAT = Cfg::kATile;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position in the CTA pair (0 = leader)
   constexpr int kStages = Cfg::kStages;
@@ -124,7 +131,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // tap-reload form: [A stages][B stages]; slab form: [B stages][slab ring]
   uint8_t* smem_b = SLAB ? smem : smem + kStages * KSUB * kAT;
   uint8_t* smem_slab = smem + kStages * Cfg::kStageBytes;
-  float* stage_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kSlabStages * kSlabBytes);   // [8 warps][32 rows][32 floats]
+  uint8_t* smem_raw_slab = smem_slab + Cfg::kSlabStages * kSlabBytes;   // XF: one raw fp32 slab [18][10][64]
+  float* stage_s = reinterpret_cast<float*>(smem_raw_slab + Cfg::kRawBytes);   // [8 warps][32 rows][32 floats]
   float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
   uint64_t* full_bar = bars;                      // [kStages]
@@ -133,7 +141,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint64_t* slab_full_bar = bars + 2 * kStages + 4;   // [3]
   uint64_t* slab_empty_bar = bars + 2 * kStages + 7;  // [3]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 10);
+  uint64_t* raw_full_bar = bars + 2 * kStages + 10;   // [1]
+  uint64_t* raw_empty_bar = bars + 2 * kStages + 11;  // [1]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -146,9 +156,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
-      ptx::mbar_init(&slab_full_bar[i], 1);
+      // XF: a slab is ready when the transform warps of every CTA of the pair have written it
+      ptx::mbar_init(&slab_full_bar[i], XF ? CG * (kXfThreads / 32) : 1);
       ptx::mbar_init(&slab_empty_bar[i], 1);
     }
+    ptx::mbar_init(raw_full_bar, 1);
+    ptx::mbar_init(raw_empty_bar, kXfThreads / 32);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], CG * kActiveEpiWarps);   // draining epilogue warps of every CTA of the pair
@@ -182,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0, ss = 0;
-    uint32_t phase = 0, sphase = 0;
+    uint32_t phase = 0, sphase = 0, rphase = 0;
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
       const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
@@ -194,16 +207,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int bk0 = (int)(img * p.b_img_k_stride);       // split-K: this image's K range of B
       if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
-          ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
-          if (ptx::elect_one()) {
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
-            uint8_t* sa = smem_slab + ss * kSlabBytes;
-            // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
-            if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-            else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+          if constexpr (XF) {
+            // raw fp32 slab (18 rows x 10 pixels x 64 channels) into this CTA's single raw buffer; the transform
+            // warps turn it into the fp16 slab
+            ptx::mbar_wait(raw_empty_bar, rphase ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(raw_full_bar, (uint32_t)kRawSlabBytes);
+              ptx::tma_load_4d(smem_raw_slab, &tmA, raw_full_bar, kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+            }
+            __syncwarp();
+            rphase ^= 1;
+          } else {
+            ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
+            if (ptx::elect_one()) {
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
+              uint8_t* sa = smem_slab + ss * kSlabBytes;
+              // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
+              if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+              else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+            }
+            __syncwarp();
+            if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
           }
-          __syncwarp();
-          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
           for (int tg = 0; tg < 9 / SLAB; ++tg) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (ptx::elect_one()) {
@@ -570,6 +595,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if constexpr (XF) {
+    if (warp >= 2 + kEpilogueThreads / 32) {
+      // ---------------------------------------------------------- operand transform (4 warps): raw fp32 slab ->
+      // y = silu(x * scale + shift) -> fp16 slab in the SWIZZLE_128B layout the MMAs read.  Thread t owns the 8
+      // channels 8 (t & 7) .. +7 of every 16th pixel-line it visits, so its scale / shift live in registers.
+      const int xt = threadIdx.x - (kNumThreads);
+      const int c8 = xt & 7;
+      int ss = 0;
+      uint32_t sphase = 0, rphase = 0;
+      for (int tile = w_first; tile < num_tiles; tile += w_step) {
+        const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
+        const bool tile_live = mt < m_tiles;
+        const int img = mt / tiles_per_img;
+        const int rem = mt - img * tiles_per_img;
+        const int ty = rem / p.tiles_x;
+        const int tx = rem - ty * p.tiles_x;
+        const int x0 = tx * p.TW, y0 = ty * p.TH;
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          float sc[8], sh[8];
+          {
+            const int ch = kb * 64 + c8 * 8;
+            const bool ok = tile_live && ch < p.xf_C;
+            const float4* ps = reinterpret_cast<const float4*>(p.xf_scale + (long long)(tile_live ? img : 0) * p.xf_C + (ok ? ch : 0));
+            const float4* pb = reinterpret_cast<const float4*>(p.xf_shift + (long long)(tile_live ? img : 0) * p.xf_C + (ok ? ch : 0));
+            const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+            if (!ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; }
+            }
+          }
+          ptx::mbar_wait(raw_full_bar, rphase);
+          ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
+          uint8_t* dst = smem_slab + ss * kSlabBytes;
+          // 180 pixel-lines, 16 per pass over the 128 threads; 4 lines in flight per thread (the loop is latency
+          // bound otherwise: measured 2x the MMA time of a 256-column K block with one line at a time)
+          const bool ch_ok = (kb * 64 + c8 * 8) < p.xf_C;
+          constexpr int kLines = kSlabRows * 10, kStep = kXfThreads / 8, kUnroll = 4;
+          for (int pl0 = xt >> 3; pl0 < kLines; pl0 += kStep * kUnroll) {
+            float4 a0[kUnroll], a1[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              const int pl = pl0 + u * kStep;
+              if (pl < kLines) {
+                const float4* src = reinterpret_cast<const float4*>(smem_raw_slab + (size_t)pl * 256 + c8 * 32);
+                a0[u] = src[0]; a1[u] = src[1];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              const int pl = pl0 + u * kStep;
+              if (pl >= kLines) break;
+              const int r = pl / 10, pc = pl - r * 10;
+              const int gy = y0 - 1 + r, gx = x0 - 1 + pc;
+              const bool inside = tile_live && ch_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+              float v[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+              uint4 o;
+              uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j] = fmaf(v[j], sc[j], sh[j]);
+                if (p.xf_silu) v[j] = silu_f(v[j]);
+                if (!inside) v[j] = 0.f;                    // conv padding is zero AFTER the normalisation
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
+              const int line = r * kSlabPitch + pc;
+              *reinterpret_cast<uint4*>(dst + line * kRowBytes + ((c8 ^ (line & 7)) << 4)) = o;
+            }
+          }
+          ptx::fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core reads
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(raw_empty_bar);                // the raw buffer may be refilled
+            if (CG == 2) ptx::mbar_arrive_cluster_release(&slab_full_bar[ss], 0);   // the leader's MMA warp waits on its own barrier
+            else ptx::mbar_arrive(&slab_full_bar[ss]);
+          }
+          rphase ^= 1;
+          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+        }
+      }
+    }
+  }
+
   ptx::tc_fence_before_sync();
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();    // the peer may still be read by the leader's MMAs
   if (warp == 1) {
@@ -597,7 +707,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int slab = 0) {
+static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int slab = 0, bool xf = false) {
   PFN_encodeTiled enc = get_encode_fn();
   HDRVAE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   const int eb = dt_bytes(p.ab_dtype);
@@ -609,7 +719,19 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int 
                  "gemm_tc: operand pointers must be 16-byte aligned");
   HDRVAE_REQUIRE(p.a_px_stride % vec == 0 && p.a_row_stride % vec == 0 && p.a_img_stride % vec == 0 && p.b_row_stride % vec == 0,
                  "gemm_tc: strides must be multiples of 16 bytes");
-  {
+  if (xf) {
+    // A is the raw fp32 tensor: plain (un-swizzled) boxes of 18 rows x 10 pixels x 64 channels for the transform warps
+    HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(p.a) & 15) == 0 && p.a_px_stride % 4 == 0, "gemm_tc: raw operand must be 16-byte aligned");
+    cuuint64_t dims[4] = {(cuuint64_t)(p.a_k_valid > 0 ? p.a_k_valid : p.k_per_tap), (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * 4, (cuuint64_t)p.a_row_stride * 4, (cuuint64_t)p.a_img_stride * 4};
+    cuuint32_t box[4] = {64, 10, (cuuint32_t)kSlabRows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&maps->a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p.a), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, raw fp32) failed: %d (W=%d H=%d N=%d K=%d)", (int)r, p.W, p.H,
+                   p.n_img, p.k_per_tap);
+  } else {
     // A: {C, W, H, N}; the channel extent visible to TMA is k_per_tap (columns beyond are never addressed)
     cuuint64_t dims[4] = {(cuuint64_t)(p.a_k_valid > 0 ? p.a_k_valid : p.k_per_tap), (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * eb, (cuuint64_t)p.a_row_stride * eb,
@@ -660,23 +782,23 @@ void choose_tile(int H, int W, GemmParams* p) {
   p->tiles_y = (H + p->TH - 1) / p->TH;
 }
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0, bool XF = false>
 static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
   constexpr int KSUB = SLAB ? 1 : (BLOCK_N <= 128) ? 2 : 1;
   GemmParams p = p_in;
   if (p.res_scale == 0.f) p.res_scale = 1.f;
-  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB, XF>;
   {
     const char* d = getenv("HDRVAE_GEMM_DBG");
     p.dbg = d ? atoi(d) : 0;
   }
   p.n_tiles_n = (p.n_cols + BLOCK_N - 1) / BLOCK_N;
   TensorMapPair maps;
-  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB));      // a CTA of a pair stages half of the B rows
+  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB, XF));  // a CTA of a pair stages half of the B rows
   static bool attr_set = false;
   if (!attr_set) {
-    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -687,7 +809,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(kNumThreads + (XF ? kXfThreads : 0));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -697,7 +819,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, maps.a, maps.b, p));
+  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, maps.a, maps.b, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -778,6 +900,19 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       }
     } else {
       epi = -1;
+    }
+    if (p.xf_scale != nullptr) {
+      // fused GroupNorm + SiLU operand transform (decoder convs without a second output)
+      HDRVAE_REQUIRE(p.slab && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0 && p.ab_dtype == DT_F16 &&
+                     p.y_pad == 0, "gemm_tc: the operand transform needs the fp16 slab form");
+      if (n128) {
+        if (epi == EPI_STATS) return launch_tc<128, false, 2, EPI_STATS, 3, true>(p, num_sms, stream);
+      } else {
+        if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1, true>(p, num_sms, stream);
+        if (epi == (EPI_RES | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_STATS, 1, true>(p, num_sms, stream);
+        if (epi == (EPI_RES | EPI_OUT2 | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_OUT2 | EPI_STATS, 1, true>(p, num_sms, stream);
+      }
+      HDRVAE_REQUIRE(false, "gemm_tc: no operand-transform build for this epilogue (%d)", epi);
     }
     if (p.slab && n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
       // the decoder's 128-channel 3x3 convs: slab variant, weights in groups of 3 taps

@@ -136,7 +136,6 @@ gn_finalize_kernel(const float* __restrict__ partial, int n_chunks, const float*
   }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 template <typename TIn, typename TOut, bool kSilu>
 __global__ void __launch_bounds__(kGnThreads)
@@ -288,6 +287,22 @@ int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride
   else launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Statistics only: conv-emitted partials (already in the scratch buffer) -> per-(image, channel) scale / shift, which
+// stay in the scratch buffer for a conv that applies them itself while staging its operand (gemm_tc.cu, XF variant).
+int launch_gn_finalize_only(int B, int HW, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
+                            int partial_chunks, const float** scale_out, const float** shift_out, cudaStream_t s) {
+  HDRVAE_REQUIRE(C % 32 == 0 && partial_chunks > 0, "groupnorm (finalize only): needs conv-emitted partials");
+  float* partial = reinterpret_cast<float*>(scratch);
+  float* scale = gn_scale_ptr(scratch, B, max_chunks);
+  float* shift = scale + (size_t)B * C;
+  gn_finalize_kernel<<<dim3(kGroups, B), 256, 0, s>>>(partial, partial_chunks, gamma, beta, scale, shift, C,
+                                                       (double)HW * (double)(C / kGroups), 1e-6f);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  *scale_out = scale; *shift_out = shift;
   return 0;
 }
 

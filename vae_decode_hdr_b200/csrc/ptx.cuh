@@ -193,6 +193,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// same with release semantics at cluster scope: orders this thread's earlier shared-memory writes (made visible to the
+// async proxy by fence.proxy.async) before the arrival is observed by the waiting thread of the other CTA
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 // In the shared::cluster window bit 24 of a CTA-pair's addresses is the rank inside the pair: clearing it
 // addresses the same offset in the even (leader) CTA.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
