@@ -47,6 +47,12 @@ constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 36 KB
 // swizzled layout the MMAs read, so the normalised 16-bit tensor never goes through HBM.
 constexpr int kXfThreads = 128;
 constexpr int kRawSlabBytes = kSlabRows * 10 * 64 * 4;            // 18 rows x 10 pixels x 64 channels fp32 = 45 KB
+// The transform warps write the fp16 slab themselves, so it can be packed at a 10-line pitch (a TMA box forces 16):
+// 22.5 KB instead of 36 KB, which is what lets a SECOND raw buffer fit (raw TMA of K block k+1 overlaps the transform
+// of k).  Descriptors may start on any 128-byte line, so SBO = 1280 B is as valid as 2048 B.
+constexpr int kXfPitch = 10;
+constexpr int kXfSlabBytes = 23 * 1024;                            // 18 x 10 lines x 128 B = 23 040, padded
+constexpr int kXfRawStages = 1;   // 2 was measured: no gain, and it starves the weight ring (3 stages instead of 6)
 template <int BLOCK_N, int CG, int KSUB, int SLAB = 0, bool XF = false>
 struct TcConfig {
   static constexpr int kATile = kABytes;
@@ -55,11 +61,13 @@ struct TcConfig {
   static constexpr int kStageBytes = SLAB ? kBBytes : KSUB * kSubBytes;
   // narrow tiles have short MMAs (a slab feeds 36 MMAs of 32 cycles): three slabs in flight cover the TMA latency
   static constexpr int kSlabStages = SLAB ? ((BLOCK_N <= 64 && !XF) ? 3 : 2) : 0;
-  static constexpr int kRawBytes = XF ? kRawSlabBytes : 0;
-  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBytes - kRawBytes) / kStageBytes;
+  static constexpr int kRawBytes = XF ? kXfRawStages * kRawSlabBytes : 0;
+  static constexpr int kSlabBuf = XF ? kXfSlabBytes : kSlabBytes;   // bytes of one fp16 slab buffer
+  static constexpr int kPitch = XF ? kXfPitch : kSlabPitch;          // 128-byte lines per slab row
+  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBuf - kRawBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 64 ... 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBytes + kRawBytes + kSmemFixed;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBuf + kRawBytes + kSmemFixed;
   static_assert(!XF || SLAB > 0, "the operand transform exists in the slab form only");
   static_assert(kStages >= (SLAB ? 2 : 3) && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
   static_assert(SLAB == 0 || ((SLAB == 9 || SLAB == 3 || SLAB == 1) && KSUB == 1), "the slab variant stages 9, 3 or 1 taps of B per pipeline slot");
@@ -131,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // tap-reload form: [A stages][B stages]; slab form: [B stages][slab ring]
   uint8_t* smem_b = SLAB ? smem : smem + kStages * KSUB * kAT;
   uint8_t* smem_slab = smem + kStages * Cfg::kStageBytes;
-  uint8_t* smem_raw_slab = smem_slab + Cfg::kSlabStages * kSlabBytes;   // XF: one raw fp32 slab [18][10][64]
+  uint8_t* smem_raw_slab = smem_slab + Cfg::kSlabStages * Cfg::kSlabBuf;   // XF: raw fp32 slabs [2][18][10][64]
   float* stage_s = reinterpret_cast<float*>(smem_raw_slab + Cfg::kRawBytes);   // [8 warps][32 rows][32 floats]
   float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
@@ -141,9 +149,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint64_t* slab_full_bar = bars + 2 * kStages + 4;   // [3]
   uint64_t* slab_empty_bar = bars + 2 * kStages + 7;  // [3]
-  uint64_t* raw_full_bar = bars + 2 * kStages + 10;   // [1]
-  uint64_t* raw_empty_bar = bars + 2 * kStages + 11;  // [1]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
+  uint64_t* raw_full_bar = bars + 2 * kStages + 10;   // [2]
+  uint64_t* raw_empty_bar = bars + 2 * kStages + 12;  // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,8 +168,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&slab_full_bar[i], XF ? CG * (kXfThreads / 32) : 1);
       ptx::mbar_init(&slab_empty_bar[i], 1);
     }
-    ptx::mbar_init(raw_full_bar, 1);
-    ptx::mbar_init(raw_empty_bar, kXfThreads / 32);
+    for (int i = 0; i < kXfRawStages; ++i) {
+      ptx::mbar_init(&raw_full_bar[i], 1);
+      ptx::mbar_init(&raw_empty_bar[i], kXfThreads / 32);
+    }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
       ptx::mbar_init(&tmem_empty_bar[i], CG * kActiveEpiWarps);   // draining epilogue warps of every CTA of the pair
@@ -196,6 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer
     int stage = 0, ss = 0;
     uint32_t phase = 0, sphase = 0, rphase = 0;
+    int rs = 0;
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
       const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
@@ -210,13 +221,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (XF) {
             // raw fp32 slab (18 rows x 10 pixels x 64 channels) into this CTA's single raw buffer; the transform
             // warps turn it into the fp16 slab
-            ptx::mbar_wait(raw_empty_bar, rphase ^ 1);
+            ptx::mbar_wait(&raw_empty_bar[rs], rphase ^ 1);
             if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(raw_full_bar, (uint32_t)kRawSlabBytes);
-              ptx::tma_load_4d(smem_raw_slab, &tmA, raw_full_bar, kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+              ptx::mbar_arrive_expect_tx(&raw_full_bar[rs], (uint32_t)kRawSlabBytes);
+              ptx::tma_load_4d(smem_raw_slab + rs * kRawSlabBytes, &tmA, &raw_full_bar[rs], kb * kElemsPerRow, x0 - 1,
+                               y0 - 1 + p.y_pad, img);
             }
             __syncwarp();
-            rphase ^= 1;
+            if (++rs == kXfRawStages) { rs = 0; rphase ^= 1; }
           } else {
             ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
             if (ptx::elect_one()) {
@@ -289,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
           ptx::mbar_wait(&slab_full_bar[ss], sphase);
-          const uint32_t sa = ptx::smem_u32(smem_slab + ss * kSlabBytes);
+          const uint32_t sa = ptx::smem_u32(smem_slab + ss * Cfg::kSlabBuf);
           for (int tg = 0; tg < 9 / SLAB; ++tg) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after_sync();
@@ -299,8 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int tt = 0; tt < SLAB; ++tt) {
                 // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
                 const int t = tg * SLAB + tt;
-                const uint32_t a_off = (uint32_t)(((t / 3) * kSlabPitch + (t % 3)) * kRowBytes);
-                const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, kSlabPitch * kRowBytes);
+                const uint32_t a_off = (uint32_t)(((t / 3) * Cfg::kPitch + (t % 3)) * kRowBytes);
+                const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, Cfg::kPitch * kRowBytes);
                 const uint64_t db = ptx::make_sw128_kmajor_desc(sb + tt * (BLOCK_N / CG) * kRowBytes);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -604,6 +616,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int c8 = xt & 7;
       int ss = 0;
       uint32_t sphase = 0, rphase = 0;
+      int rs = 0;
       for (int tile = w_first; tile < num_tiles; tile += w_step) {
         const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
         const bool tile_live = mt < m_tiles;
@@ -627,9 +640,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; }
             }
           }
-          ptx::mbar_wait(raw_full_bar, rphase);
+          ptx::mbar_wait(&raw_full_bar[rs], rphase);
           ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
-          uint8_t* dst = smem_slab + ss * kSlabBytes;
+          uint8_t* dst = smem_slab + ss * Cfg::kSlabBuf;
+          const uint8_t* raw = smem_raw_slab + rs * kRawSlabBytes;
           // 180 pixel-lines, 16 per pass over the 128 threads; 4 lines in flight per thread (the loop is latency
           // bound otherwise: measured 2x the MMA time of a 256-column K block with one line at a time)
           const bool ch_ok = (kb * 64 + c8 * 8) < p.xf_C;
@@ -640,7 +654,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = 0; u < kUnroll; ++u) {
               const int pl = pl0 + u * kStep;
               if (pl < kLines) {
-                const float4* src = reinterpret_cast<const float4*>(smem_raw_slab + (size_t)pl * 256 + c8 * 32);
+                const float4* src = reinterpret_cast<const float4*>(raw + (size_t)pl * 256 + c8 * 32);
                 a0[u] = src[0]; a1[u] = src[1];
               }
             }
@@ -662,18 +676,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) w[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
-              const int line = r * kSlabPitch + pc;
-              *reinterpret_cast<uint4*>(dst + line * kRowBytes + ((c8 ^ (line & 7)) << 4)) = o;
+              // SWIZZLE_128B is a function of the absolute address: 16-byte chunk index XOR (address bits 7..9)
+              uint8_t* lp = dst + (r * kXfPitch + pc) * kRowBytes;
+              const uint32_t la = ptx::smem_u32(lp);
+              *reinterpret_cast<uint4*>(lp + ((c8 ^ ((la >> 7) & 7)) << 4)) = o;
             }
           }
           ptx::fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core reads
           __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive(raw_empty_bar);                // the raw buffer may be refilled
+            ptx::mbar_arrive(&raw_empty_bar[rs]);           // the raw buffer may be refilled
             if (CG == 2) ptx::mbar_arrive_cluster_release(&slab_full_bar[ss], 0);   // the leader's MMA warp waits on its own barrier
             else ptx::mbar_arrive(&slab_full_bar[ss]);
           }
-          rphase ^= 1;
+          if (++rs == kXfRawStages) { rs = 0; rphase ^= 1; }
           if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
         }
       }
