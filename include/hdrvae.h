@@ -61,9 +61,9 @@ enum { HDRVAE_PRECISION_BF16 = 0, HDRVAE_PRECISION_F16 = 1 };
  * on the GPU and is never selected implicitly. */
 enum { HDRVAE_CONV_TCGEN05 = 0, HDRVAE_CONV_DIRECT = 1 };
 /* Upscaler: reversal hook kinds (hdr_upscale_with_model.py:79-107, :266-279) and the resampling methods of
- * local_fix that are implemented (:241; "area", "bicubic" and ComfyUI's "bislerp" are rejected with an error). */
+ * local_fix that are implemented (:241; ComfyUI's own "bislerp" is rejected with an error). */
 enum { HDRVAE_REVERSAL_NONE = 0, HDRVAE_REVERSAL_ATANH = 1, HDRVAE_REVERSAL_LOGIT = 2 };
-enum { HDRVAE_UPSCALE_NEAREST_EXACT = 0, HDRVAE_UPSCALE_BILINEAR = 1 };
+enum { HDRVAE_UPSCALE_NEAREST_EXACT = 0, HDRVAE_UPSCALE_BILINEAR = 1, HDRVAE_UPSCALE_AREA = 2, HDRVAE_UPSCALE_BICUBIC = 3 };
 
 /*
  * Scalars the reference computes with ~25 full-tensor reductions + host syncs

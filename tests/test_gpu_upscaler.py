@@ -101,7 +101,8 @@ class _GpuModel(torch.nn.Module):
 
 @pytest.mark.parametrize("B,H,W,blur,fix,method", [(1, 24, 20, False, False, "bilinear"), (1, 530, 24, False, False, "bilinear"),
                                                    (1, 40, 600, True, True, "nearest-exact"), (2, 20, 28, True, True, "bilinear"),
-                                                   (1, 520, 520, False, True, "bilinear")])
+                                                   (1, 520, 520, False, True, "bilinear"), (1, 36, 44, False, True, "area"),
+                                                   (2, 30, 26, False, True, "bicubic")])
 def test_tiling_blend_and_recombination_are_exact_given_the_model(nets, B, H, W, blur, fix, method):
     net, eng = nets[(1, 1.0)] if max(H, W) > 512 else nets[(2, 40.0)]
     img = make_image(B, H, W, 31, 3.0)

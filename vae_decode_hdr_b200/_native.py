@@ -101,7 +101,7 @@ SIGNATURES = {
     "hdrvae_upscale": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
 }
 REVERSAL_NONE, REVERSAL_ATANH, REVERSAL_LOGIT = 0, 1, 2
-UPSCALE_METHODS = {"nearest-exact": 0, "bilinear": 1}
+UPSCALE_METHODS = {"nearest-exact": 0, "bilinear": 1, "area": 2, "bicubic": 3}
 
 _lib = None
 

@@ -211,8 +211,31 @@ __global__ void up_local_fix_kernel(const float* __restrict__ img, int B, int H,
       return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, p[0]), __fmul_rn(0.587f, p[1])), __fmul_rn(0.114f, p[2]));
     };
     float ys;
-    if (method == HDRVAE_UPSCALE_NEAREST_EXACT) {
+    if (method == HDRVAE_UPSCALE_NEAREST_EXACT || method == HDRVAE_UPSCALE_AREA) {
+      // nearest-exact: floor((dst + 0.5) / scale); "area" = adaptive average pooling, whose window for an integer
+      // upscale factor is exactly that one source pixel
       ys = luma(min((int)floorf((y + 0.5f) / scale), H - 1), min((int)floorf((x + 0.5f) / scale), W - 1));
+    } else if (method == HDRVAE_UPSCALE_BICUBIC) {
+      // torch upsample_bicubic2d, align_corners = False: cubic convolution, A = -0.75, border indices clamped
+      auto coef = [](float t, float* c) {
+        const float A = -0.75f;
+        auto c1 = [A](float x) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; };
+        auto c2 = [A](float x) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; };
+        c[0] = c2(t + 1.f); c[1] = c1(t); c[2] = c1(1.f - t); c[3] = c2(2.f - t);
+      };
+      const float fy = (y + 0.5f) / scale - 0.5f, fx = (x + 0.5f) / scale - 0.5f;
+      const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+      float cy[4], cx[4];
+      coef(fy - iy, cy); coef(fx - ix, cx);
+      ys = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int yy = min(max(iy - 1 + a, 0), H - 1);
+        float rowv = 0.f;
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) rowv += cx[b2] * luma(yy, min(max(ix - 1 + b2, 0), W - 1));
+        ys += cy[a] * rowv;
+      }
     } else {   // bilinear, align_corners = False (torch.nn.functional.interpolate)
       const float fy = fmaxf((y + 0.5f) / scale - 0.5f, 0.f), fx = fmaxf((x + 0.5f) / scale - 0.5f, 0.f);
       const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
@@ -595,8 +618,8 @@ int hdrvae_upscale(hdrvae_upscaler* up, const float* image_bhwc, int B, int H, i
                    void* stream) {
   HDRVAE_REQUIRE(up && up->loaded && image_bhwc && out_bhwc && workspace, "hdrvae_upscale: null argument / no weights");
   HDRVAE_REQUIRE(reversal == 1 || reversal == 2, "hdrvae_upscale: reversal must be 1 (atanh) or 2 (logit)");
-  HDRVAE_REQUIRE(!local_fix || upscale_method == HDRVAE_UPSCALE_NEAREST_EXACT || upscale_method == HDRVAE_UPSCALE_BILINEAR,
-                 "hdrvae_upscale: local_fix supports upscale_method nearest-exact and bilinear only (got %d)", upscale_method);
+  HDRVAE_REQUIRE(!local_fix || (upscale_method >= HDRVAE_UPSCALE_NEAREST_EXACT && upscale_method <= HDRVAE_UPSCALE_BICUBIC),
+                 "hdrvae_upscale: local_fix supports upscale_method nearest-exact, bilinear, area and bicubic (got %d)", upscale_method);
   HDRVAE_CUDA_OK(cudaSetDevice(up->store.device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const UpTiling t = up_make_tiling(B, H, W);

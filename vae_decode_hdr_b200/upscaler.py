@@ -11,7 +11,8 @@ from . import _native as N
 from .engine import _DTYPE_ID, _require_cuda
 
 REVERSAL = {"none": N.REVERSAL_NONE, "atanh": N.REVERSAL_ATANH, "logit": N.REVERSAL_LOGIT}
-# hdr_upscale_with_model.py:64 — the node's enum; the library implements the torch-expressible ones used by local_fix
+# hdr_upscale_with_model.py:64 — the node's enum; the library implements the torch-expressible ones (all but ComfyUI's
+# own "bislerp") for local_fix
 UPSCALE_METHODS = ["nearest-exact", "bilinear", "area", "bicubic", "bislerp"]
 
 
