@@ -52,7 +52,11 @@ constexpr int kRawSlabBytes = kSlabRows * 10 * 64 * 4;            // 18 rows x 1
 // of k).  Descriptors may start on any 128-byte line, so SBO = 1280 B is as valid as 2048 B.
 constexpr int kXfPitch = 10;
 constexpr int kXfSlabBytes = 23 * 1024;                            // 18 x 10 lines x 128 B = 23 040, padded
-constexpr int kXfRawStages = 1;   // 2 was measured: no gain, and it starves the weight ring (3 stages instead of 6)
+// The raw fp32 pixels are read by the transform warps straight from global memory (6 pixel-lines = 6 x 32 B in flight
+// per thread): staging them in shared memory through TMA was measured first — one 45 KB raw buffer serialises the HBM
+// latency with the transform (ncu: the transform warps spend 43 % of their time waiting for the raw TMA), two leave
+// only 3 weight stages — so no raw buffer at all, three fp16 slabs and the full weight ring instead.
+constexpr int kXfRawStages = 0;
 template <int BLOCK_N, int CG, int KSUB, int SLAB = 0, bool XF = false>
 struct TcConfig {
   static constexpr int kATile = kABytes;
@@ -60,7 +64,7 @@ struct TcConfig {
   static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block (tap-reload form)
   static constexpr int kStageBytes = SLAB ? kBBytes : KSUB * kSubBytes;
   // narrow tiles have short MMAs (a slab feeds 36 MMAs of 32 cycles): three slabs in flight cover the TMA latency
-  static constexpr int kSlabStages = SLAB ? ((BLOCK_N <= 64 && !XF) ? 3 : 2) : 0;
+  static constexpr int kSlabStages = SLAB ? ((BLOCK_N <= 64 || XF) ? 3 : 2) : 0;
   static constexpr int kRawBytes = XF ? kXfRawStages * kRawSlabBytes : 0;
   static constexpr int kSlabBuf = XF ? kXfSlabBytes : kSlabBytes;   // bytes of one fp16 slab buffer
   static constexpr int kPitch = XF ? kXfPitch : kSlabPitch;          // 128-byte lines per slab row
@@ -139,8 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // tap-reload form: [A stages][B stages]; slab form: [B stages][slab ring]
   uint8_t* smem_b = SLAB ? smem : smem + kStages * KSUB * kAT;
   uint8_t* smem_slab = smem + kStages * Cfg::kStageBytes;
-  uint8_t* smem_raw_slab = smem_slab + Cfg::kSlabStages * Cfg::kSlabBuf;   // XF: raw fp32 slabs [2][18][10][64]
-  float* stage_s = reinterpret_cast<float*>(smem_raw_slab + Cfg::kRawBytes);   // [8 warps][32 rows][32 floats]
+  float* stage_s = reinterpret_cast<float*>(smem_slab + Cfg::kSlabStages * Cfg::kSlabBuf);   // [8 warps][32 rows][32 floats]
   float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
   uint64_t* full_bar = bars;                      // [kStages]
@@ -149,9 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint64_t* slab_full_bar = bars + 2 * kStages + 4;   // [3]
   uint64_t* slab_empty_bar = bars + 2 * kStages + 7;  // [3]
-  uint64_t* raw_full_bar = bars + 2 * kStages + 10;   // [2]
-  uint64_t* raw_empty_bar = bars + 2 * kStages + 12;  // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 14);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,10 +168,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // XF: a slab is ready when the transform warps of every CTA of the pair have written it
       ptx::mbar_init(&slab_full_bar[i], XF ? CG * (kXfThreads / 32) : 1);
       ptx::mbar_init(&slab_empty_bar[i], 1);
-    }
-    for (int i = 0; i < kXfRawStages; ++i) {
-      ptx::mbar_init(&raw_full_bar[i], 1);
-      ptx::mbar_init(&raw_empty_bar[i], kXfThreads / 32);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
@@ -205,8 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0, ss = 0;
-    uint32_t phase = 0, sphase = 0, rphase = 0;
-    int rs = 0;
+    uint32_t phase = 0, sphase = 0;
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
       const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
@@ -219,16 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
           if constexpr (XF) {
-            // raw fp32 slab (18 rows x 10 pixels x 64 channels) into this CTA's single raw buffer; the transform
-            // warps turn it into the fp16 slab
-            ptx::mbar_wait(&raw_empty_bar[rs], rphase ^ 1);
-            if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(&raw_full_bar[rs], (uint32_t)kRawSlabBytes);
-              ptx::tma_load_4d(smem_raw_slab + rs * kRawSlabBytes, &tmA, &raw_full_bar[rs], kb * kElemsPerRow, x0 - 1,
-                               y0 - 1 + p.y_pad, img);
-            }
-            __syncwarp();
-            if (++rs == kXfRawStages) { rs = 0; rphase ^= 1; }
+            // the transform warps fetch the raw pixels themselves; the producer only streams the weights
           } else {
             ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
             if (ptx::elect_one()) {
@@ -615,8 +602,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int xt = threadIdx.x - (kNumThreads);
       const int c8 = xt & 7;
       int ss = 0;
-      uint32_t sphase = 0, rphase = 0;
-      int rs = 0;
+      uint32_t sphase = 0;
       for (int tile = w_first; tile < num_tiles; tile += w_step) {
         const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
         const bool tile_live = mt < m_tiles;
@@ -640,22 +626,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; }
             }
           }
-          ptx::mbar_wait(&raw_full_bar[rs], rphase);
           ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
           uint8_t* dst = smem_slab + ss * Cfg::kSlabBuf;
-          const uint8_t* raw = smem_raw_slab + rs * kRawSlabBytes;
-          // 180 pixel-lines, 16 per pass over the 128 threads; 4 lines in flight per thread (the loop is latency
-          // bound otherwise: measured 2x the MMA time of a 256-column K block with one line at a time)
+          // 180 pixel-lines (18 rows x 10 pixels of the halo slab), 16 per pass over the 128 threads, kUnroll lines
+          // in flight per thread: 8 threads read the 256 contiguous bytes of one pixel's 64 fp32 channels
           const bool ch_ok = (kb * 64 + c8 * 8) < p.xf_C;
-          constexpr int kLines = kSlabRows * 10, kStep = kXfThreads / 8, kUnroll = 4;
+          const float* xin = reinterpret_cast<const float*>(p.a) + (long long)(tile_live ? img : 0) * p.a_img_stride +
+                             kb * 64 + c8 * 8;
+          constexpr int kLines = kSlabRows * 10, kStep = kXfThreads / 8, kUnroll = 6;
           for (int pl0 = xt >> 3; pl0 < kLines; pl0 += kStep * kUnroll) {
             float4 a0[kUnroll], a1[kUnroll];
+            bool inside[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
               const int pl = pl0 + u * kStep;
-              if (pl < kLines) {
-                const float4* src = reinterpret_cast<const float4*>(raw + (size_t)pl * 256 + c8 * 32);
-                a0[u] = src[0]; a1[u] = src[1];
+              const int r = pl / 10, pc = pl - r * 10;
+              const int gy = y0 - 1 + r, gx = x0 - 1 + pc;
+              inside[u] = pl < kLines && tile_live && ch_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+              a0[u] = make_float4(0.f, 0.f, 0.f, 0.f); a1[u] = a0[u];
+              if (inside[u]) {
+                const float4* src = reinterpret_cast<const float4*>(xin + (long long)gy * p.a_row_stride + (long long)gx * p.a_px_stride);
+                a0[u] = __ldg(src); a1[u] = __ldg(src + 1);
               }
             }
 #pragma unroll
@@ -663,8 +654,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int pl = pl0 + u * kStep;
               if (pl >= kLines) break;
               const int r = pl / 10, pc = pl - r * 10;
-              const int gy = y0 - 1 + r, gx = x0 - 1 + pc;
-              const bool inside = tile_live && ch_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
               float v[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
               uint4 o;
               uint32_t* w = reinterpret_cast<uint32_t*>(&o);
@@ -672,7 +661,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 8; ++j) {
                 v[j] = fmaf(v[j], sc[j], sh[j]);
                 if (p.xf_silu) v[j] = silu_f(v[j]);
-                if (!inside) v[j] = 0.f;                    // conv padding is zero AFTER the normalisation
+                if (!inside[u]) v[j] = 0.f;                 // conv padding is zero AFTER the normalisation
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) w[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
@@ -685,11 +674,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core reads
           __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive(&raw_empty_bar[rs]);           // the raw buffer may be refilled
             if (CG == 2) ptx::mbar_arrive_cluster_release(&slab_full_bar[ss], 0);   // the leader's MMA warp waits on its own barrier
             else ptx::mbar_arrive(&slab_full_bar[ss]);
           }
-          if (++rs == kXfRawStages) { rs = 0; rphase ^= 1; }
           if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
         }
       }
