@@ -250,3 +250,17 @@ def test_upscaler_node_surface_equals_reference():
         assert list(inspect.signature(cls.upscale).parameters) == list(inspect.signature(ref.upscale).parameters)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cls._compute_device(torch.zeros(1, 4, 4, 3))
+
+
+def test_groupnorm_partial_capacity_covers_both_conv_tilings(lib):
+    """Host logic, no GPU: the GroupNorm partial-chunk capacity the library reports for an H x W conv output must cover
+    both ways the tensor-core kernel may tile it (the best 128-pixel patch, and the 8 x 16 tiles of the slab form) —
+    the conv epilogue writes one partial per tile."""
+    import itertools
+    for H, W in itertools.chain([(1, 1), (5, 9), (16, 8), (40, 72), (128, 128), (1024, 1024), (4096, 4096), (17, 1000)],
+                                [(h, w) for h in (3, 24, 100) for w in (7, 64, 257)]):
+        cap = lib.hdrvae_conv2d_stats_chunks(H, W, 0)
+        slab = -(-W // 8) * -(-H // 16)
+        best = min(-(-W // (1 << lg)) * -(-H // (128 >> lg)) for lg in range(8))
+        assert cap >= slab and cap >= best, (H, W, cap, slab, best)
+        assert lib.hdrvae_conv2d_stats_chunks(H, W, 1) == 4 * cap          # upsample convs: 4 phases
