@@ -557,9 +557,8 @@ hdr_phase_b_kernel(const float* __restrict__ post3, const float* __restrict__ pr
   const HdrScalars sc = *scp;
   float omin = INFINITY, omax = -INFINITY, imax = -INFINITY;
   unsigned long long hdr = 0, neg = 0, ihdr = 0;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float s = post3[i];
-    const float p3 = pre3[i];
+  // one element: the mode formula, the multiplier, the output statistics
+  auto one = [&](float s, float p3) -> float {
     const float ldr = srgb_to_linear_f(s);                                // :1074
     float map = p3, aligned = 1.0f;                                       // :1080-1081
     if (sc.has_hdr) {                                                     // :1082-1102
@@ -584,10 +583,24 @@ hdr_phase_b_kernel(const float* __restrict__ post3, const float* __restrict__ pr
     }
     ihdr += r > 1.0f; imax = fmaxf(imax, r);                              // :100-102 (before the multiplier)
     if (ev != 1.0f) r = __fmul_rn(r, ev);                                 // :180-182
-    out[i] = r;
     omin = fminf(omin, r); omax = fmaxf(omax, r);                         // :188-191
     hdr += r > 1.0f; neg += r < 0.0f;
+    return r;
+  };
+  // 16-byte accesses over the bulk, scalars over the (< 4 element) tail
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(post3) | reinterpret_cast<uintptr_t>(pre3) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long long n4 = vec_ok ? (n >> 2) : 0;
+  const float4* post4 = reinterpret_cast<const float4*>(post3);
+  const float4* pre4 = reinterpret_cast<const float4*>(pre3);
+  float4* out4 = reinterpret_cast<float4*>(out);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 s4 = post4[i], p4 = pre4[i];
+    float4 r4;
+    r4.x = one(s4.x, p4.x); r4.y = one(s4.y, p4.y); r4.z = one(s4.z, p4.z); r4.w = one(s4.w, p4.w);
+    out4[i] = r4;
   }
+  for (long long i = (n4 << 2) + blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = one(post3[i], pre3[i]);
   __shared__ float fm[3][8];
   __shared__ unsigned long long cn[3][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
