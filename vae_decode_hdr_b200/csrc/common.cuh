@@ -130,6 +130,19 @@ __device__ __forceinline__ float silu_f(float v) {
 }
 #endif
 
+// cudaFuncSetAttribute is per device: remember per (call site, device) whether the opt-in shared-memory size has
+// been set, so that a process driving several GPUs (not the one-process-per-GPU model, but legal) still works.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 struct TensorMapPair {
   CUtensorMap a, b;
 };

@@ -682,11 +682,10 @@ float* epilogue_pre3_ptr(void* scratch, int B, int H, int W) { return carve(scra
 template <typename T>
 static void launch_phase_a(const void* pre, const float* conv_w, const float* conv_b, int H, int W, float* post3, float* pre3,
                            int* argmax3, PartialA* pa, dim3 grid, size_t smem, int y_pad, long long img_stride, cudaStream_t s) {
-  static bool set = false;
-  if (!set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(hdr_phase_a_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(hdr_phase_a_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    set = true;
   }
   if (argmax3 != nullptr)
     hdr_phase_a_kernel<T, true><<<grid, kEpiThreads, smem, s>>>(reinterpret_cast<const T*>(pre), conv_w, conv_b, H, W, post3, pre3, argmax3, pa, y_pad, img_stride);

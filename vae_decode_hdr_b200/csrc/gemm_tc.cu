@@ -799,12 +799,10 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   p.n_tiles_n = (p.n_cols + BLOCK_N - 1) / BLOCK_N;
   TensorMapPair maps;
   HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB, XF));  // a CTA of a pair stages half of the B rows
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
     HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
-    attr_set = true;
-  }
   const long long m_tiles = (long long)p.n_img * p.tiles_x * p.tiles_y;
   const long long work = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
   long long groups = num_sms / CG;

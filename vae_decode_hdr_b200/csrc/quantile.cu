@@ -96,8 +96,8 @@ int launch_quantiles(const float* x, long long n, const unsigned long long* rank
   int grid = ceil_div(n, 256 * 16);
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid < 1) grid = 1;
-  static bool set = false;
-  if (!set) { HDRVAE_CUDA_OK(cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxQ * kBins * 4)); set = true; }
+  static PerDeviceOnce once;
+  if (once.first()) HDRVAE_CUDA_OK(cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxQ * kBins * 4));
   for (int pass = 0; pass < 3; ++pass) {
     radix_hist_kernel<<<grid, 256, nq * kBins * sizeof(unsigned int), s>>>(x, n, st, nq, pass, hist);
     HDRVAE_LAUNCHED();

@@ -161,6 +161,9 @@ class RowsP2P:
     all-reduce, so a push can never overtake the neighbour's last read of the previous contents.  One NCCL call per
     exchange point instead of three.  K/V all-gather and the HDR statistics stay on NCCL.
 
+    The mappings use torch's CUDA-IPC plumbing (`UntypedStorage._share_cuda_` / `_new_shared_cuda`, the private calls
+    behind torch.multiprocessing's tensor sharing) — the one place this package leans on a private torch API; the C ABI
+    itself only sees raw pointers (any cudaIpcOpenMemHandle mapping will do).
     The workspace is persistent (the IPC handles are exchanged once, in the constructor); `decode` may be called any
     number of times for latents of the shape given at construction."""
 
