@@ -272,7 +272,7 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   pl.off_o = take((size_t)B * pl.T * 512 * 2);
   pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
   pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
-  pl.off_inv = take((size_t)pl.s_rows * 4);
+  pl.off_inv = take((size_t)pl.s_rows * 4 * 2);          // 1 / row sum, and -row max of the two-pass soft-max
   pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials of the PV GEMM
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
   pl.off_lat_in = take(attn_only ? 0 : (size_t)B * 16 * pl.T * 4);          // graph input: fp32 latent copy
@@ -380,14 +380,43 @@ static int attention_rows(hdrvae_ctx* ctx, uint8_t* ws, size_t off_s, size_t off
   float* S = reinterpret_cast<float*>(ws + off_s);
   uint16_t* P = reinterpret_cast<uint16_t*>(ws + off_p);
   float* inv = reinterpret_cast<float*>(ws + off_inv);
+  float* negmax = inv + s_rows;                        // the plan reserves 2 * s_rows floats at off_inv
+  static int two_pass_on = -1;
+  if (two_pass_on < 0) { const char* e = getenv("HDRVAE_ATTN_TWO_PASS"); two_pass_on = (e && atoi(e) == 0) ? 0 : 1; }
+  // the fused form needs the 256-column CTA-pair build and whole 256-column tiles of keys
+  const bool two_pass = two_pass_on && impl == HDRVAE_CONV_TCGEN05 && ctx->cta_group != 1 && Tp % 256 == 0 && Tp >= 256;
   for (int r0 = 0; r0 < n_q; r0 += s_rows) {
     const int rows = std::min(s_rows, n_q - r0);
-    // S = alpha q k^T, fp32 (the decoder folds 1/sqrt(d) into the q weights: alpha = 1); padded key
-    // columns give 0 and are masked by the softmax
-    HDRVAE_TRY(run_gemm(ctx, dt, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, Tp, Tp, S, Tp, DT_F32, nullptr, false,
-                        qk_alpha, nullptr, impl, s));
-    // P = exp(S - rowmax) (16-bit), inv = 1 / rowsum; O = inv * (P V)
-    HDRVAE_TRY(launch_softmax_rows(S, P, dt, inv, rows, T, Tp, Tp, Tp, s));
+    if (two_pass) {
+      // Soft-max fused into the QK^T GEMM, two passes (no fp32 score matrix in HBM: 4 bytes per score instead of 12).
+      // Pass 1: row max of alpha q k^T from the epilogue's row-per-thread layout; pass 2 recomputes q k^T and writes
+      // P = exp(s - rowmax) as the 16-bit operand of the PV GEMM plus the row sums.  S doubles as the partial buffer.
+      GemmParams g;
+      memset(&g, 0, sizeof g);
+      g.a = q + (size_t)r0 * 1024; g.ab_dtype = dt;
+      g.a_px_stride = 1024; g.a_row_stride = (long long)rows * 1024; g.a_img_stride = (long long)rows * 1024;
+      g.n_img = 1; g.H = 1; g.W = rows;
+      g.k_per_tap = 512; g.ntaps = 1;
+      g.b = k; g.b_row_stride = 1024; g.b_rows = Tp; g.n_cols = Tp; g.n_valid_cols = T;
+      g.out = P; g.out_dtype = dt; g.out_px_stride = Tp;
+      g.sy = g.sx = 1; g.alpha = qk_alpha;
+      g.tw_log2 = 7; g.TW = 128; g.TH = 1; g.tiles_x = (rows + 127) / 128; g.tiles_y = 1;
+      g.cta_group = ctx->cta_group;
+      g.row_part = S; g.row_parts = (Tp / 256) * 2;
+      g.row_mode = 1;
+      HDRVAE_TRY(launch_gemm_tc(g, ctx->num_sms, s));
+      HDRVAE_TRY(launch_attn_row_parts(S, rows, g.row_parts, 1, negmax, s));
+      g.row_mode = 2; g.bias = negmax; g.bias_per_row = 1;
+      HDRVAE_TRY(launch_gemm_tc(g, ctx->num_sms, s));
+      HDRVAE_TRY(launch_attn_row_parts(S, rows, g.row_parts, 2, inv, s));
+    } else {
+      // S = alpha q k^T, fp32 (the decoder folds 1/sqrt(d) into the q weights: alpha = 1); padded key
+      // columns give 0 and are masked by the softmax
+      HDRVAE_TRY(run_gemm(ctx, dt, q + (size_t)r0 * 1024, 1024, rows, 512, k, 1024, Tp, Tp, S, Tp, DT_F32, nullptr, false,
+                          qk_alpha, nullptr, impl, s));
+      // P = exp(S - rowmax) (16-bit), inv = 1 / rowsum; O = inv * (P V)
+      HDRVAE_TRY(launch_softmax_rows(S, P, dt, inv, rows, T, Tp, Tp, Tp, s));
+    }
     // A row chunk gives only rows/128 x 2 tiles: when that cannot fill the GPU the K (key) dimension is split
     // across `splits` images of one GEMM (fp32 partials) and reduced afterwards.
     const int tiles = ((rows + 127) / 128) * 2;
@@ -567,7 +596,7 @@ static RowsPlan make_rows_plan(int h, int w, int world) {
   pl.off_o = take((size_t)pl.Tl * 512 * 2);
   pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
   pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
-  pl.off_inv = take((size_t)pl.s_rows * 4);
+  pl.off_inv = take((size_t)pl.s_rows * 4 * 2);          // 1 / row sum, and -row max of the two-pass soft-max
   pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);
   pl.off_epi = take(epilogue_scratch_bytes(1, 8 * pl.hl, 8 * w));
   pl.total = off;

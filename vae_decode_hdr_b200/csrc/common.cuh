@@ -87,6 +87,14 @@ struct GemmParams {
   const float* residual2;  // second fp32 residual, same addressing as out, added unscaled; or null
   float lrelu;       // LeakyReLU negative slope applied last (0: none)
   int n_store;       // columns actually stored (multiple of 4; 0: n_cols) — a Cout padded up to 32 stores less
+  // attention soft-max fused into the QK^T GEMM, two passes (row_mode 1 and 2): the epilogue works on whole rows in
+  // the TMEM row-per-thread layout.  1: per-row max of alpha * acc over this tile's valid columns -> row_part, nothing
+  // else is stored.  2: e = exp(alpha * acc + bias[row]) (bias = -row max), stored as the 16-bit output (0 in the
+  // padding columns), per-row sum of e -> row_part.  row_part[row * row_parts + n_tile * 2 + column half].
+  int row_mode;
+  float* row_part;
+  int row_parts;
+  int n_valid_cols;        // columns >= this are padding (0: n_cols)
   const float* row_scale;  // per M row (x coordinate) multiplier of the accumulator, or null
   float alpha;       // accumulator scale applied before bias (1.0 for convs)
   void* out2;        // optional second output: out * out2_scale as a 16-bit tensor (same addressing), or null

@@ -123,6 +123,8 @@ enum : int {
   EPI_ROWOPS = 32,   // per-row bias / per-row scale (attention GEMMs)
   EPI_LRELU = 64,    // LeakyReLU applied last (upscaler convs)
   EPI_RES2 = 128,    // + second fp32 residual (end of an RRDB: 0.04 acc + 0.2 x2 + x0)
+  EPI_ROWMAX = 256,  // attention pass 1: per-row max of the scores, nothing stored (GemmParams::row_mode 1)
+  EPI_EXPSUM = 512,  // attention pass 2: exp(score - row max) as the 16-bit output + per-row sums (row_mode 2)
 };
 
 template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0, bool XF = false>
@@ -444,6 +446,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      if constexpr ((EPI & (EPI_ROWMAX | EPI_EXPSUM)) != 0) {
+        // ---- soft-max passes of the attention (rows = queries, H = 1, 128-pixel row tiles): TMEM hands every thread
+        // one whole query row of the tile, so the row max / the row sum of exp are plain per-thread reductions
+        constexpr bool kExp = (EPI & EPI_EXPSUM) != 0;
+        const int xrow = tx * p.TW + q * 32 + lane;
+        const bool row_live = tile_live && xrow < p.W;
+        const int n_valid = p.n_valid_cols > 0 ? p.n_valid_cols : p.n_cols;
+        const float negm = (kExp && row_live) ? __ldg(p.bias + xrow) : 0.f;
+        float racc = kExp ? 0.f : -INFINITY;
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_row + cbase, v);
+#pragma unroll 1
+        for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+          const int c0 = cbase + ci * 32;
+          const int col = c0 + slot * 4;
+          ptx::tmem_ld_wait(v);
+          float e[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool valid = (n0 + c0 + j) < n_valid;
+            const float sv = __uint_as_float(v[j]);
+            if (kExp) {
+              e[j] = valid ? __expf(fmaf(sv, alpha, negm)) : 0.f;
+              racc += e[j];
+            } else if (valid) {
+              racc = fmaxf(racc, sv * alpha);
+            }
+          }
+          if (kExp) {
+            __syncwarp();                                   // previous chunk's readers are done with the patch
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              patch[lane * 8 + (j ^ (lane & 7))] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+          }
+          if (ci + 1 < kChunksPerWarp) ptx::tmem_ld_32x32(t_row + c0 + 32, v);
+          if (kExp) {
+            __syncwarp();
+            const uint32_t cmask = (n0 + col) < p.n_cols ? pmask : 0u;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sr;
+              const float4 a = patch[rr * 8 + (slot ^ (rr & 7))];
+              if (cmask >> it & 1) {
+                uint2 o;
+                if (out16_bf) { o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); }
+                else { o.x = pack_f16x2(a.x, a.y); o.y = pack_f16x2(a.z, a.w); }
+                *reinterpret_cast<uint2*>(outh + poff[it] + col) = o;
+              }
+            }
+          }
+        }
+        if (row_live) p.row_part[(long long)xrow * p.row_parts + nt * 2 + half] = racc;
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       // Software pipeline over the warp's chunks: the TMEM load of chunk ci+1 is issued as soon as the registers of
       // chunk ci have gone to the transpose patch, so it overlaps the store phase.  (Prefetching the next chunk's
       // residual the same way was measured 13 % SLOWER on the 128-channel layers: it competes with the stores.)
@@ -836,6 +901,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
   HDRVAE_REQUIRE(p.stats == nullptr || (p.n_cols % 128 == 0 && p.n_cols <= 512),
                  "gemm_tc: GroupNorm statistics need 128/256/512 output channels");
   const bool tf32 = p.ab_dtype == DT_F32;
+  HDRVAE_REQUIRE(p.row_mode == 0 || (!tf32 && p.cta_group != 1), "gemm_tc: the soft-max passes exist for 16-bit CTA-pair builds");
   static int cg = -1;                                       // CTA pairs by default; HDRVAE_CTA_GROUP=1 selects single CTAs
   if (cg < 0) { const char* e = getenv("HDRVAE_CTA_GROUP"); cg = (e && atoi(e) == 1) ? 1 : 2; }
   int use_cg = p.cta_group > 0 ? p.cta_group : cg;
@@ -901,6 +967,13 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       }
     } else {
       epi = -1;
+    }
+    if (p.row_mode != 0) {
+      HDRVAE_REQUIRE(!n128 && p.tw_log2 == 7 && p.H == 1 && p.row_part != nullptr && p.ntaps == 1 && p.b_img_k_stride == 0,
+                     "gemm_tc: the soft-max passes are row-major GEMMs with >= 256 columns");
+      if (p.row_mode == 1) return launch_tc<256, false, 2, EPI_ROWMAX>(p, num_sms, stream);
+      HDRVAE_REQUIRE(p.out_dtype != DT_F32 && p.bias != nullptr, "gemm_tc: soft-max pass 2 writes a 16-bit output and needs -max per row");
+      return launch_tc<256, false, 2, EPI_OUT16 | EPI_EXPSUM>(p, num_sms, stream);
     }
     if (p.xf_scale != nullptr) {
       // fused GroupNorm + SiLU operand transform (decoder convs without a second output)
