@@ -137,7 +137,7 @@ gn_finalize_kernel(const float* __restrict__ partial, int n_chunks, const float*
 }
 
 
-template <typename TIn, typename TOut, bool kSilu>
+template <typename TIn, typename TOut, bool kSilu, bool kMufu = false>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, int HW, int C, int px_per_block, long long x_img_stride,
@@ -171,7 +171,7 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[u][j] = fmaf(v[u][j], a[j], b[j]);
-        if (kSilu) v[u][j] = silu_f(v[u][j]);
+        if (kSilu) v[u][j] = kMufu ? silu_mufu(v[u][j]) : silu_f(v[u][j]);
       }
       St8<TOut>::st(yout + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
     }
@@ -182,7 +182,7 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] = fmaf(v[j], a[j], b[j]);
-      if (kSilu) v[j] = silu_f(v[j]);
+      if (kSilu) v[j] = kMufu ? silu_mufu(v[j]) : silu_f(v[j]);
     }
     St8<TOut>::st(yout + ((long long)p * vpp + vi) * 8, v);
   }
@@ -212,7 +212,15 @@ static void launch_apply(const void* x, void* y, const float* scale, const float
                          int ppb, bool silu, long long xs, long long ys, cudaStream_t s) {
   const dim3 grid(chunks, B);
   const size_t sm = 2 * C * sizeof(float);
-  if (silu)
+  // exp of the SiLU on the special-function unit (default) or as a polynomial on the FMA pipe (HDRVAE_SILU_MUFU=0).
+  // This kernel is not purely HBM bound: same-box A/B of the C2 step 44.3 ms (polynomial) vs 43.4 ms (ex2 + rcp).  The
+  // polynomial exists for the experimental fused operand transform, where the XU pipe is the scarce one.
+  static int mufu = -1;
+  if (mufu < 0) { const char* e = getenv("HDRVAE_SILU_MUFU"); mufu = (e && atoi(e) == 0) ? 0 : 1; }
+  if (silu && mufu)
+    gn_apply_kernel<TIn, TOut, true, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
+                                                                        scale, shift, HW, C, ppb, xs, ys);
+  else if (silu)
     gn_apply_kernel<TIn, TOut, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
                                                                   scale, shift, HW, C, ppb, xs, ys);
   else
