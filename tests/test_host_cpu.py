@@ -264,3 +264,14 @@ def test_groupnorm_partial_capacity_covers_both_conv_tilings(lib):
         best = min(-(-W // (1 << lg)) * -(-H // (128 >> lg)) for lg in range(8))
         assert cap >= slab and cap >= best, (H, W, cap, slab, best)
         assert lib.hdrvae_conv2d_stats_chunks(H, W, 1) == 4 * cap          # upsample convs: 4 phases
+
+
+def test_public_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/hdrvae.h must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "hdrvae.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
