@@ -17,7 +17,13 @@ e2e   : the same metric through the node API with HOST buffers (pinned latent H2
 roofline : the tcgen05 implicit-GEMM conv kernel (dominant): algorithmic conv FLOPs of one step
         (9.4628 MFLOP per output pixel) / summed device time of its launches in one
         step (CUDA events on the launching stream), against the measured sustained bf16 peak.
-cpu_baseline : the oracle port of the reference node on the host cores, bounded sample.
+cpu_baseline : the oracle port of the reference node on the host cores, bounded sample (one C1-sized call).
+torch_eager_gpu : the same decoder graph in PyTorch eager (cuDNN) on the SAME B200 + the reference's eager HDR math,
+        fp32 (TF32 off) and bf16 autocast, CUDA-event timed — the comparator SURVEY.md §2.1 names.
+aux_c4_4096 / aux_c4_rows : BASELINE config C4 (1x16x512x512 -> 4096^2, "aggressive") on one GPU, and — for N > 1 —
+        row-tiled over the N GPUs of the job (strong scaling), outside the headline's timed region.
+--impl reference : the reference node's CPU path (oracle port, TWO decoder passes + conv_out per call as the
+        reference does) on the host cores: every step is ONE image of the C2 batch at its full 1024^2 size.
 """
 from __future__ import annotations
 
@@ -39,6 +45,18 @@ UNIT = "MP/s"
 CONV_MFLOP_PER_PX = 9.4628          # 3x3/1x1 convs of the decoder, resolution independent
 PER_GPU_BATCH, LATENT = 4, 128      # config C2
 MODE = "moderate"
+C4_ROOFLINE_MP_S = 76.8             # 17.851 MFLOP/px at 4096^2 against the sustained bf16 peak, per GPU
+
+
+def workload_config(world: int) -> dict:
+    """The `config` object of the JSON line: ONE function for both arms, so the reference arm reports exactly the
+    configuration the B200 arm measures (arm-specific detail lives outside `config`)."""
+    B, L = PER_GPU_BATCH, LATENT
+    return {"workload": f"C2 per GPU: {B}x16x{L}x{L} random latents -> {B} x {8 * L}x{8 * L}, mode {MODE} "
+                        "(smart expansion x3), Flux.1 AE decoder random-init",
+            "global_batch": B * world,
+            "parallelism": "single GPU" if world == 1 else f"batch-sharded dp{world} + all-reduce of HDR statistics",
+            "l2": "inputs larger than L2: ~6 GB of activations stream through HBM every step (L2 126 MB)"}
 
 
 def _peaks():
@@ -139,18 +157,20 @@ class ClockSampler:
                 "samples": len(sm), "source": self.src}
 
 
-def cpu_reference_run(steps: int, warmup: int, sample_latent: int = 32):
-    """The reference node's CPU path (oracle port: fp32 PyTorch eager decoder + the restated HDR math,
-    with the reference's real call structure: TWO decoder passes + a third conv_out per call,
-    hdr_vae_decode.py:859,876,1022) on all host cores.  Bounded sample: one 1x16xSxS latent per step."""
+def cpu_reference_run(steps: int, warmup: int, sample_latent: int = 64, budget_s: float = 0.0, dec=None):
+    """The reference node's CPU path (oracle port: fp32 PyTorch eager decoder + the restated HDR math, with the
+    reference's real call structure: TWO decoder passes + a third conv_out per call, hdr_vae_decode.py:859,876,1022)
+    on all host cores.  One 1x16xSxS latent per step; budget_s > 0 stops early once the projected time of another
+    step would exceed it (never fewer than 2 timed steps)."""
     import torch
     from oracle import hdr_oracle as ho
     from oracle.flux_decoder import build_decoder, make_latent
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    dec = build_decoder(0)
+    dec = dec if dec is not None else build_decoder(0)
     z = make_latent(1, sample_latent, sample_latent, seed=1234)
     times = []
+    t_begin = time.perf_counter()
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
@@ -159,27 +179,93 @@ def cpu_reference_run(steps: int, warmup: int, sample_latent: int = 32):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
+            if budget_s > 0 and len(times) >= 2 and (time.perf_counter() - t_begin) + dt > budget_s:
+                break
     mp = (8 * sample_latent) ** 2 / 1e6
     per = sum(times) / len(times)
     return {"value": mp / per, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{len(times)} x (1x16x{sample_latent}x{sample_latent} latent -> {8 * sample_latent}^2, {MODE}; "
-                      f"2 decoder passes + conv_out as the reference node does), {per:.2f} s per call, fp32 torch CPU"}, per
+                      f"2 decoder passes + conv_out as the reference node does), {per:.2f} s per call, fp32 torch CPU, "
+                      f"{cores} threads"}, per, len(times)
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores, on the B200 arm's
+    config.  Every step decodes ONE image of the C2 batch at its full size (1x16x128x128 -> 1024^2, "moderate") with
+    the reference node's call structure; MP/s is per pixel, so one image of the batch is a bounded sample of the
+    4-image step.  Warm-up is a single C2-sized call; the timed steps stop once REF_BUDGET_S (default 420 s) would be
+    exceeded (reported in `steps`, the request in `steps_requested`).  Three C1-sized calls (1x16x64x64 -> 512^2,
+    BASELINE configs[0], the reference's own CPU-runnable case) are timed as well and reported in cpu_baseline."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, per = cpu_reference_run(max(1, min(args.steps, 3)), 1)
+    from oracle.flux_decoder import build_decoder
+    dec = build_decoder(0)
+    budget = float(os.environ.get("REF_BUDGET_S", "420"))
+    c1, c1_per, c1_n = cpu_reference_run(3, 1, 64, dec=dec)
+    base, per, done = cpu_reference_run(max(2, args.steps), 1, LATENT, budget_s=budget, dec=dec)
+    base["c1_512"] = {"value": c1["value"], "unit": UNIT, "s_per_call": c1_per, "calls": c1_n,
+                      "workload": "C1: 1x16x64x64 latent -> 512x512, reference node call structure"}
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "steps": done, "steps_requested": args.steps, "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: {PER_GPU_BATCH}x16x{LATENT}x{LATENT} latents -> 1024x1024, {MODE} "
-                                   "(each reference step is a bounded sample of it, see cpu_baseline.sample)"},
+            "config": workload_config(args.gpus),
+            "reference_step": f"one image of the C2 batch at full size: 1x16x{LATENT}x{LATENT} -> {8 * LATENT}^2, {MODE}, "
+                              "two decoder passes + conv_out + eager HDR math per call (hdr_vae_decode.py:859,876,1022)",
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def torch_eager_gpu(dev, B: int, L: int, seed: int) -> dict:
+    """Same-box comparator: the decoder graph in PyTorch eager on this B200 (cuDNN convs, eager
+    GroupNorm / SiLU / attention) + the reference's eager HDR math, on the headline workload.  (i) fp32 with TF32 off,
+    (ii) bf16 autocast.  Timed with CUDA events: `node_call` = the reference node's call structure (two decoder passes +
+    conv_out, hdr_vae_decode.py:859,876,1022), `one_pass` = a single decoder pass + HDR math (what this library runs).
+    The oracle decoder is used here as a timed baseline only, never by the product path."""
+    import torch
+    from oracle import hdr_oracle as ho
+    from oracle.flux_decoder import build_decoder, make_latent
+    res = {}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        dec = build_decoder(0).to(dev)
+        z = make_latent(B, L, L, seed=seed).to(dev)
+        mp = B * (8 * L) ** 2 / 1e6
+
+        def timed(fn, reps):
+            fn(); torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+
+        for name, ctx, reps in (("fp32_tf32_off", torch.autocast("cuda", enabled=False), 2),
+                                ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16), 3)):
+            with torch.no_grad(), ctx:
+                def one_pass():
+                    return ho.simple_hdr_decode(dec, z, MODE, 1.0)[0]
+
+                def node_call():
+                    dec(z)
+                    return ho.simple_hdr_decode(dec, z, MODE, 1.0)[0]
+                ms1 = timed(one_pass, reps)
+                ms2 = timed(node_call, reps)
+            res[name] = {"node_call_ms": ms2, "node_call_mp_s": mp / (ms2 / 1e3), "one_pass_ms": ms1,
+                         "one_pass_mp_s": mp / (ms1 / 1e3)}
+        res["workload"] = f"{B}x16x{L}x{L} -> {B} x {8 * L}^2, {MODE}; torch {torch.__version__} eager, cuDNN {torch.backends.cudnn.version()}"
+        del dec, z
+    except Exception as exc:      # a comparator must never cost the headline line
+        res["error"] = repr(exc)[:300]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+    return res
 
 
 _REAL_STDOUT = None
@@ -211,6 +297,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary 4096^2 single-GPU measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-the-same-GPU comparator")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -317,12 +404,12 @@ def main():
                 "groupnorm_gbs": (1837.1e6 * B * 6.0 / (gn_ms / 1e3) / 1e9) if gn_ms > 0 else None,
                 "hbm_peak_gbs": peak_gbs}
 
-    # ---- e2e through the node API with host buffers
+    # ---- e2e through the node API with host buffers: same number of steps as the device-timed value
     vae = SyntheticVAE(sd, device=dev, output_device="cpu")
     node = NODE_CLASS_MAPPINGS["HDRVAEDecode"]()
     node.adopt_engine(vae, dev, engine)          # reuse the packed weights (same state dict)
     z_host = synthetic_latent(B, L, L, seed=1234 + rank).pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = args.steps
     for _ in range(2):
         (img,) = node.simple_hdr_decode({"samples": z_host}, vae, hdr_mode=MODE)
     barrier()
@@ -335,25 +422,34 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = {"value": mp_per_rank * world / (float(dt.item()) / e2e_steps), "unit": UNIT,
-           "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": img.numel() * 4,
-           "note": "node API, pinned host latent in, host IMAGE out; N>1: independent per-rank node calls"}
+           "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": img.numel() * 4, "steps": e2e_steps,
+           "note": "node API, pinned host latent in, host IMAGE out (wall clock incl. both copies); N>1: independent per-rank node calls"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": f"C2 per GPU: {B}x16x{L}x{L} random latents -> {B} x {8 * L}x{8 * L}, mode {MODE} "
-                                   "(smart expansion x3), Flux.1 AE decoder random-init, fp16 operands / fp32 accumulate / fp32 residual stream",
-                       "precision": "fp16 tensor-core operands (16-bit, same width and rate as the bf16 BASELINE names; bf16 "
-                                    "misses its 1e-2 parity bar, DESIGN.md), fp32 accumulate, fp32 residual stream",
-                       "global_batch": B * world,
-                       "parallelism": "single GPU" if world == 1 else f"batch-sharded dp{world} + all-reduce of HDR statistics",
-                       "l2": "inputs larger than L2: ~6 GB of activations stream through HBM every step (L2 126 MB)"},
+            "config": workload_config(world),
+            "precision": "fp16 tensor-core operands (16-bit, same width and rate as the bf16 BASELINE names; bf16 "
+                         "misses its 1e-2 parity bar, DESIGN.md), fp32 accumulate, fp32 residual stream",
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary()}
+    del img
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_reference_run(2, 1)
+        # bounded sample: C1-sized calls (BASELINE configs[0], 1x16x64x64 -> 512^2) with the reference's call structure
+        line["cpu_baseline"], _, _ = cpu_reference_run(2, 1, 64)
+    if rank == 0 and not args.no_eager:
+        engine._workspace = None
+        torch.cuda.empty_cache()
+        line["torch_eager_gpu"] = torch_eager_gpu(dev, B, L, 1234)
+        te = line["torch_eager_gpu"]
+        if "bf16_autocast" in te:
+            line["speedup_vs_torch_eager_same_gpu"] = {
+                "per_gpu_value_mp_s": value / world,
+                "vs_bf16_autocast_node_call": (value / world) / te["bf16_autocast"]["node_call_mp_s"],
+                "vs_bf16_autocast_one_pass": (value / world) / te["bf16_autocast"]["one_pass_mp_s"],
+                "vs_fp32_node_call": (value / world) / te["fp32_tf32_off"]["node_call_mp_s"]}
     if world == 1 and not args.no_aux:
         # BASELINE.json quotes the metric at 1024^2 AND 4096^2: config C4 (1x16x512x512 -> 4096^2, "aggressive") on this
-        # one GPU, outside the timed region of the headline value; the 8-GPU row-tiled number is in profiles/ (58.4 ms).
+        # one GPU, outside the timed region of the headline value
         try:
             engine._workspace = None
             torch.cuda.empty_cache()
@@ -368,13 +464,124 @@ def main():
             ms4 = e0.elapsed_time(e1) / 2
             line["aux_c4_4096"] = {"workload": "C4 on one GPU: 1x16x512x512 latent -> 4096x4096, aggressive (not row-tiled)",
                                    "ms_per_image": ms4, "value": 16.777216 / (ms4 / 1e3), "unit": UNIT,
+                                   "roofline_frac": 16.777216 / (ms4 / 1e3) / C4_ROOFLINE_MP_S,
                                    "finite": bool(torch.isfinite(out4).all())}
+            del out4, z4
         except Exception as exc:      # never lose the headline line to the auxiliary measurement
             line["aux_c4_4096"] = {"error": repr(exc)[:200]}
+    if world > 1:
+        line["multi_gpu_selftest"] = multi_gpu_selftest(engine, dev, rank, world)
+    if world > 1 and not args.no_aux:
+        line["aux_c4_rows"] = aux_c4_rows(engine, dev, rank, world, args)
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_selftest(engine, dev, rank: int, world: int) -> dict:
+    """Real-NCCL parity checks run inside the driver's multi-GPU step (the pytest box has one GPU): every rank compares
+    what the sharded paths gave it with its OWN single-GPU decode of the same input; the worst difference over ranks is
+    reported.  (a) ragged batch sharding (world + 1 images: the first rank gets two), (b) a batch of ONE image over all
+    ranks (every rank but the first holds an empty shard), (c) row tiling of one image with 16 latent rows per rank
+    (conv tiles coincide with the single-GPU tiling, so the result must be identical)."""
+    import torch
+    import torch.distributed as dist
+    from vae_decode_hdr_b200.sharding import decode_batch_sharded, decode_rows_sharded, shard_bounds
+    from vae_decode_hdr_b200.synthetic import synthetic_latent
+    res = {}
+    try:
+        def worst(x: float) -> float:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def rel(a, b):
+            return float((a.double() - b.double()).norm() / b.double().norm()) if b.numel() else 0.0
+        zb = synthetic_latent(world + 1, 8, 8, seed=5).to(dev)
+        s, e = shard_bounds(world + 1, world)[rank]
+        out, st = decode_batch_sharded(engine, zb[s:e], "adaptive_recovery", 1.0)
+        whole, st1 = engine.decode(zb, "adaptive_recovery", 1.0)
+        res["batch_ragged_rel"] = worst(rel(out, whole[s:e]))
+        res["batch_stats_rel"] = worst(max(abs(st[k] - st1[k]) / max(1.0, abs(st1[k])) for k in ("pre_min", "pre_max", "pre_mean", "rec_max", "aligned_max")))
+        z1 = synthetic_latent(1, 8, 8, seed=6).to(dev)
+        s, e = shard_bounds(1, world)[rank]
+        out, _ = decode_batch_sharded(engine, z1[s:e], "exposure", 1.0)
+        whole, _ = engine.decode(z1, "exposure", 1.0)
+        res["batch_empty_shards_rel"] = worst(rel(out, whole[s:e]) if tuple(out.shape) == (e - s, 64, 64, 3) else 1.0)
+        zr = synthetic_latent(1, 16 * world, 8, seed=9).to(dev)
+        out, _ = decode_rows_sharded(engine, zr, "moderate", 1.0)
+        whole, _ = engine.decode(zr, "moderate", 1.0)
+        rows = 8 * 16
+        res["rows_tiled_rel"] = worst(rel(out, whole[:, rank * rows:(rank + 1) * rows]))
+        res["pass"] = bool(res["batch_ragged_rel"] < 1e-6 and res["batch_stats_rel"] < 1e-6 and
+                           res["batch_empty_shards_rel"] < 1e-6 and res["rows_tiled_rel"] < 1e-6)
+    except Exception as exc:
+        res["error"] = repr(exc)[:300]
+        res["pass"] = False
+    return res
+
+
+def aux_c4_rows(engine, dev, rank: int, world: int, args) -> dict:
+    """BASELINE config C4 under the driver's eyes: ONE 1x16x512x512 latent -> 4096x4096, "aggressive", spatially
+    row-tiled over the N GPUs of this job (conv halos over NVLink, GroupNorm sums all-reduced, attention K/V
+    all-gathered; sharding.decode_rows_sharded) — strong scaling.  Device-timed, max over ranks; the tiled image is
+    compared with the single-GPU decode of the same latent on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from vae_decode_hdr_b200.sharding import decode_rows_sharded
+    from vae_decode_hdr_b200.synthetic import synthetic_latent
+    L4 = int(os.environ.get("HDRVAE_BENCH_C4_LATENT", "512"))
+    res = {"workload": f"C4: 1x16x{L4}x{L4} latent -> {8 * L4}x{8 * L4}, aggressive, row-tiled over {world} GPUs "
+                       f"({L4 // world} latent rows per GPU)", "n_gpus": world, "transport": "nccl"}
+    try:
+        engine._workspace = None
+        torch.cuda.empty_cache()
+        z4 = synthetic_latent(1, L4, L4, seed=1234).to(dev)
+        for _ in range(2):
+            out, _ = decode_rows_sharded(engine, z4, "aggressive", 1.0, want_stats=False)
+        torch.cuda.synchronize(dev); dist.barrier()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out, _ = decode_rows_sharded(engine, z4, "aggressive", 1.0, want_stats=False)
+        e1.record()
+        torch.cuda.synchronize(dev); dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        mp = (8 * L4) ** 2 / 1e6
+        res.update({"ms_per_image": ms, "value": mp / (ms / 1e3), "unit": UNIT, "scaling": "strong",
+                    "per_gpu_mp_s": mp / (ms / 1e3) / world,
+                    "per_gpu_roofline_frac": mp / (ms / 1e3) / world / C4_ROOFLINE_MP_S,
+                    "roofline_mp_s_per_gpu": C4_ROOFLINE_MP_S})
+        parts = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        dist.gather(out.contiguous(), parts, dst=0)
+        del out
+        if rank == 0:
+            tiled = torch.cat(parts, dim=1)
+            del parts
+            torch.cuda.empty_cache()
+            whole, _ = engine.decode(z4, "aggressive", 1.0, want_stats=False)
+            e0.record()
+            whole, _ = engine.decode(z4, "aggressive", 1.0, want_stats=False)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            res["single_gpu_ms"] = e0.elapsed_time(e1)
+            res["speedup_vs_single_gpu"] = res["single_gpu_ms"] / ms
+            d = n = 0.0
+            for r0 in range(0, whole.shape[1], 256):       # chunked: fp64 copies of a 4096^2 image are large
+                wch, tch = whole[:, r0:r0 + 256].double(), tiled[:, r0:r0 + 256].double()
+                d += float(((wch - tch) ** 2).sum()); n += float((wch ** 2).sum())
+            res["rel_l2_vs_single_gpu"] = (d / n) ** 0.5
+            del whole, tiled
+        engine._workspace = None
+        torch.cuda.empty_cache()
+        dist.barrier()
+    except Exception as exc:
+        res["error"] = repr(exc)[:300]
+    return res
 
 
 if __name__ == "__main__":

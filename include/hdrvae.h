@@ -167,6 +167,12 @@ int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float e
                          float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Batch sharding, the exchange step: merge `n` gathered hdrvae_raw_stats blocks (device memory, 96 bytes each, rank
+ * order — the result of ONE all-gather of every rank's block) into *dst (device; must not alias `blocks`), MIN / MAX /
+ * SUM in rank order, so every rank derives bit-identical batch-global statistics (hdr_vae_decode.py:862-865,1098,1116
+ * take them over the whole batch tensor). */
+int hdrvae_raw_stats_merge(const void* blocks, int n, void* dst, void* stream);
+
 /* ---- spatial row tiling across GPUs (BASELINE config C4) --------------------------------------
  * One image, latent rows split evenly over `world` ranks (h % world == 0).  Every rank runs the same step
  * program on its slab; between steps the HOST performs the exchange the library describes (NCCL in

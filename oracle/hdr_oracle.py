@@ -87,12 +87,13 @@ def inverse_tanh(x: torch.Tensor) -> torch.Tensor:
     return torch.atanh(torch.clamp(x, -1 + 1e-6, 1 - 1e-6))
 
 
-def analyze(pre: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor) -> Dict:
+def analyze(pre: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, conv_fn=None) -> Dict:
     """analyze_conv_out (hdr_vae_decode.py:837-925) given the hooked tensor.
 
     ``pre`` is the input of decoder.conv_out ([B,128,H,W]); the "final result"
     is ComfyUI's VAE.decode output clamp((conv+1)/2,0,1) in BHWC."""
-    conv_only = F.conv2d(pre, conv_w, conv_b, padding=1)                      # :876
+    # conv_fn: the same convolution evaluated band by band (oracle/big_oracle.py) for tensors of >= 2^31 elements
+    conv_only = conv_fn(pre) if conv_fn is not None else F.conv2d(pre, conv_w, conv_b, padding=1)   # :876
     standard = torch.clamp((conv_only + 1.0) / 2.0, 0.0, 1.0).movedim(1, -1)  # comfy.sd.VAE.decode
     st = {
         "pre_min": float(pre.min()), "pre_max": float(pre.max()),             # :862-865
@@ -168,12 +169,12 @@ def intelligent(standard: torch.Tensor, pre: torch.Tensor, st: Dict, mode: str,
 
 def hdr_epilogue(pre: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor,
                  hdr_mode: str = "mathematical_recovery",
-                 conservative_ev_multiplier: float = 1.0) -> Tuple[torch.Tensor, Dict]:
+                 conservative_ev_multiplier: float = 1.0, conv_fn=None) -> Tuple[torch.Tensor, Dict]:
     """Everything simple_hdr_decode does after the decoder produced ``pre``
     (hdr_vae_decode.py:88-112, 180-195) -> (float32 [B,H,W,3] contiguous, stats)."""
     mode, factor = resolve_mode(hdr_mode)
     pre = pre.float()
-    an = analyze(pre, conv_w.float(), conv_b.float())
+    an = analyze(pre, conv_w.float(), conv_b.float(), conv_fn)
     st = dict(an["stats"])
     decoded, st2 = intelligent(an["standard"], pre, st, mode, factor)
     st.update(st2)

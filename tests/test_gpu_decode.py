@@ -5,6 +5,8 @@ import torch
 from oracle import hdr_oracle as ho
 from oracle.flux_decoder import FakeComfyVAE, build_decoder, make_latent
 
+from _metrics import rel_l2_outside, saturation_band_mask
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
@@ -18,15 +20,6 @@ def setup():
     eng = HdrVaeEngine(dec.state_dict(), DEV)          # default precision: fp16 operands, fp32 streams
     yield dec, eng
     eng.close()
-
-
-def _rel_trimmed(a, b, frac):
-    """rel-L2 with the `frac` largest per-pixel squared errors left out (frac = 0: plain rel-L2)."""
-    e = ((a - b).double() ** 2).sum(dim=-1).flatten()
-    if frac > 0:
-        k = e.numel() - int(frac * e.numel())
-        e = e.sort().values[:k]
-    return float(e.sum().sqrt() / b.double().norm())
 
 
 def _rel(a, b):
@@ -67,7 +60,8 @@ def test_tcgen05_path_equals_direct_path(setup):
 
 @pytest.mark.parametrize("mode", list(ho.HDR_MODES) + ["moderate"])
 def test_full_decode_vs_oracle(setup, mode):
-    """Node-level output within rel-L2 <= 1e-2 of the fp32 reference output (BASELINE.json north_star)."""
+    """Node-level output within rel-L2 <= 1e-2 of the fp32 reference output (BASELINE.json north_star), plain rel-L2.
+    BASELINE's own shapes (C1, C3, C4) and the known ill-conditioned case are in test_gpu_parity_big.py."""
     dec, eng = setup
     z = make_latent(2, 16, 16, seed=77).to(DEV)
     out, st = eng.decode(z, mode, 1.0)
@@ -182,14 +176,18 @@ def test_row_tiled_decode_equals_single_gpu(setup, world, h, w, mode):
     tiled, st = decode_rows_emulated(eng, z, world, mode)
     whole, st1 = eng.decode(z, mode)
     assert tiled.shape == whole.shape
-    ref, _, _ = ho.simple_hdr_decode(dec, z, mode, 1.0)
-    # The logit-recovery modes are ill-conditioned at saturated pixels (logit(x), x -> 1: the reference clamps at
-    # 1 - 1e-7), so a handful of pixels can carry any rounding difference amplified 100x (measured: one pixel row
-    # at 9e-2 while the features differ by 1.4e-3).  Those modes are compared with the 0.2% worst pixels set aside;
-    # conservative / smart expansion are compared in full.
-    trim = 0.0 if mode in ("conservative", "moderate") else 0.002
-    assert _rel_trimmed(tiled, ref.to(DEV), trim) < 1e-2, _rel_trimmed(tiled, ref.to(DEV), trim)
-    assert _rel_trimmed(tiled, whole, trim) < 5e-3, _rel_trimmed(tiled, whole, trim)
+    ref, _, pre = ho.simple_hdr_decode(dec, z, mode, 1.0)
+    # The logit-recovery modes are ill-conditioned at pixels whose sigmoid-domain value sits within 1e-4 of a clamp end
+    # (logit slope > 1e4; the reference clamps at 1e-7): those pixels are identified BY RULE from the reference's own
+    # conv_out values (tests/_metrics.py: saturation_band_mask) and set aside for the three logit modes; they must be a
+    # small minority.  conservative / smart expansion are compared in full.
+    if mode in ("conservative", "moderate"):
+        band = torch.zeros(tiled.shape[:3], dtype=torch.bool, device=DEV)
+    else:
+        band = saturation_band_mask(dec, pre)
+        assert float(band.float().mean()) < 5e-3
+    assert rel_l2_outside(tiled, ref.to(DEV), band) < 1e-2, rel_l2_outside(tiled, ref.to(DEV), band)
+    assert rel_l2_outside(tiled, whole, band) < 5e-3, rel_l2_outside(tiled, whole, band)
     assert st["pre_max"] == pytest.approx(st1["pre_max"], rel=2e-3) and st["norm_function"] == st1["norm_function"]
     if (world, h, w) == (2, 32, 8):
         assert _rel(tiled, whole) < 1e-6, _rel(tiled, whole)

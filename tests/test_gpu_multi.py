@@ -28,6 +28,13 @@ def _worker(rank, world, port, q):
     whole, st1 = eng.decode(z.to(dev), "adaptive_recovery", 1.0)        # every rank also decodes the whole batch alone
     same = torch.allclose(out, whole[s:e], rtol=1e-6, atol=1e-7)
     stats_same = all(abs(st[k] - st1[k]) <= 1e-6 * max(1.0, abs(st1[k])) for k in ("pre_min", "pre_max", "pre_mean", "post_mean", "rec_max", "aligned_max"))
+    # batch smaller than the world size: rank 1 holds an EMPTY shard, contributes the neutral statistics block and must
+    # neither raise nor dead-lock the exchange; rank 0's image equals the single-GPU decode
+    z1 = synthetic_latent(1, 8, 8, seed=6)
+    s1, e1 = shard_bounds(1, world)[rank]
+    out1, _ = decode_batch_sharded(eng, z1[s1:e1].to(dev), "exposure", 1.0)
+    whole1, _ = eng.decode(z1.to(dev), "exposure", 1.0)
+    same = same and tuple(out1.shape) == (e1 - s1, 64, 64, 3) and torch.allclose(out1, whole1[s1:e1], rtol=1e-6, atol=1e-7)
     q.put((rank, bool(same), bool(stats_same), int(st["hdr_pixels"])))
     dist.destroy_process_group()
 

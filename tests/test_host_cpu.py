@@ -88,7 +88,9 @@ def test_node_surface_equals_reference():
     from vae_decode_hdr_b200 import NODE_CLASS_MAPPINGS, NODE_DISPLAY_NAME_MAPPINGS
     cls = NODE_CLASS_MAPPINGS["HDRVAEDecode"]
     it = cls.INPUT_TYPES()
-    assert NODE_DISPLAY_NAME_MAPPINGS == {"HDRVAEDecode": "HDR VAE Decode", "HDRUpscaleWithModel": "HDR Upscale with Model"}
+    assert NODE_DISPLAY_NAME_MAPPINGS == {"HDRVAEDecode": "HDR VAE Decode", "LinearEXRExport": "Linear EXR Export",
+                                          "HDRUpscaleWithModel": "HDR Upscale with Model"}
+    assert list(NODE_CLASS_MAPPINGS) == ["HDRVAEDecode", "LinearEXRExport", "HDRUpscaleWithModel"]     # __init__.py:43-47
     assert (cls.RETURN_TYPES, cls.RETURN_NAMES, cls.FUNCTION, cls.CATEGORY) == (("IMAGE",), ("image",), "simple_hdr_decode", "latent")
     from oracle.ref_loader import load_reference_module, reference_available
     if reference_available():      # build container: compare with the unmodified reference class
@@ -97,8 +99,35 @@ def test_node_surface_equals_reference():
         assert (cls.RETURN_TYPES, cls.RETURN_NAMES, cls.FUNCTION, cls.CATEGORY) == \
             (ref.RETURN_TYPES, ref.RETURN_NAMES, ref.FUNCTION, ref.CATEGORY)
         import inspect
-        assert list(inspect.signature(cls.simple_hdr_decode).parameters) == \
+        mine = inspect.signature(cls.simple_hdr_decode).parameters
+        # same named parameters in the same order; the only addition is a **kwargs sink for the README-era inputs
+        assert [n for n, p in mine.items() if p.kind is not inspect.Parameter.VAR_KEYWORD] == \
             list(inspect.signature(ref.simple_hdr_decode).parameters)
+        assert NODE_CLASS_MAPPINGS.keys() == load_reference_package_mappings().keys()
+
+
+def load_reference_package_mappings():
+    """NODE_CLASS_MAPPINGS keys of the unmodified reference __init__.py (read as text: importing it needs ComfyUI)."""
+    src = open("/root/reference/__init__.py").read()
+    block = src[src.index("NODE_CLASS_MAPPINGS = {"):]
+    block = block[:block.index("}")]
+    return {k: None for k in re.findall(r'"(\w+)":', block)}
+
+
+def test_legacy_readme_inputs_are_tolerated_and_unknown_ones_rejected():
+    """README.md:143-145 / workflow_examples/HDR_VAE_DECODE.json:499-504: max_range, scale_factor, enable_negatives no
+    longer exist in the reference code; prompts that still carry them must not fail on the argument list."""
+    from vae_decode_hdr_b200 import NODE_CLASS_MAPPINGS
+    from vae_decode_hdr_b200.synthetic import SyntheticVAE
+    node = NODE_CLASS_MAPPINGS["HDRVAEDecode"]()
+    z = {"samples": torch.zeros(1, 16, 4, 4)}
+    with pytest.raises(TypeError, match="bogus"):
+        node.simple_hdr_decode(z, SyntheticVAE({}, device="cpu"), bogus=1)
+    if not torch.cuda.is_available():
+        # the legacy names pass the argument check; what fails afterwards is the missing GPU, not the call signature
+        with pytest.raises(RuntimeError, match="CUDA"):
+            node.simple_hdr_decode(z, SyntheticVAE({}, device="cpu"), hdr_mode="conservative", max_range=50,
+                                   scale_factor=1, enable_negatives=False)
 
 
 def test_mode_resolution_and_synthetic_weights():
@@ -153,6 +182,42 @@ def _gloo_worker(rank, world, port, q):
     ok = torch.equal(vmin, fmin) and torch.equal(vmax, fmax) and torch.allclose(vsum, fsum, rtol=1e-12)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
+
+
+def _gloo_block_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from vae_decode_hdr_b200.sharding import exchange_raw_stats_block, identity_raw_block
+    # rank 2 holds an EMPTY shard (batch 2 over 3 ranks): it contributes the neutral block
+    if rank == 2:
+        blk = identity_raw_block("cpu")
+    else:
+        blk = torch.zeros(96, dtype=torch.uint8)
+        blk[0:16].view(torch.float32).copy_(torch.tensor([1.0, -2.0, 0.5, 3.0]) + rank)
+        blk[16:32].view(torch.float32).copy_(torch.tensor([5.0, 6.0, 7.0, 8.0]) - rank)
+        blk[32:96].view(torch.float64).copy_(torch.arange(8, dtype=torch.float64) * (rank + 1))
+    exchange_raw_stats_block(blk, group=None)
+    ok = torch.equal(blk[0:16].view(torch.float32), torch.tensor([1.0, -2.0, 0.5, 3.0]))
+    ok &= torch.equal(blk[16:32].view(torch.float32), torch.tensor([5.0, 6.0, 7.0, 8.0]))
+    ok &= torch.equal(blk[32:96].view(torch.float64), torch.arange(8, dtype=torch.float64) * 3)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_raw_stats_single_collective_exchange_with_empty_shard_gloo_world3():
+    """The batch-sharded exchange step (ONE all-gather + rank-order merge) on 3 CPU ranks, one of which holds an empty
+    shard and contributes the neutral block: every rank ends with the statistics of the two non-empty shards."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_block_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True), (2, True)]
 
 
 def test_batch_sharded_stats_allreduce_gloo_world2():

@@ -144,3 +144,22 @@ def test_live_reference_agrees_with_oracle_fresh_seed():
     out, st, _ = ho.simple_hdr_decode(dec, z, "exposure", 1.5)
     assert st["accepted"] == 1
     assert (out - ref).norm() / ref.norm() < 1e-6
+
+
+def test_banded_oracle_equals_plain_oracle():
+    """oracle/big_oracle.py (what the 4096^2 GPU parity test compares against) == FluxDecoder.features + the HDR math
+    at a size both run, with band / chunk sizes that do not divide the image."""
+    import torch
+    from oracle import big_oracle as bo
+    from oracle import hdr_oracle as ho
+    from oracle.flux_decoder import build_decoder, make_latent
+    dec = build_decoder(0)
+    z = make_latent(1, 6, 5, seed=3)
+    with torch.no_grad():
+        a = dec.features(z)
+    b = bo.features_banded(dec, z, band=7, q_chunk=11)
+    assert float((a - b).norm() / a.norm()) < 1e-5
+    o1, s1, _ = ho.simple_hdr_decode(dec, z, "aggressive")
+    o2, s2, _ = bo.simple_hdr_decode_banded(dec, z, "aggressive", band=7, q_chunk=11)
+    assert float((o1 - o2).norm() / o1.norm()) < 1e-4
+    assert s1["norm_function"] == s2["norm_function"] and s1["has_hdr"] == s2["has_hdr"]

@@ -73,6 +73,7 @@ SIGNATURES = {
     "hdrvae_decode": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp, C.POINTER(HdrvaeStats), _vp, _sz, _vp]),
     "hdrvae_decode_begin": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, C.POINTER(_vp), _vp]),
     "hdrvae_decode_finish": (_i, [_vp, _i, _i, _i, _i, _f, _f, _vp, C.POINTER(HdrvaeStats), _vp, _sz, _vp]),
+    "hdrvae_raw_stats_merge": (_i, [_vp, _i, _vp, _vp]),
     "hdrvae_rows_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "hdrvae_rows_begin": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, C.POINTER(_vp)]),
     "hdrvae_rows_run": (_i, [_vp, C.POINTER(HdrvaeExchange), _vp]),

@@ -1026,6 +1026,56 @@ int hdrvae_workspace_bytes(hdrvae_ctx* ctx, int B, int h, int w, size_t* bytes) 
   return 0;
 }
 
+// ---- CUDA-graph segments ------------------------------------------------------------------------------------------
+// The decode is captured into two CUDA graphs the second time a (shape, mode, workspace) key is seen and replayed
+// afterwards: segment 0 = decoder + epilogue phase A (~160 launches for a batch of 4), segment 1 = epilogue phase B.
+// The split sits exactly where batch sharding all-reduces the raw statistics (hdrvae_decode_begin / _finish), so the
+// sharded path replays the same graphs as the single-GPU one.  The latent is staged into / the image out of fixed
+// workspace buffers so the graphs do not depend on the caller's tensor addresses.  HDRVAE_NO_GRAPH=1 disables it.
+static bool graphs_enabled(hdrvae_ctx* ctx, cudaStream_t s) {
+  static int no_graph = -1;
+  if (no_graph < 0) { const char* e = getenv("HDRVAE_NO_GRAPH"); no_graph = (e && atoi(e) != 0) ? 1 : 0; }
+  return ctx->use_graphs && !no_graph && !g_prof_on && s != nullptr;     // capture needs a non-default stream
+}
+
+static int run_segment(hdrvae_ctx* ctx, hdrvae_ctx::GraphEntry key, cudaStream_t s, const std::function<int()>& body) {
+  auto same = [&](const hdrvae_ctx::GraphEntry& g) {
+    return g.seg == key.seg && g.B == key.B && g.h == key.h && g.w == key.w && g.mode == key.mode && g.factor == key.factor &&
+           g.ev == key.ev && g.ws == key.ws && g.conv_impl == key.conv_impl && g.cta_group == key.cta_group;
+  };
+  for (auto& g : ctx->graphs)
+    if (same(g)) {
+      g_launch_count += g.n_kernels;
+      HDRVAE_CUDA_OK(cudaGraphLaunch(g.exec, s));
+      return 0;
+    }
+  bool seen = false;
+  for (auto& g : ctx->seen) if (same(g)) seen = true;
+  if (!seen) {
+    // first use of this key: plain launches (also runs every one-time cudaFuncSetAttribute outside a capture)
+    if (ctx->seen.size() > 64) ctx->seen.clear();
+    ctx->seen.push_back(key);
+    return body();
+  }
+  const long long n_before = g_launch_count;    // launches recorded by the capture = kernels of every replay
+  HDRVAE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  const int r = body();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+  HDRVAE_REQUIRE(e == cudaSuccess && graph != nullptr, "hdrvae_decode: CUDA graph capture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  HDRVAE_REQUIRE(e == cudaSuccess, "hdrvae_decode: cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  if (ctx->graphs.size() >= 16) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+  key.exec = exec;
+  key.n_kernels = g_launch_count - n_before;
+  ctx->graphs.push_back(key);
+  HDRVAE_CUDA_OK(cudaGraphLaunch(exec, s));
+  return 0;
+}
+
 int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, void* workspace, size_t ws_bytes,
                         void** raw_stats_dev, void* stream) {
   HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr, "hdrvae_decode: null argument");
@@ -1035,11 +1085,19 @@ int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int 
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  void* feat = nullptr;
-  HDRVAE_TRY(run_decoder(ctx, latent, pl, ws, &feat, s));
-  {
+  auto body = [&](const float* lat) -> int {
+    void* feat = nullptr;
+    HDRVAE_TRY(run_decoder(ctx, lat, pl, ws, &feat, s));
     ProfScope prof("epilogue phase A (conv_out, max-pool, stats)", 2.0 * B * 64.0 * h * w * 3 * 1152, B * 64.0 * h * w * (256 + 24), s);
-    HDRVAE_TRY(run_phase_a(ctx, feat, B, 8 * h, 8 * w, 0, reinterpret_cast<float*>(ws + pl.off_h), ws + pl.off_epi, s));
+    return run_phase_a(ctx, feat, B, 8 * h, 8 * w, 0, reinterpret_cast<float*>(ws + pl.off_h), ws + pl.off_epi, s);
+  };
+  if (graphs_enabled(ctx, s)) {
+    float* lat_in = reinterpret_cast<float*>(ws + pl.off_lat_in);
+    HDRVAE_CUDA_OK(cudaMemcpyAsync(lat_in, latent, (size_t)B * 16 * pl.T * 4, cudaMemcpyDeviceToDevice, s));
+    hdrvae_ctx::GraphEntry key{0, B, h, w, 0, ctx->conv_impl, ctx->cta_group, 0.f, 0.f, workspace, nullptr, 0};
+    HDRVAE_TRY(run_segment(ctx, key, s, [&]() { return body(lat_in); }));
+  } else {
+    HDRVAE_TRY(body(latent));
   }
   if (raw_stats_dev != nullptr) *raw_stats_dev = epilogue_raw_stats_ptr(ws + pl.off_epi, B, 8 * h, 8 * w);
   return 0;
@@ -1048,75 +1106,21 @@ int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int 
 int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float expansion_factor, float ev_multiplier,
                          float* out_bhwc, hdrvae_stats* stats, void* workspace, size_t ws_bytes, void* stream) {
   HDRVAE_REQUIRE(ctx != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
-  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w);
-  HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  ProfScope prof("epilogue phase B (mode formula)", 0.0, B * 64.0 * h * w * 36, reinterpret_cast<cudaStream_t>(stream));
-  return launch_epilogue_phase_b(B, 8 * h, 8 * w, mode, expansion_factor, ev_multiplier, out_bhwc, stats,
-                                 ws + pl.off_epi, reinterpret_cast<cudaStream_t>(stream));
-}
-
-// The whole decode (~130 launches) is captured into a CUDA graph the second time a (shape, mode, workspace) key
-// is seen and replayed afterwards: the latent is staged into / the image out of fixed workspace buffers so the
-// graph does not depend on the caller's tensor addresses.  HDRVAE_NO_GRAPH=1 disables it.
-int hdrvae_decode(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, int mode, float expansion_factor,
-                  float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace, size_t ws_bytes,
-                  void* stream) {
-  HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
-  HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode: empty latent batch [%d,16,%d,%d]", B, h, w);
   HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_decode: bad mode %d", mode);
-  static int no_graph = -1;
-  if (no_graph < 0) { const char* e = getenv("HDRVAE_NO_GRAPH"); no_graph = (e && atoi(e) != 0) ? 1 : 0; }
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool graphs = ctx->use_graphs && !no_graph && !g_prof_on && s != nullptr;     // capture needs a non-default stream
-  if (!graphs) {
-    HDRVAE_TRY(hdrvae_decode_begin(ctx, latent, B, h, w, workspace, ws_bytes, nullptr, stream));
-    return hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, out_bhwc, stats, workspace, ws_bytes,
-                                stream);
-  }
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   const Plan pl = make_plan(B, h, w);
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  float* lat_in = reinterpret_cast<float*>(ws + pl.off_lat_in);
-  float* img = reinterpret_cast<float*>(ws + pl.off_img);
-  HDRVAE_CUDA_OK(cudaMemcpyAsync(lat_in, latent, (size_t)B * 16 * pl.T * 4, cudaMemcpyDeviceToDevice, s));
-  auto same = [&](const hdrvae_ctx::GraphEntry& g) {
-    return g.B == B && g.h == h && g.w == w && g.mode == mode && g.factor == expansion_factor && g.ev == ev_multiplier &&
-           g.ws == workspace && g.conv_impl == ctx->conv_impl && g.cta_group == ctx->cta_group;
-  };
-  cudaGraphExec_t exec = nullptr;
-  for (auto& g : ctx->graphs) if (same(g)) { exec = g.exec; g_launch_count += g.n_kernels; }
-  if (exec == nullptr) {
-    bool seen = false;
-    for (auto& g : ctx->seen) if (same(g)) seen = true;
-    hdrvae_ctx::GraphEntry key{B, h, w, mode, ctx->conv_impl, ctx->cta_group, expansion_factor, ev_multiplier, workspace, nullptr, 0};
-    if (!seen) {
-      // first use of this key: plain launches (also runs every one-time cudaFuncSetAttribute outside a capture)
-      if (ctx->seen.size() > 64) ctx->seen.clear();
-      ctx->seen.push_back(key);
-      HDRVAE_TRY(hdrvae_decode_begin(ctx, lat_in, B, h, w, workspace, ws_bytes, nullptr, stream));
-      HDRVAE_TRY(hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, img, nullptr, workspace, ws_bytes, stream));
-    } else {
-      const long long n_before = g_launch_count;    // launches recorded by the capture = kernels of every replay
-      HDRVAE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      int r = hdrvae_decode_begin(ctx, lat_in, B, h, w, workspace, ws_bytes, nullptr, stream);
-      if (r == 0) r = hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, img, nullptr, workspace, ws_bytes, stream);
-      cudaGraph_t graph = nullptr;
-      cudaError_t e = cudaStreamEndCapture(s, &graph);
-      if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
-      HDRVAE_REQUIRE(e == cudaSuccess && graph != nullptr, "hdrvae_decode: CUDA graph capture failed: %s", cudaGetErrorString(e));
-      e = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      HDRVAE_REQUIRE(e == cudaSuccess, "hdrvae_decode: cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-      if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
-      key.exec = exec;
-      key.n_kernels = g_launch_count - n_before;
-      ctx->graphs.push_back(key);
-    }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!graphs_enabled(ctx, s)) {
+    ProfScope prof("epilogue phase B (mode formula)", 0.0, B * 64.0 * h * w * 36, s);
+    return launch_epilogue_phase_b(B, 8 * h, 8 * w, mode, expansion_factor, ev_multiplier, out_bhwc, stats, ws + pl.off_epi, s);
   }
-  if (exec != nullptr) HDRVAE_CUDA_OK(cudaGraphLaunch(exec, s));
+  float* img = reinterpret_cast<float*>(ws + pl.off_img);
+  hdrvae_ctx::GraphEntry key{1, B, h, w, mode, ctx->conv_impl, ctx->cta_group, expansion_factor, ev_multiplier, workspace, nullptr, 0};
+  HDRVAE_TRY(run_segment(ctx, key, s, [&]() {
+    return launch_epilogue_phase_b(B, 8 * h, 8 * w, mode, expansion_factor, ev_multiplier, img, nullptr, ws + pl.off_epi, s);
+  }));
   HDRVAE_CUDA_OK(cudaMemcpyAsync(out_bhwc, img, (size_t)B * 64 * pl.T * 3 * 4, cudaMemcpyDeviceToDevice, s));
   if (stats != nullptr) {
     HDRVAE_CUDA_OK(cudaMemcpyAsync(stats, epilogue_stats_dev_ptr(ws + pl.off_epi, B, 8 * h, 8 * w), sizeof(hdrvae_stats),
@@ -1124,6 +1128,25 @@ int hdrvae_decode(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, int
     HDRVAE_CUDA_OK(cudaStreamSynchronize(s));
   }
   return 0;
+}
+
+// One call = the two segments back to back (single GPU: nothing to exchange in between).
+int hdrvae_decode(hdrvae_ctx* ctx, const float* latent, int B, int h, int w, int mode, float expansion_factor,
+                  float ev_multiplier, float* out_bhwc, hdrvae_stats* stats, void* workspace, size_t ws_bytes,
+                  void* stream) {
+  HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
+  HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode: empty latent batch [%d,16,%d,%d]", B, h, w);
+  HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_decode: bad mode %d", mode);
+  HDRVAE_TRY(hdrvae_decode_begin(ctx, latent, B, h, w, workspace, ws_bytes, nullptr, stream));
+  return hdrvae_decode_finish(ctx, B, h, w, mode, expansion_factor, ev_multiplier, out_bhwc, stats, workspace, ws_bytes, stream);
+}
+
+// Merge `n` gathered hdrvae_raw_stats blocks (96 bytes each, rank order) into `dst`: MIN / MAX / SUM in a fixed order,
+// so every rank computes bit-identical batch-global statistics from ONE all-gather.
+int hdrvae_raw_stats_merge(const void* blocks, int n, void* dst, void* stream) {
+  HDRVAE_REQUIRE(blocks != nullptr && dst != nullptr && n >= 1, "hdrvae_raw_stats_merge: bad argument");
+  return launch_raw_stats_merge(reinterpret_cast<const hdrvae_raw_stats*>(blocks), n, reinterpret_cast<hdrvae_raw_stats*>(dst),
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hdrvae_rows_workspace_bytes(hdrvae_ctx* ctx, int h, int w, int world, size_t* bytes) {

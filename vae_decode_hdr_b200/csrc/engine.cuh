@@ -51,6 +51,7 @@ int launch_epilogue_phase_a_pre(const void* pre, int dtype, int B, int H, int W,
 int launch_split_hi_lo(const float* w, float* w8, int k, cudaStream_t s);
 int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
                             void* scratch, cudaStream_t s);
+int launch_raw_stats_merge(const hdrvae_raw_stats* blocks, int n, hdrvae_raw_stats* dst, cudaStream_t s);
 
 // ---- per-op device timing (diagnostics; enabled by hdrvae_profile_begin) -----------------------------
 struct ProfEntry { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
@@ -103,7 +104,7 @@ struct hdrvae_ctx {
   int conv_impl = HDRVAE_CONV_TCGEN05;
   int op_dtype = DT_F16;                          // 16-bit tensor-core operand type (HDRVAE_PRECISION_*)
   int cta_group = 0;                              // 0 = default (CTA pairs), 1 / 2 forced
-  struct GraphEntry { int B, h, w, mode, conv_impl, cta_group; float factor, ev; void* ws; cudaGraphExec_t exec; long long n_kernels; };
+  struct GraphEntry { int seg, B, h, w, mode, conv_impl, cta_group; float factor, ev; void* ws; cudaGraphExec_t exec; long long n_kernels; };
   std::vector<GraphEntry> graphs;                 // captured whole-decode CUDA graphs (hdrvae_decode)
   std::vector<GraphEntry> seen;                   // keys decoded once already (capture happens on the second use)
   bool use_graphs = true;

@@ -763,4 +763,32 @@ int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float e
   return 0;
 }
 
+// Multi-GPU batch sharding: merge n gathered raw-statistics blocks (rank order) into one, MIN / MAX / SUM in a fixed
+// order.  One thread per scalar; dst may be one of the inputs' storage only if it is not among `blocks`.
+__global__ void raw_stats_merge_kernel(const hdrvae_raw_stats* __restrict__ blocks, int n, hdrvae_raw_stats* __restrict__ dst) {
+  const int t = threadIdx.x;
+  if (t < HDRVAE_RAW_NMIN) {
+    float v = blocks[0].vmin[t];
+    for (int i = 1; i < n; ++i) v = fminf(v, blocks[i].vmin[t]);
+    dst->vmin[t] = v;
+  } else if (t < HDRVAE_RAW_NMIN + HDRVAE_RAW_NMAX) {
+    const int k = t - HDRVAE_RAW_NMIN;
+    float v = blocks[0].vmax[k];
+    for (int i = 1; i < n; ++i) v = fmaxf(v, blocks[i].vmax[k]);
+    dst->vmax[k] = v;
+  } else if (t < HDRVAE_RAW_NMIN + HDRVAE_RAW_NMAX + HDRVAE_RAW_NSUM) {
+    const int k = t - HDRVAE_RAW_NMIN - HDRVAE_RAW_NMAX;
+    double v = blocks[0].vsum[k];
+    for (int i = 1; i < n; ++i) v += blocks[i].vsum[k];
+    dst->vsum[k] = v;
+  }
+}
+
+int launch_raw_stats_merge(const hdrvae_raw_stats* blocks, int n, hdrvae_raw_stats* dst, cudaStream_t s) {
+  raw_stats_merge_kernel<<<1, 32, 0, s>>>(blocks, n, dst);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace hdrvae

@@ -109,6 +109,11 @@ class HdrVaeEngine:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._workspace
 
+    def free_workspace(self) -> None:
+        """Drop the persistent workspace (the next decode allocates it again; captured CUDA graphs stay valid only if
+        the allocator returns the same block, otherwise the library re-captures)."""
+        self._workspace = None
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -147,9 +152,9 @@ class HdrVaeEngine:
                 cur.wait_stream(run_on)
         return out, (st.as_dict() if want_stats else None)
 
-    def decode_begin(self, latent: torch.Tensor) -> torch.Tensor:
-        """Decoder + epilogue phase A.  Returns the device-resident raw statistics block as three
-        tensor VIEWS (vmin float32[4], vmax float32[4], vsum float64[8]) for the cross-rank all-reduce."""
+    def decode_begin_block(self, latent: torch.Tensor) -> torch.Tensor:
+        """Decoder + epilogue phase A.  Returns the device-resident raw statistics block (hdrvae_raw_stats, 96 bytes)
+        as a uint8 VIEW of the workspace, for the cross-rank exchange."""
         B, h, w = self._check_latent(latent)
         with torch.cuda.device(self.device):
             z = latent.to(device=self.device, dtype=torch.float32).contiguous()
@@ -159,12 +164,12 @@ class HdrVaeEngine:
                                                  C.byref(raw), self._stream()), "hdrvae_decode_begin")
             self._pending = (B, h, w)
             off = raw.value - ws.data_ptr()
-        nb = C.sizeof(N.HdrvaeRawStats)
-        blk = ws[off:off + nb]
-        vmin = blk[0:16].view(torch.float32)
-        vmax = blk[16:32].view(torch.float32)
-        vsum = blk[32:32 + 64].view(torch.float64)
-        return vmin, vmax, vsum
+        return ws[off:off + C.sizeof(N.HdrvaeRawStats)]
+
+    def decode_begin(self, latent: torch.Tensor):
+        """Same, returning the block as three tensor VIEWS (vmin float32[4], vmax float32[4], vsum float64[8])."""
+        blk = self.decode_begin_block(latent)
+        return blk[0:16].view(torch.float32), blk[16:32].view(torch.float32), blk[32:32 + 64].view(torch.float64)
 
     def decode_finish(self, hdr_mode: str = DEFAULT_MODE, ev_multiplier: float = 1.0, want_stats: bool = True):
         B, h, w = self._pending

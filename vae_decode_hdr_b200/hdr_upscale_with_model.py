@@ -13,7 +13,9 @@ the 4x RRDBNet (nf 64, gc 32) are rejected by the library with an error naming t
 from __future__ import annotations
 
 import logging
-from typing import Any, Dict, Tuple
+import os
+from collections import OrderedDict
+from typing import Any, Tuple
 
 import torch
 
@@ -29,7 +31,10 @@ def _model_filenames():
 
 
 class HDRUpscaleWithModel:
-    _engines: Dict[Any, HdrUpscalerEngine] = {}
+    # LRU of at most MAX_ENGINES engines keyed on the model FILE (resolved path, mtime, size) and the device: the node
+    # reloads the model through spandrel on every execution (:149-152), so object identity never repeats
+    _engines: "OrderedDict[Any, HdrUpscalerEngine]" = OrderedDict()
+    MAX_ENGINES = 2
     logger = logging.getLogger("HDRUpscaleWithModel")
 
     @classmethod
@@ -48,10 +53,14 @@ class HDRUpscaleWithModel:
     CATEGORY = "HDR/Upscale"
 
     # hdr_upscale_with_model.py:73-77 — unchanged: ComfyUI's model folder + spandrel's loader
-    def _load_model_internal(self, model_name):
+    @staticmethod
+    def _model_path(model_name) -> str:
         import folder_paths
+        return folder_paths.get_full_path("upscale_models", model_name)
+
+    def _load_model_internal(self, model_name):
         from spandrel import ModelLoader
-        return ModelLoader().load_from_file(folder_paths.get_full_path("upscale_models", model_name))
+        return ModelLoader().load_from_file(self._model_path(model_name))
 
     @staticmethod
     def _compute_device(image: torch.Tensor) -> torch.device:
@@ -61,27 +70,57 @@ class HDRUpscaleWithModel:
             raise RuntimeError("HDRUpscaleWithModel (B200) needs a CUDA device; there is no CPU fallback")
         return torch.device("cuda", torch.cuda.current_device())
 
-    @classmethod
-    def _engine_for(cls, descriptor: Any, device: torch.device) -> HdrUpscalerEngine:
-        model = descriptor.model
-        params = list(model.parameters())
-        key = (id(model), str(device), tuple((p.data_ptr(), p._version) for p in params[:4]))
-        eng = cls._engines.get(key)
-        if eng is None:
-            for k in [k for k in cls._engines if k[0] == id(model) and k[1] == str(device)]:
-                cls._engines.pop(k).close()
-            eng = HdrUpscalerEngine(model.state_dict(), device)
-            cls._engines[key] = eng
-        return eng
+    @staticmethod
+    def _file_key(path: str, device: torch.device):
+        try:
+            st = os.stat(path)
+            return (os.path.realpath(path), st.st_mtime_ns, st.st_size, str(device))
+        except (OSError, TypeError):
+            return (str(path), 0, 0, str(device))
 
-    def upscale(self, image, model_name, small_blur=False, local_fix=False, upscale_method="bislerp") -> Tuple[torch.Tensor]:
-        descriptor = self._load_model_internal(model_name)
+    @classmethod
+    def _engine_for(cls, key, load_descriptor, device: torch.device):
+        """-> (engine, scale, architecture name).  `load_descriptor()` is only called on a cache miss."""
+        hit = cls._engines.get(key)
+        if hit is not None:
+            cls._engines.move_to_end(key)
+            return hit
+        descriptor = load_descriptor()
         scale = getattr(descriptor, "scale", 4)
         if scale != 4:
-            raise RuntimeError(f"HDRUpscaleWithModel (B200) implements 4x RRDBNet models; {model_name!r} has scale {scale}")
+            raise RuntimeError(f"HDRUpscaleWithModel (B200) implements 4x RRDBNet models; this model has scale {scale}")
+        entry = (HdrUpscalerEngine(descriptor.model.state_dict(), device), scale, descriptor.architecture.name)
+        cls._engines[key] = entry
+        while len(cls._engines) > cls.MAX_ENGINES:
+            _, (old, _, _) = cls._engines.popitem(last=False)
+            old.close()
+        return entry
+
+    @classmethod
+    def release_memory(cls) -> None:
+        while cls._engines:
+            _, (eng, _, _) = cls._engines.popitem(last=False)
+            eng.close()
+
+    def upscale(self, image, model_name, small_blur=False, local_fix=False, upscale_method="bislerp") -> Tuple[torch.Tensor]:
         device = self._compute_device(image)
-        engine = self._engine_for(descriptor, device)
-        reversal = reversal_for_architecture(descriptor.architecture.name)     # :266-279
+        try:
+            key = self._file_key(self._model_path(model_name), device)
+        except ImportError:                 # no folder_paths (outside ComfyUI): nothing stable to key on, do not cache
+            key = None
+        if key is None:
+            descriptor = self._load_model_internal(model_name)
+            if getattr(descriptor, "scale", 4) != 4:
+                raise RuntimeError(f"HDRUpscaleWithModel (B200) implements 4x RRDBNet models; {model_name!r} has scale {descriptor.scale}")
+            engine = HdrUpscalerEngine(descriptor.model.state_dict(), device)
+            try:
+                out = engine.upscale(image, reversal_for_architecture(descriptor.architecture.name), bool(small_blur),
+                                     bool(local_fix), upscale_method)
+            finally:
+                engine.close()
+            return (out if image.device.type == "cuda" else out.to(image.device),)
+        engine, _scale, arch = self._engine_for(key, lambda: self._load_model_internal(model_name), device)
+        reversal = reversal_for_architecture(arch)                             # :266-279
         out = engine.upscale(image, reversal, bool(small_blur), bool(local_fix), upscale_method)
         if image.device.type != "cuda":
             out = out.to(image.device)

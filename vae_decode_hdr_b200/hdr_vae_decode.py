@@ -17,6 +17,9 @@ Differences, all documented in DESIGN.md:
 from __future__ import annotations
 
 import logging
+import os
+import weakref
+from collections import OrderedDict
 from typing import Any, Dict, Optional, Tuple
 
 import torch
@@ -34,14 +37,32 @@ def _decoder_of(vae: Any):
 
 
 def _weights_key(decoder) -> Tuple:
+    """Identity + in-place-modification fingerprint of EVERY parameter (storage address, version counter, size).  The
+    id() half is safe against reuse because an engine never outlives its decoder (weakref.finalize below)."""
     ps = list(decoder.parameters())
-    return (id(decoder), len(ps), tuple((p.data_ptr(), p._version) for p in ps[:4] + ps[-4:]))
+    return (id(decoder), len(ps), hash(tuple((p.data_ptr(), p._version, p.numel()) for p in ps)))
+
+
+# README.md:143-145 documents three inputs the code no longer has; the shipped example workflow still names them
+# (workflow_examples/HDR_VAE_DECODE.json:499-504).  They are accepted and ignored so API-format prompts that carry them load.
+LEGACY_IGNORED_INPUTS = ("max_range", "scale_factor", "enable_negatives")
+MAX_CACHED_ENGINES = 2
+
+
+def _in_comfyui() -> bool:
+    try:
+        import comfy.model_management  # noqa: F401
+        return True
+    except Exception:
+        return False
 
 
 class HDRVAEDecode:
     """HDR VAE Decode (B200-native).  Drop-in for the reference node class of the same name."""
 
-    _engines: Dict[Tuple, HdrVaeEngine] = {}
+    # LRU of at most MAX_CACHED_ENGINES engines (packed weights + CUDA graphs + workspace each); an engine is closed
+    # when it is evicted, when its weights change in place, or when its decoder is garbage-collected
+    _engines: "OrderedDict[Tuple, HdrVaeEngine]" = OrderedDict()
 
     def __init__(self):
         self.logger = logger
@@ -83,21 +104,54 @@ class HDRVAEDecode:
         return torch.device("cuda", torch.cuda.current_device())
 
     @classmethod
+    def _evict(cls, key) -> None:
+        eng = cls._engines.pop(key, None)
+        if eng is not None:
+            eng.close()
+
+    @classmethod
     def _engine_for(cls, vae: Any, device: torch.device) -> HdrVaeEngine:
         decoder = _decoder_of(vae)
         key = (_weights_key(decoder), str(device))
         eng = cls._engines.get(key)
         if eng is None:
             for k in [k for k in cls._engines if k[0][0] == id(decoder) and k[1] == str(device)]:
-                cls._engines.pop(k).close()           # weights changed in place: repack
+                cls._evict(k)                          # weights changed in place: repack
             eng = HdrVaeEngine(decoder.state_dict(), device)
-            cls._engines[key] = eng
+            cls._register(decoder, key, eng)
+        else:
+            cls._engines.move_to_end(key)
         return eng
+
+    @classmethod
+    def _register(cls, decoder, key, eng: HdrVaeEngine) -> None:
+        cls._engines[key] = eng
+        cls._engines.move_to_end(key)
+        try:
+            weakref.finalize(decoder, cls._evict, key)     # the engine dies with its decoder (no stale id() reuse)
+        except TypeError:
+            pass
+        while len(cls._engines) > MAX_CACHED_ENGINES:
+            cls._evict(next(iter(cls._engines)))
 
     @classmethod
     def adopt_engine(cls, vae: Any, device, engine: HdrVaeEngine) -> None:
         """Register an already-built engine for this vae's decoder weights (avoids a second repack)."""
-        cls._engines[(_weights_key(_decoder_of(vae)), str(torch.device(device)))] = engine
+        decoder = _decoder_of(vae)
+        cls._register(decoder, (_weights_key(decoder), str(torch.device(device))), engine)
+
+    @classmethod
+    def release_memory(cls, keep_weights: bool = True) -> None:
+        """Give the GPU memory back: drop every engine's workspace (and, with keep_weights=False, the engines).  ComfyUI's
+        model_management cannot see this memory; inside ComfyUI the workspace is released after every call unless
+        HDRVAE_KEEP_WORKSPACE=1."""
+        for k in list(cls._engines):
+            if keep_weights:
+                cls._engines[k].free_workspace()
+            else:
+                cls._evict(k)
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
 
     def simple_hdr_decode(
         self,
@@ -105,7 +159,14 @@ class HDRVAEDecode:
         vae: Any,
         hdr_mode: str = DEFAULT_MODE,
         conservative_ev_multiplier: float = 1.0,
+        **legacy_inputs,
     ) -> Tuple[torch.Tensor]:
+        unknown = [k for k in legacy_inputs if k not in LEGACY_IGNORED_INPUTS]
+        if unknown:
+            raise TypeError(f"simple_hdr_decode() got unexpected keyword argument(s) {unknown}")
+        if legacy_inputs:
+            self.logger.info("HDRVAEDecode: ignoring README-era inputs %s (the reference code has no such inputs, "
+                             "hdr_vae_decode.py:40-55)", sorted(legacy_inputs))
         latent = samples["samples"]                    # hdr_vae_decode.py:78
         device = self._compute_device(vae, latent)
         engine = self._engine_for(vae, device)
@@ -135,4 +196,8 @@ class HDRVAEDecode:
                 image = host
             else:
                 image = image.to(out_dev)
+        keep = os.environ.get("HDRVAE_KEEP_WORKSPACE")
+        if keep == "0" or (keep is None and _in_comfyui()):
+            engine.free_workspace()                    # hand the workspace back to the host application's allocator
+            torch.cuda.empty_cache()
         return (image,)

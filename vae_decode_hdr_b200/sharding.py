@@ -28,7 +28,9 @@ def shard_bounds(n_items: int, world_size: int) -> List[Tuple[int, int]]:
 
 
 def allreduce_raw_stats(vmin: torch.Tensor, vmax: torch.Tensor, vsum: torch.Tensor, group=None) -> None:
-    """In-place cross-rank reduction of an hdrvae_raw_stats block (include/hdrvae.h): MIN / MAX / SUM."""
+    """In-place cross-rank reduction of an hdrvae_raw_stats block (include/hdrvae.h): MIN / MAX / SUM, as three
+    all-reduces.  Used for host-side (CPU / gloo) blocks and by the row-tiling executor; the batch-sharded GPU path
+    uses :func:`exchange_raw_stats_block` (ONE all-gather + a fixed-order merge kernel)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     dist.all_reduce(vmin, op=dist.ReduceOp.MIN, group=group)
@@ -44,16 +46,102 @@ def merge_raw_stats(blocks: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Ten
     return vmin, vmax, vsum
 
 
+RAW_BLOCK_BYTES = 96
+_gather_bufs = {}
+
+
+def identity_raw_block(device) -> torch.Tensor:
+    """The neutral hdrvae_raw_stats block (+inf mins, -inf maxes, zero sums) a rank with an EMPTY shard contributes."""
+    blk = torch.zeros(RAW_BLOCK_BYTES, dtype=torch.uint8, device=device)
+    blk[0:16].view(torch.float32).fill_(float("inf"))
+    blk[16:32].view(torch.float32).fill_(float("-inf"))
+    return blk
+
+
+def exchange_raw_stats_block(block: torch.Tensor, lib=None, group=None) -> None:
+    """The ONE exchange step of batch sharding: all-gather every rank's 96-byte block (one NCCL collective), then merge
+    the gathered blocks in rank order into `block` (uint8[96] view of the workspace) with one kernel
+    (hdrvae_raw_stats_merge) — every rank ends with bit-identical statistics.  CPU tensors (gloo tests) are merged
+    with torch ops in the same order."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world = dist.get_world_size(group)
+    key = (block.device, world)
+    buf = _gather_bufs.get(key)
+    if buf is None:
+        buf = _gather_bufs[key] = torch.empty(world * RAW_BLOCK_BYTES, dtype=torch.uint8, device=block.device)
+    dist.all_gather_into_tensor(buf, block, group=group)
+    if block.is_cuda:
+        from . import _native as N
+        lib = lib or N.load_library()
+        N.check(lib.hdrvae_raw_stats_merge(buf.data_ptr(), world, block.data_ptr(),
+                                           torch.cuda.current_stream(block.device).cuda_stream), "hdrvae_raw_stats_merge")
+    else:
+        rows = buf.view(world, RAW_BLOCK_BYTES)
+        vmin = rows[:, 0:16].contiguous().view(torch.float32).view(world, 4).amin(0)
+        vmax = rows[:, 16:32].contiguous().view(torch.float32).view(world, 4).amax(0)
+        vs = rows[:, 32:96].contiguous().view(torch.float64).view(world, 8)
+        vsum = vs[0].clone()
+        for r in range(1, world):
+            vsum += vs[r]
+        block[0:16].view(torch.float32).copy_(vmin)
+        block[16:32].view(torch.float32).copy_(vmax)
+        block[32:96].view(torch.float64).copy_(vsum)
+
+
+_validated = set()
+
+
+def _validate_across_ranks(latent_local: torch.Tensor, hdr_mode: str, ev_multiplier: float, group) -> None:
+    """Once per (shape, mode, multiplier, group): every rank must decode the same latent shape (apart from the batch
+    count) with the same mode and multiplier, otherwise the batch-global statistics would be meaningless."""
+    sig = (tuple(latent_local.shape[1:]), str(hdr_mode).lower(), float(ev_multiplier))
+    key = (sig, id(group))
+    if key in _validated:
+        return
+    sigs = [None] * dist.get_world_size(group)
+    dist.all_gather_object(sigs, sig, group=group)
+    if any(s != sigs[0] for s in sigs):
+        raise ValueError(f"decode_batch_sharded: ranks disagree on latent shape / mode / multiplier: {sigs}")
+    _validated.add(key)
+
+
 def decode_batch_sharded(engine, latent_local: torch.Tensor, hdr_mode: str, ev_multiplier: float = 1.0, group=None,
                          want_stats: bool = True):
     """Decode this rank's slice of the batch with batch-global HDR statistics.
 
     engine: vae_decode_hdr_b200.engine.HdrVaeEngine on this rank's GPU.  Returns (image_local, stats)
     where the pre/post/conv/pre3 statistics and every derived scalar are those of the whole batch;
-    out_min/out_max/hdr_pixels describe the local slice."""
-    vmin, vmax, vsum = engine.decode_begin(latent_local)
-    allreduce_raw_stats(vmin, vmax, vsum, group)
-    return engine.decode_finish(hdr_mode, ev_multiplier, want_stats)
+    out_min/out_max/hdr_pixels describe the local slice.  A rank whose slice is EMPTY (batch smaller than the world
+    size, shard_bounds) skips the decoder, contributes the neutral block to the exchange and returns an empty image."""
+    distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+    if distributed:
+        _validate_across_ranks(latent_local, hdr_mode, ev_multiplier, group)
+    if latent_local.shape[0] == 0:
+        if latent_local.dim() != 4 or latent_local.shape[1] != 16:
+            raise ValueError(f"expected a Flux latent [B,16,h,w], got {tuple(latent_local.shape)}")
+        if distributed:
+            exchange_raw_stats_block(identity_raw_block(engine.device), engine.lib, group)
+        h, w = latent_local.shape[2:]
+        return torch.empty((0, 8 * h, 8 * w, 3), dtype=torch.float32, device=engine.device), None
+    # The library replays the two halves of the decode as CUDA graphs, which needs a non-default stream: hop to the
+    # engine's stream when the caller sits on the legacy default stream (the NCCL collective follows torch's current
+    # stream, so it is ordered between the two graphs either way).
+    cur = torch.cuda.current_stream(engine.device)
+    if cur.cuda_stream != 0:
+        block = engine.decode_begin_block(latent_local)
+        exchange_raw_stats_block(block, engine.lib, group)
+        return engine.decode_finish(hdr_mode, ev_multiplier, want_stats)
+    side = engine._side
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        latent_local.record_stream(side)
+        block = engine.decode_begin_block(latent_local)
+        exchange_raw_stats_block(block, engine.lib, group)
+        out, st = engine.decode_finish(hdr_mode, ev_multiplier, want_stats)
+    cur.wait_stream(side)
+    out.record_stream(cur)
+    return out, st
 
 
 # ------------------------------------------------------------------------------------------------ row tiling
