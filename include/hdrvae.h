@@ -53,17 +53,23 @@ enum { HDRVAE_F32 = 0, HDRVAE_BF16 = 1, HDRVAE_F16 = 2 };
  * copy scaled by 2^-4 from the producing conv's epilogue.
  *   F16  (default): fp16 operands (GroupNorm outputs, weights, attention operands are bounded) — meets the
  *                   1e-2 end-to-end tolerance;
- *   BF16          : bf16 operands, same speed, ~8x larger operand rounding (DESIGN.md "Precision"). */
-enum { HDRVAE_PRECISION_BF16 = 0, HDRVAE_PRECISION_F16 = 1 };
+ *   BF16          : bf16 operands, same speed, ~8x larger operand rounding (DESIGN.md "Precision");
+ *   HIGH          : every tensor-core operand as an fp16 hi + lo pair (x = hi + lo to ~2^-22): the K dimension of every
+ *                   GEMM-shaped op is the concatenation [hi | lo | hi] x [hi | hi | lo], i.e. 3 MMAs per product, fp32
+ *                   accumulation; features and conv_out in fp32.  Meets rel-L2 <= 1e-3 on the image (BASELINE.json's
+ *                   "TF32 path at <= 1e-3": tf32 itself has fp16's 10-bit mantissa and cannot) at ~3x the conv time.
+ *                   Single-GPU decode only (no row tiling). */
+enum { HDRVAE_PRECISION_BF16 = 0, HDRVAE_PRECISION_F16 = 1, HDRVAE_PRECISION_HIGH = 2 };
 
 /* conv implementation selector (debug/validation): the tcgen05 implicit-GEMM
  * kernel is the product path; the CUDA-core direct kernel exists to validate it
  * on the GPU and is never selected implicitly. */
 enum { HDRVAE_CONV_TCGEN05 = 0, HDRVAE_CONV_DIRECT = 1 };
 /* Upscaler: reversal hook kinds (hdr_upscale_with_model.py:79-107, :266-279) and the resampling methods of
- * local_fix that are implemented (:241; ComfyUI's own "bislerp" is rejected with an error). */
+ * local_fix (:241; the torch-expressible ones and ComfyUI's own "bislerp"). */
 enum { HDRVAE_REVERSAL_NONE = 0, HDRVAE_REVERSAL_ATANH = 1, HDRVAE_REVERSAL_LOGIT = 2 };
-enum { HDRVAE_UPSCALE_NEAREST_EXACT = 0, HDRVAE_UPSCALE_BILINEAR = 1, HDRVAE_UPSCALE_AREA = 2, HDRVAE_UPSCALE_BICUBIC = 3 };
+enum { HDRVAE_UPSCALE_NEAREST_EXACT = 0, HDRVAE_UPSCALE_BILINEAR = 1, HDRVAE_UPSCALE_AREA = 2, HDRVAE_UPSCALE_BICUBIC = 3,
+       HDRVAE_UPSCALE_BISLERP = 4 /* ComfyUI's spherical-linear resampler, the node's default (hdr_upscale_with_model.py:65) */ };
 
 /*
  * Scalars the reference computes with ~25 full-tensor reductions + host syncs
@@ -124,6 +130,8 @@ int hdrvae_destroy(hdrvae_ctx* ctx);
 int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl);
 /* HDRVAE_F16 or HDRVAE_BF16: element type of hdrvae_decode_features' output (set by hdrvae_load_weights). */
 int hdrvae_operand_dtype(hdrvae_ctx* ctx);
+/* element type of the tensor hdrvae_decode_features returns: the operand type, or HDRVAE_F32 in the HIGH precision mode */
+int hdrvae_features_dtype(hdrvae_ctx* ctx);
 /* tcgen05 cta_group of the GEMM/conv kernel: 0 = default (2: CTA pairs, M = 256 MMAs), 1 = single CTAs, 2 = pairs. */
 int hdrvae_set_cta_group(hdrvae_ctx* ctx, int cta_group);
 

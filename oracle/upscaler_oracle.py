@@ -172,11 +172,74 @@ def tiled_scale(samples, function, tile_x=64, tile_y=64, overlap=8, upscale_amou
     return output
 
 
+def bislerp(samples, width, height):
+    """ComfyUI's own "bislerp" resampler (comfy.utils.bislerp; third party, un-vendored, un-pinned — restated from the
+    published source, parity unpinned): separable (width pass, then height pass) SPHERICAL linear interpolation of
+    the per-pixel channel vectors between the two source pixels that bilinear interpolation (align_corners=False)
+    would blend, with the blend ratio of that bilinear interpolation.  For the single-channel luma the reference
+    feeds it (hdr_upscale_with_model.py:235-240) the vectors are scalars: same sign -> the FIRST pixel is returned
+    (dot = 1 > 1 - 1e-5), opposite signs -> plain linear interpolation, a zero -> the sine-weighted formula."""
+    def slerp(b1, b2, r):
+        c = b1.shape[-1]
+        b1_norms = torch.norm(b1, dim=-1, keepdim=True)
+        b2_norms = torch.norm(b2, dim=-1, keepdim=True)
+        b1_normalized = b1 / b1_norms
+        b2_normalized = b2 / b2_norms
+        b1_normalized[b1_norms.expand(-1, c) == 0.0] = 0.0
+        b2_normalized[b2_norms.expand(-1, c) == 0.0] = 0.0
+        dot = (b1_normalized * b2_normalized).sum(1)
+        omega = torch.acos(dot)
+        so = torch.sin(omega)
+        res = (torch.sin((1.0 - r.squeeze(1)) * omega) / so).unsqueeze(1) * b1_normalized + \
+              (torch.sin(r.squeeze(1) * omega) / so).unsqueeze(1) * b2_normalized
+        res *= (b1_norms * (1.0 - r) + b2_norms * r).expand(-1, c)
+        res[dot > 1 - 1e-5] = b1[dot > 1 - 1e-5]
+        res[dot < 1e-5 - 1] = (b1 * (1.0 - r) + b2 * r)[dot < 1e-5 - 1]
+        return res
+
+    def generate_bilinear_data(length_old, length_new, device):
+        coords_1 = torch.arange(length_old, dtype=torch.float32, device=device).reshape((1, 1, 1, -1))
+        coords_1 = F.interpolate(coords_1, size=(1, length_new), mode="bilinear")
+        ratios = coords_1 - coords_1.floor()
+        coords_1 = coords_1.to(torch.int64)
+        coords_2 = torch.arange(length_old, dtype=torch.float32, device=device).reshape((1, 1, 1, -1)) + 1
+        coords_2[:, :, :, -1] -= 1
+        coords_2 = F.interpolate(coords_2, size=(1, length_new), mode="bilinear")
+        coords_2 = coords_2.to(torch.int64)
+        return ratios, coords_1, coords_2
+
+    orig_dtype = samples.dtype
+    samples = samples.float()
+    n, c, h, w = samples.shape
+    h_new, w_new = (height, width)
+
+    ratios, coords_1, coords_2 = generate_bilinear_data(w, w_new, samples.device)
+    coords_1 = coords_1.expand((n, c, h, -1))
+    coords_2 = coords_2.expand((n, c, h, -1))
+    ratios = ratios.expand((n, 1, h, -1))
+    pass_1 = samples.gather(-1, coords_1).movedim(1, -1).reshape((-1, c))
+    pass_2 = samples.gather(-1, coords_2).movedim(1, -1).reshape((-1, c))
+    ratios = ratios.movedim(1, -1).reshape((-1, 1))
+    result = slerp(pass_1, pass_2, ratios)
+    result = result.reshape(n, h, w_new, c).movedim(-1, 1)
+
+    ratios, coords_1, coords_2 = generate_bilinear_data(h, h_new, samples.device)
+    coords_1 = coords_1.reshape((1, 1, -1, 1)).expand((n, c, -1, w_new))
+    coords_2 = coords_2.reshape((1, 1, -1, 1)).expand((n, c, -1, w_new))
+    ratios = ratios.reshape((1, 1, -1, 1)).expand((n, 1, -1, w_new))
+    pass_1 = result.gather(-2, coords_1).movedim(1, -1).reshape((-1, c))
+    pass_2 = result.gather(-2, coords_2).movedim(1, -1).reshape((-1, c))
+    ratios = ratios.movedim(1, -1).reshape((-1, 1))
+    result = slerp(pass_1, pass_2, ratios)
+    result = result.reshape(n, h_new, w_new, c).movedim(-1, 1)
+    return result.to(orig_dtype)
+
+
 def common_upscale(samples, width, height, upscale_method, crop):
-    """comfy.utils.common_upscale for the methods torch offers (crop "disabled"/False); "bislerp" (ComfyUI's own
-    slerp resampler) is not restated."""
+    """comfy.utils.common_upscale (crop "disabled"/False): torch's interpolate for the methods torch offers, ComfyUI's
+    own bislerp otherwise."""
     if upscale_method == "bislerp":
-        raise NotImplementedError("bislerp is ComfyUI-specific and not restated")
+        return bislerp(samples, width, height)
     return F.interpolate(samples, size=(height, width), mode=upscale_method)
 
 

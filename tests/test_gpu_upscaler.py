@@ -102,7 +102,8 @@ class _GpuModel(torch.nn.Module):
 @pytest.mark.parametrize("B,H,W,blur,fix,method", [(1, 24, 20, False, False, "bilinear"), (1, 530, 24, False, False, "bilinear"),
                                                    (1, 40, 600, True, True, "nearest-exact"), (2, 20, 28, True, True, "bilinear"),
                                                    (1, 520, 520, False, True, "bilinear"), (1, 36, 44, False, True, "area"),
-                                                   (2, 30, 26, False, True, "bicubic")])
+                                                   (2, 30, 26, False, True, "bicubic"), (1, 36, 44, False, True, "bislerp"),
+                                                   (2, 20, 28, True, True, "bislerp")])
 def test_tiling_blend_and_recombination_are_exact_given_the_model(nets, B, H, W, blur, fix, method):
     net, eng = nets[(1, 1.0)] if max(H, W) > 512 else nets[(2, 40.0)]
     img = make_image(B, H, W, 31, 3.0)
@@ -148,8 +149,12 @@ def test_node_surface_and_call(nets, golden_dir, monkeypatch):
     (out,) = node.upscale(torch.from_numpy(g["image"]), "fake.pth", False, False, "bislerp")
     assert out.device.type == "cpu" and out.dtype == torch.float32 and out.shape == g["output"].shape
     assert _rel(out, torch.from_numpy(g["output"])) < 1e-2
-    with pytest.raises(NotImplementedError):
-        node.upscale(torch.from_numpy(g["image"]), "fake.pth", False, True, "bislerp")
+    # the node's own defaults with local_fix ticked: bislerp is implemented, an unknown method is a ValueError
+    (fixed,) = node.upscale(torch.from_numpy(g["image"]), "fake.pth", False, True, "bislerp")
+    ref_fixed = uo.upscale(torch.from_numpy(g["image"]), uo.FakeDescriptor(net, 4, "ESRGAN"), False, True, "bislerp")
+    assert _rel(fixed, ref_fixed) < 1e-2, _rel(fixed, ref_fixed)
+    with pytest.raises(ValueError):
+        node.upscale(torch.from_numpy(g["image"]), "fake.pth", False, True, "lanczos")
 
 
 def test_c5_pipeline_decode_upscale_pack(nets):

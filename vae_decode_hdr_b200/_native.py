@@ -18,7 +18,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 MODE_CONSERVATIVE, MODE_EXPOSURE, MODE_ADAPTIVE_RECOVERY, MODE_MATHEMATICAL_RECOVERY = range(4)
 NORM_NONE, NORM_SIGMOID, NORM_TANH = range(3)
 F32, BF16, F16 = range(3)
-PRECISION_BF16, PRECISION_F16 = 0, 1
+PRECISION_BF16, PRECISION_F16, PRECISION_HIGH = 0, 1, 2
 CONV_TCGEN05, CONV_DIRECT = 0, 1
 RAW_NMIN, RAW_NMAX, RAW_NSUM = 4, 4, 8
 
@@ -84,6 +84,7 @@ SIGNATURES = {
     "hdrvae_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _vp, C.POINTER(HdrvaeStats),
                              _vp, _vp, _vp, _vp, _sz, _vp]),
     "hdrvae_operand_dtype": (_i, [_vp]),
+    "hdrvae_features_dtype": (_i, [_vp]),
     "hdrvae_set_cta_group": (_i, [_vp, _i]),
     "hdrvae_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp,
                            C.POINTER(_i), _i, _vp]),
@@ -102,7 +103,7 @@ SIGNATURES = {
     "hdrvae_upscale": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
 }
 REVERSAL_NONE, REVERSAL_ATANH, REVERSAL_LOGIT = 0, 1, 2
-UPSCALE_METHODS = {"nearest-exact": 0, "bilinear": 1, "area": 2, "bicubic": 3}
+UPSCALE_METHODS = {"nearest-exact": 0, "bilinear": 1, "area": 2, "bicubic": 3, "bislerp": 4}
 
 _lib = None
 

@@ -72,8 +72,10 @@ static void phase_taps(int py, int px, int* dy, int* dx, int* mask) {
 }
 
 int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int cin, int ks, bool upsample,
-                     float scale, int w_dtype, PackedConv* pc, cudaStream_t s) {
+                     float scale, int w_dtype, PackedConv* pc, cudaStream_t s, bool split3) {
   pc->cin = cin; pc->cout = cout; pc->ks = ks; pc->upsample = upsample; pc->w_dtype = w_dtype;
+  pc->kmul = split3 ? 3 : 1;
+  HDRVAE_REQUIRE(!split3 || w_dtype == DT_F16, "pack_conv: the hi|hi|lo operand is fp16");
   pc->cin_pad = (cin + 63) / 64 * 64;
   pc->cout_pad = (cout + 31) / 32 * 32;
   const size_t eb = dt_bytes(w_dtype);
@@ -86,15 +88,15 @@ int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int 
     const int ntaps = ks * ks;
     int mask[9];
     for (int t = 0; t < ntaps; ++t) mask[t] = 1 << t;
-    HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * ntaps * pc->cin_pad * eb, &pc->w[0]));
-    HDRVAE_TRY(launch_pack_weight(w, pc->w[0], w_dtype, cout, cin, ks, ntaps, pc->cin_pad, mask, scale, s));
+    HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * ntaps * pc->cin_pad * pc->kmul * eb, &pc->w[0]));
+    HDRVAE_TRY(launch_pack_weight(w, pc->w[0], w_dtype, cout, cin, ks, ntaps, pc->cin_pad, mask, scale, s, split3 ? 1 : 0));
   } else {
     HDRVAE_REQUIRE(ks == 3, "upsample folding needs a 3x3 kernel");
     for (int ph = 0; ph < 4; ++ph) {
       int dy[4], dx[4], mask[4];
       phase_taps(ph >> 1, ph & 1, dy, dx, mask);
-      HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * 4 * pc->cin_pad * eb, &pc->w[ph]));
-      HDRVAE_TRY(launch_pack_weight(w, pc->w[ph], w_dtype, cout, cin, 3, 4, pc->cin_pad, mask, scale, s));
+      HDRVAE_TRY(dev_alloc(ctx, (size_t)cout * 4 * pc->cin_pad * pc->kmul * eb, &pc->w[ph]));
+      HDRVAE_TRY(launch_pack_weight(w, pc->w[ph], w_dtype, cout, cin, 3, 4, pc->cin_pad, mask, scale, s, split3 ? 1 : 0));
     }
   }
   return 0;
@@ -111,24 +113,33 @@ static int tiles_for(int H, int W) {
 
 int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int H, int W, int impl,
                     cudaStream_t s) {
+  if (pc.kmul == 3 && io.y2 != nullptr) {
+    // "precision high": the scaled operand copy of the output is the hi|lo|hi split of the fp32 tensor (separate pass)
+    HDRVAE_REQUIRE(io.y_dtype == DT_F32 && io.y_channels == 0 && io.y_pad == 0, "run_conv: split operand copy needs a dense fp32 output");
+    ConvIO c = io; c.y2 = nullptr;
+    HDRVAE_TRY(run_conv(ctx, pc, c, B, H, W, impl, s));
+    const long long px = (long long)B * H * W * (pc.upsample ? 4 : 1);
+    return launch_split3(reinterpret_cast<const float*>(io.y), pc.cout, io.y2, 3 * pc.cout, px, pc.cout, io.y2_scale, 0, s);
+  }
+  const int kpad = pc.cin_pad * pc.kmul;            // K per tap as the GEMM sees it
   char pname[96];
   snprintf(pname, sizeof pname, "conv%dx%d%s%s %d->%d @%dx%dx%d", pc.ks, pc.ks, pc.upsample ? "up" : "",
            pc.w_dtype == DT_F32 ? " tf32" : "", pc.cin, pc.cout, B, H, W);
   const double out_px = (double)B * H * W * (pc.upsample ? 4 : 1);
   ProfScope prof(pname, 2.0 * out_px * pc.cout * pc.cin * pc.ks * pc.ks,
-                 (double)B * H * W * pc.cin_pad * dt_bytes(pc.w_dtype) +
+                 (double)B * H * W * kpad * dt_bytes(pc.w_dtype) +
                      out_px * pc.cout * (dt_bytes(io.y_dtype) + (io.residual ? dt_bytes(io.res_dtype) : 0)), s);
   GemmParams p;
   memset(&p, 0, sizeof p);
   p.a = io.x;
   p.ab_dtype = pc.w_dtype;
-  const int xch = io.x_channels > 0 ? io.x_channels : pc.cin_pad;
+  const int xch = io.x_channels > 0 ? io.x_channels : kpad;
   p.a_px_stride = xch; p.a_row_stride = (long long)W * xch;
   p.a_img_stride = (long long)(H + 2 * io.x_pad) * W * xch;
   p.a_k_valid = io.x_channels > 0 ? pc.cin : 0;
   p.y_pad = io.x_pad;
   p.n_img = B; p.H = H; p.W = W;
-  p.k_per_tap = pc.cin_pad;
+  p.k_per_tap = kpad;
   p.n_cols = pc.cout_pad;
   p.n_store = io.n_store > 0 ? io.n_store : (pc.cout_pad != pc.cout ? (pc.cout + 3) / 4 * 4 : 0);
   p.res_scale = io.res_scale; p.lrelu = io.lrelu;
@@ -187,7 +198,7 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
     }
     p.stats_chunk0 = ph * tiles;
     p.b = pc.w[ph];
-    p.b_row_stride = (long long)p.ntaps * pc.cin_pad;
+    p.b_row_stride = (long long)p.ntaps * kpad;
     p.b_rows = pc.cout;
     if (impl == HDRVAE_CONV_DIRECT) {
       HDRVAE_REQUIRE(io.stats == nullptr, "the validation conv kernel does not emit GroupNorm statistics");
@@ -238,13 +249,14 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
-  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_s, off_p, off_inv, off_part, off_epi, off_lat_in, off_img, total;
+  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_f32, off_s, off_p, off_inv, off_part, off_epi, off_lat_in, off_img, total;
 };
 static constexpr long long kScoreBudgetElems = 1024ll << 20;  // fp32 score chunk <= 4 GiB (K and V^T are re-read once per chunk)
 static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
 
-static Plan make_plan(int B, int h, int w, bool attn_only = false) {
+static Plan make_plan(int B, int h, int w, bool attn_only = false, bool high = false) {
   Plan pl;
+  const size_t km = high ? 3 : 1;                              // hi|lo|hi operands are 3x as wide
   pl.B = B; pl.h = h; pl.w = w;
   pl.T = h * w;
   pl.Tp = (pl.T + 63) / 64 * 64;
@@ -260,18 +272,19 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
   const size_t widest = attn_only ? 0 : (size_t)B * pl.T * 64 * 256;   // elements of [B, 8h, 8w, 256]
-  pl.off_lat = take(attn_only ? 0 : (size_t)B * pl.T * 64 * 2);
+  pl.off_lat = take(attn_only ? 0 : (size_t)B * pl.T * 64 * 2 * km);
   pl.off_x = take(widest * 4);       // residual stream, fp32
   pl.off_h = take(widest * 4);       // conv1 / shortcut / upsample outputs, fp32
-  pl.off_t = take(widest * 2);       // GroupNorm outputs: 16-bit tensor-core operands
-  pl.off_x16 = take(widest / 2);     // scaled 16-bit copy of x feeding an upsample conv (<= [B,4h,4w,256] elements)
-  pl.off_x16b = take(widest * 2);    // scaled 16-bit copy of an upsample output feeding a nin_shortcut (<= [B,8h,8w,256])
+  pl.off_t = take(widest * 2 * km);  // GroupNorm outputs: 16-bit tensor-core operands
+  pl.off_x16 = take(widest / 2 * km);  // scaled 16-bit copy of x feeding an upsample conv (<= [B,4h,4w,256] elements)
+  pl.off_x16b = take(widest * 2 * km); // scaled 16-bit copy of an upsample output feeding a nin_shortcut (<= [B,8h,8w,256])
   pl.off_gn = take(attn_only ? 0 : gn_scratch_bytes(B, 512, pl.gn_chunks));
-  pl.off_qk = take((size_t)B * pl.Tp * 1024 * 2);
-  pl.off_vt = take((size_t)B * 512 * pl.Tp * 2);
-  pl.off_o = take((size_t)B * pl.T * 512 * 2);
+  pl.off_qk = take((size_t)B * pl.Tp * 1024 * 2 * km);
+  pl.off_vt = take((size_t)B * 512 * pl.Tp * 2 * km);
+  pl.off_o = take((size_t)B * pl.T * 512 * 2 * km);
+  pl.off_f32 = take(high ? (size_t)pl.Tp * 1536 * 4 + (size_t)B * 64 * pl.T * 4 : 0);   // high: fp32 q|k, v^T / o of one image; fp32 NHWC latent
   pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
-  pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
+  pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2 * km);
   pl.off_inv = take((size_t)pl.s_rows * 4 * 2);          // 1 / row sum, and -row max of the two-pass soft-max
   pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials of the PV GEMM
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
@@ -299,14 +312,14 @@ struct DecState {
 };
 
 static int run_gn(hdrvae_ctx* ctx, const void* x, int x_dtype, void* y, int B, int HW, const NormW& nw, bool silu,
-                  DecState* st, cudaStream_t s) {
+                  DecState* st, cudaStream_t s, int y_dtype = -1) {
   char pname[64];
   snprintf(pname, sizeof pname, "groupnorm%s C=%d @%dx%d", silu ? "+silu" : "", nw.C, B, HW);
   ProfScope prof(pname, 0.0, (double)B * HW * nw.C * (dt_bytes(x_dtype) * (st->pending > 0 ? 1 : 2) + 2.0), s);
   const int partials = st->pending;
   st->pending = 0;
-  return launch_groupnorm(x, x_dtype, y, ctx->op_dtype, B, HW, nw.C, nw.gamma, nw.beta, silu, st->gn, st->gn_chunks,
-                          partials, s);
+  return launch_groupnorm(x, x_dtype, y, y_dtype >= 0 ? y_dtype : (ctx->high ? DT_F16X3 : ctx->op_dtype), B, HW, nw.C, nw.gamma,
+                          nw.beta, silu, st->gn, st->gn_chunks, partials, s);
 }
 
 static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
@@ -324,7 +337,7 @@ static int gn_before_conv(hdrvae_ctx* ctx, const float* x, const NormW& nw, cons
     const char* e = getenv("HDRVAE_FUSE_GN"); fuse = (e && atoi(e) != 0) ? 1 : 0;
     const char* m = getenv("HDRVAE_FUSE_GN_MINN"); if (m) fuse_min_n = atoi(m);
   }
-  const bool fusable = fuse && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && st->pending > 0 &&
+  const bool fusable = fuse && !ctx->high && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && st->pending > 0 &&
                        pc.cout_pad >= fuse_min_n && io->y2 == nullptr && conv_takes_slab(pc, *io, H, W, ctx->conv_impl) &&
                        !(pc.cout_pad == 128 && io->residual != nullptr);
   if (!fusable) {
@@ -371,12 +384,30 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
   return 0;
 }
 
+// HDRVAE_ATTN_FUSED=0 selects the GEMM-level form (QK^T twice with the soft-max fused into the GEMM epilogues, P through
+// HBM, split-K PV + reduce) that the fused kernel replaced; the CUDA-core validation build always takes it.
+static bool attention_fused_enabled(hdrvae_ctx* ctx) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HDRVAE_ATTN_FUSED"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on && ctx->conv_impl == HDRVAE_CONV_TCGEN05;
+}
+static int attention_cta_group(hdrvae_ctx* ctx) {
+  static int cg = -1;
+  if (cg < 0) { const char* e = getenv("HDRVAE_ATTN_CG"); cg = e ? atoi(e) : 0; }
+  if (cg == 1 || cg == 2) return cg;
+  return ctx->cta_group == 1 ? 1 : 2;
+}
+
 // Attention of n_q query rows (q: 16-bit, row stride 1024) against T keys (k: row stride 1024, rows >= T zero up to
 // Tp) and v^T [512][Tp]; o: 16-bit [n_q][512].  Scratch (S, P, 1/sum, split-K partials) comes from the plan.
 static int attention_rows(hdrvae_ctx* ctx, uint8_t* ws, size_t off_s, size_t off_p, size_t off_inv, size_t off_part,
                           int s_rows, const uint16_t* q, int n_q, const uint16_t* k, const uint16_t* v, int T, int Tp,
                           uint16_t* o, float qk_alpha, cudaStream_t s) {
   const int impl = ctx->conv_impl, dt = ctx->op_dtype;
+  if (attention_fused_enabled(ctx)) {
+    // ONE launch: flash-style kernel, scores and probabilities never leave the SM (attention.cu)
+    return launch_attention_fused(q, 1024, 0, n_q, k, 1024, 0, Tp, v, Tp, 0, T, o, 0, 1, dt, qk_alpha, attention_cta_group(ctx), s);
+  }
   float* S = reinterpret_cast<float*>(ws + off_s);
   uint16_t* P = reinterpret_cast<uint16_t*>(ws + off_p);
   float* inv = reinterpret_cast<float*>(ws + off_inv);
@@ -458,6 +489,8 @@ static int run_phase_a(hdrvae_ctx* ctx, const void* feat, int B, int H, int W, i
   static int tc_on = -1;
   if (tc_on < 0) { const char* e = getenv("HDRVAE_TC_CONVOUT"); tc_on = (e && atoi(e) == 0) ? 0 : 1; }
   const long long img_stride = (long long)(H + 2 * pad) * W * 128;
+  if (ctx->high)     // fp32 features: conv_out in fp32 on the CUDA cores (the 1e-5 parity kernel)
+    return launch_epilogue_phase_a(feat, DT_F32, B, H, W, ctx->conv_out_w, ctx->conv_out_b, nullptr, epi, s, 0, img_stride);
   const uint16_t* interior = reinterpret_cast<const uint16_t*>(feat) + (size_t)pad * W * 128;
   if (tc_on && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && ctx->conv_out_tc.w[0] != nullptr) {
     ConvIO io; io.x = feat; io.x_pad = pad; io.y = conv8; io.y_dtype = DT_F32; io.y_channels = 8; io.n_store = 8;
@@ -467,9 +500,49 @@ static int run_phase_a(hdrvae_ctx* ctx, const void* feat, int B, int H, int W, i
   return launch_epilogue_phase_a(interior, ctx->op_dtype, B, H, W, ctx->conv_out_w, ctx->conv_out_b, nullptr, epi, s, pad, img_stride);
 }
 
+// "precision high" attention of ONE image: every GEMM on K-concatenated fp16 hi / lo operands (activations [hi|lo|hi],
+// weight-like operands [hi|hi|lo]), fp32 scores and outputs.  t3: GroupNorm output [T][1536]; o3: [T][1536] operand of
+// proj_out.  GEMM-level form (the fused kernel keeps a 16-bit Q tile resident and has no room for a second copy).
+static int run_attention_high(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const uint16_t* t3, uint16_t* o3, cudaStream_t s) {
+  const int impl = ctx->conv_impl, T = pl.T, Tp = pl.Tp;
+  float* f32 = reinterpret_cast<float*>(ws + pl.off_f32);                 // [Tp][1024] q|k, then [512][Tp] v^T, then [T][512] o
+  uint16_t* q3 = reinterpret_cast<uint16_t*>(ws + pl.off_qk);            // [Tp][1536] hi|lo|hi
+  uint16_t* k3 = q3 + (size_t)Tp * 1536;                                 // [Tp][1536] hi|hi|lo
+  uint16_t* vt3 = reinterpret_cast<uint16_t*>(ws + pl.off_vt);           // [512][3 Tp] hi|hi|lo along the keys
+  float* S = reinterpret_cast<float*>(ws + pl.off_s);
+  uint16_t* P3 = reinterpret_cast<uint16_t*>(ws + pl.off_p);             // [rows][3 Tp] hi|lo|hi
+  float* inv = reinterpret_cast<float*>(ws + pl.off_inv);
+  if (Tp != T) HDRVAE_CUDA_OK(cudaMemsetAsync(f32, 0, (size_t)Tp * 1024 * 4, s));
+  HDRVAE_TRY(run_gemm(ctx, DT_F16, t3, 1536, T, 1536, ctx->qk.w[0], 1536, 1024, 1024, f32, 1024, DT_F32, ctx->qk.bias, false, 1.0f,
+                      nullptr, impl, s));
+  HDRVAE_TRY(launch_split3(f32, 1024, q3, 1536, Tp, 512, 1.f, 0, s));
+  HDRVAE_TRY(launch_split3(f32 + 512, 1024, k3, 1536, Tp, 512, 1.f, 1, s));
+  // v^T = Wv t^T + bv: the weights are the A operand here ([hi|hi|lo] against the activations' [hi|lo|hi]: same 3 terms)
+  HDRVAE_TRY(run_gemm(ctx, DT_F16, ctx->vproj.w[0], 1536, 512, 1536, t3, 1536, T, Tp, f32, Tp, DT_F32, ctx->vproj.bias, true, 1.0f,
+                      nullptr, impl, s));
+  HDRVAE_TRY(launch_split3(f32, Tp, vt3, 3ll * Tp, 512, Tp, 1.f, 1, s));
+  float* of = f32;                                                       // [T][512], v^T fp32 is dead after the split
+  for (int r0 = 0; r0 < T; r0 += pl.s_rows) {
+    const int rows = std::min(pl.s_rows, T - r0);
+    HDRVAE_TRY(run_gemm(ctx, DT_F16, q3 + (size_t)r0 * 1536, 1536, rows, 1536, k3, 1536, Tp, Tp, S, Tp, DT_F32, nullptr, false, 1.0f,
+                        nullptr, impl, s));
+    HDRVAE_TRY(launch_softmax_rows(S, P3, DT_F16X3, inv, rows, T, Tp, Tp, 3ll * Tp, s));
+    HDRVAE_TRY(run_gemm(ctx, DT_F16, P3, 3ll * Tp, rows, 3 * Tp, vt3, 3ll * Tp, 512, 512, of + (size_t)r0 * 512, 512, DT_F32, nullptr,
+                        false, 1.0f, inv, impl, s));
+  }
+  return launch_split3(of, 512, o3, 1536, T, 512, 1.f, 0, s);
+}
+
 static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const void* qk /*[B][Tp][1024]*/,
                               const void* vt /*[B][512][Tp]*/, void* o /*[B][T][512]*/, float qk_alpha,
                               cudaStream_t s) {
+  if (attention_fused_enabled(ctx)) {
+    // all images in one launch
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(qk);
+    return launch_attention_fused(q, 1024, (long long)pl.Tp * 1024, pl.T, q + 512, 1024, (long long)pl.Tp * 1024, pl.Tp, vt, pl.Tp,
+                                  (long long)512 * pl.Tp, pl.T, o, (long long)pl.T * 512, pl.B, ctx->op_dtype, qk_alpha,
+                                  attention_cta_group(ctx), s);
+  }
   for (int b = 0; b < pl.B; ++b) {
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk) + (size_t)b * pl.Tp * 1024;
     HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.s_rows, q, pl.T, q + 512,
@@ -495,7 +568,13 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
   st.gn_chunks = pl.gn_chunks;
   st.pending = 0;
 
-  HDRVAE_TRY(launch_latent_to_nhwc(latent, lat, dt, B, 16, H * W, 64, s));
+  if (ctx->high) {
+    float* latf = reinterpret_cast<float*>(ws + pl.off_f32) + (size_t)pl.Tp * 1536;
+    HDRVAE_TRY(launch_latent_to_nhwc(latent, latf, DT_F32, B, 16, H * W, 64, s));
+    HDRVAE_TRY(launch_split3(latf, 64, lat, 192, (long long)B * H * W, 64, 1.f, 0, s));
+  } else {
+    HDRVAE_TRY(launch_latent_to_nhwc(latent, lat, dt, B, 16, H * W, 64, s));
+  }
   {
     ConvIO io; io.x = lat; io.y = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
     HDRVAE_TRY(run_conv(ctx, ctx->conv_in, io, B, H, W, impl, s));
@@ -507,6 +586,12 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
     void* vt = ws + pl.off_vt;
     void* o = ws + pl.off_o;
     HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->attn_norm, false, &st, s));
+    if (ctx->high) {
+      ProfScope prof("attention (high precision, GEMM form)", 4.0 * B * (double)pl.T * pl.T * 512 * 3, 0.0, s);
+      for (int b = 0; b < B; ++b)
+        HDRVAE_TRY(run_attention_high(ctx, pl, ws, reinterpret_cast<const uint16_t*>(st.t) + (size_t)b * pl.T * 1536,
+                                      reinterpret_cast<uint16_t*>(o) + (size_t)b * pl.T * 1536, s));
+    } else {
     if (pl.Tp != pl.T) HDRVAE_CUDA_OK(cudaMemsetAsync(qk, 0, (size_t)B * pl.Tp * 1024 * 2, s));
     {
       ProfScope pq("attention q|k and v^T projections", 2.0 * B * (double)pl.T * 512 * 1536, 0.0, s);
@@ -526,6 +611,7 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
       ProfScope prof("attention core (QK^T, softmax, PV)", 4.0 * B * (double)pl.T * pl.T * 512, 10.0 * B * (double)pl.T * pl.Tp, s);
       HDRVAE_TRY(run_attention_core(ctx, pl, ws, qk, vt, o, 1.0f, s));
     }
+    }
     ConvIO io; io.x = o; io.y = st.x; io.residual = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
     HDRVAE_TRY(run_conv(ctx, ctx->proj_out, io, B, H, W, impl, s));
   }
@@ -543,7 +629,8 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
       H *= 2; W *= 2;
     }
   }
-  HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->norm_out, true, &st, s));
+  // the tensor the reference's hook captures: 16-bit operand of conv_out, or fp32 in the high-precision mode
+  HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->norm_out, true, &st, s, ctx->high ? DT_F32 : -1));
   *features = st.t;
   return 0;
 }
@@ -900,6 +987,7 @@ int hdrvae_set_conv_impl(hdrvae_ctx* ctx, int impl) {
 }
 
 int hdrvae_operand_dtype(hdrvae_ctx* ctx) { return ctx ? ctx->op_dtype : -1; }
+int hdrvae_features_dtype(hdrvae_ctx* ctx) { return ctx ? (ctx->high ? DT_F32 : ctx->op_dtype) : -1; }
 
 int hdrvae_set_cta_group(hdrvae_ctx* ctx, int cta_group) {
   HDRVAE_REQUIRE(ctx != nullptr && cta_group >= 0 && cta_group <= 2, "bad cta_group");
@@ -909,11 +997,13 @@ int hdrvae_set_cta_group(hdrvae_ctx* ctx, int cta_group) {
 
 int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n, int precision) {
   HDRVAE_REQUIRE(ctx != nullptr && descs != nullptr, "hdrvae_load_weights: null argument");
-  HDRVAE_REQUIRE(precision == HDRVAE_PRECISION_BF16 || precision == HDRVAE_PRECISION_F16,
+  HDRVAE_REQUIRE(precision == HDRVAE_PRECISION_BF16 || precision == HDRVAE_PRECISION_F16 || precision == HDRVAE_PRECISION_HIGH,
                  "hdrvae_load_weights: unsupported precision %d", precision);
   HDRVAE_REQUIRE(!ctx->loaded, "hdrvae_load_weights: context already holds weights (create a new one)");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->op_dtype = precision == HDRVAE_PRECISION_BF16 ? DT_BF16 : DT_F16;
+  ctx->high = precision == HDRVAE_PRECISION_HIGH;
+  const bool high = ctx->high;
   const int op = ctx->op_dtype;
   cudaStream_t s = nullptr;
   std::vector<void*> staging;
@@ -945,7 +1035,7 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
   };
   auto conv = [&](const std::string& k, int cout, int cin, int ks, bool up, int w_dtype, PackedConv* pc) -> int {
     HDRVAE_TRY(need_conv(k, cout, cin, ks));
-    return pack_conv(ctx, W(k + ".weight"), W(k + ".bias"), cout, cin, ks, up, 1.f, w_dtype, pc, s);
+    return pack_conv(ctx, W(k + ".weight"), W(k + ".bias"), cout, cin, ks, up, 1.f, w_dtype, pc, s, high);
   };
   auto norm = [&](const std::string& k, int C, NormW* nw) -> int {
     HDRVAE_REQUIRE(W(k + ".weight") && W(k + ".bias") && ctx->shapes[k + ".weight"].size() == 1 &&
@@ -973,13 +1063,13 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
     HDRVAE_TRY(need_conv("mid.attn_1.k", 512, 512, 1));
     const float scale = 1.0f / sqrtf(512.0f);
     PackedConv& qk = ctx->qk;
-    qk.cin = qk.cin_pad = 512; qk.cout = 1024; qk.ks = 1; qk.w_dtype = op;
-    HDRVAE_TRY(dev_alloc(ctx, (size_t)1024 * 512 * 2, &qk.w[0]));
+    qk.cin = qk.cin_pad = 512; qk.cout = 1024; qk.ks = 1; qk.w_dtype = op; qk.kmul = high ? 3 : 1;
+    HDRVAE_TRY(dev_alloc(ctx, (size_t)1024 * 512 * 2 * qk.kmul, &qk.w[0]));
     HDRVAE_TRY(dev_alloc(ctx, 1024 * sizeof(float), (void**)&qk.bias));
     int mask1[1] = {1};
-    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.q.weight"), qk.w[0], op, 512, 512, 1, 1, 512, mask1, scale, s));
-    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.k.weight"), reinterpret_cast<uint16_t*>(qk.w[0]) + 512 * 512, op, 512, 512, 1,
-                                  1, 512, mask1, 1.f, s));
+    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.q.weight"), qk.w[0], op, 512, 512, 1, 1, 512, mask1, scale, s, high ? 1 : 0));
+    HDRVAE_TRY(launch_pack_weight(W("mid.attn_1.k.weight"), reinterpret_cast<uint16_t*>(qk.w[0]) + 512 * 512 * qk.kmul, op, 512, 512, 1,
+                                  1, 512, mask1, 1.f, s, high ? 1 : 0));
     std::vector<float> hb(1024);
     HDRVAE_CUDA_OK(cudaMemcpyAsync(hb.data(), W("mid.attn_1.q.bias"), 512 * 4, cudaMemcpyDeviceToHost, s));
     HDRVAE_CUDA_OK(cudaMemcpyAsync(hb.data() + 512, W("mid.attn_1.k.bias"), 512 * 4, cudaMemcpyDeviceToHost, s));
@@ -1005,7 +1095,7 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
   HDRVAE_TRY(need_conv("conv_out", 3, 128, 3));
   ctx->conv_out_w = W("conv_out.weight");
   ctx->conv_out_b = W("conv_out.bias");
-  if (op == DT_F16) {
+  if (op == DT_F16 && !high) {
     // conv_out on the tensor cores for the product path: fp32 weights as fp16 hi + lo rows (exact to ~2^-21)
     float* w8 = nullptr;
     HDRVAE_CUDA_OK(cudaMalloc((void**)&w8, 8 * 1152 * sizeof(float)));
@@ -1022,7 +1112,7 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
 int hdrvae_workspace_bytes(hdrvae_ctx* ctx, int B, int h, int w, size_t* bytes) {
   HDRVAE_REQUIRE(ctx != nullptr && bytes != nullptr, "hdrvae_workspace_bytes: null argument");
   HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_workspace_bytes: empty latent batch [%d,16,%d,%d]", B, h, w);
-  *bytes = make_plan(B, h, w).total;
+  *bytes = make_plan(B, h, w, false, ctx->high).total;
   return 0;
 }
 
@@ -1081,7 +1171,7 @@ int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int 
   HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr, "hdrvae_decode: null argument");
   HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode: empty latent batch [%d,16,%d,%d]", B, h, w);
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w);
+  const Plan pl = make_plan(B, h, w, false, ctx->high);
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1108,7 +1198,7 @@ int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float e
   HDRVAE_REQUIRE(ctx != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
   HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_decode: bad mode %d", mode);
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w);
+  const Plan pl = make_plan(B, h, w, false, ctx->high);
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1165,6 +1255,7 @@ int hdrvae_rows_begin(hdrvae_ctx* ctx, const float* latent_full, int h, int w, i
                  "hdrvae_rows_begin: latent height %d must split evenly over %d ranks (rank %d)", h, world, rank);
   HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_rows_begin: bad mode %d", mode);
   HDRVAE_REQUIRE(ctx->conv_impl == HDRVAE_CONV_TCGEN05, "row tiling runs on the tcgen05 kernels only");
+  HDRVAE_REQUIRE(!ctx->high, "row tiling is not available in the high-precision mode");
   hdrvae_rows* st = new hdrvae_rows();
   st->ctx = ctx;
   st->pl = make_rows_plan(h, w, world);
@@ -1248,12 +1339,12 @@ int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent, int B, int h, i
   HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr && features != nullptr, "hdrvae_decode_features: null argument");
   HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode_features: empty latent batch");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w);
+  const Plan pl = make_plan(B, h, w, false, ctx->high);
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   void* feat = nullptr;
   HDRVAE_TRY(run_decoder(ctx, latent, pl, reinterpret_cast<uint8_t*>(workspace), &feat, s));
-  HDRVAE_CUDA_OK(cudaMemcpyAsync(features, feat, (size_t)B * 64 * h * w * 128 * 2, cudaMemcpyDeviceToDevice, s));
+  HDRVAE_CUDA_OK(cudaMemcpyAsync(features, feat, (size_t)B * 64 * h * w * 128 * (ctx->high ? 4 : 2), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

@@ -43,7 +43,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ----------------------------------------------------------------- GEMM / conv descriptor
 // element type codes = the ABI codes of include/hdrvae.h
-enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2,
+       DT_F16X3 = 3 /* internal: fp16 [hi | lo | hi] K-concatenated operand of the "high" precision mode (groupnorm output) */ };
 __host__ __device__ inline int dt_bytes(int dt) { return dt == DT_F32 ? 4 : 2; }
 
 // out[n, y*sy+py, x*sx+px, col] = row_scale[x] * alpha * sum_{t<ntaps} sum_{c<K_per_tap}

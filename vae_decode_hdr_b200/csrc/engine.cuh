@@ -15,7 +15,9 @@ int launch_gemm_direct(const GemmParams& p, cudaStream_t s);
 void choose_tile(int H, int W, GemmParams* p);
 int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStream_t s);
 int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
-                       const int* tap_mask, float scale, cudaStream_t s);
+                       const int* tap_mask, float scale, cudaStream_t s, int split3 = 0);
+int launch_split3(const float* x, long long x_ld, void* out, long long out_ld, long long n, int C, float scale, int order,
+                  cudaStream_t s);
 int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C, int HW, int cpad, cudaStream_t s);
 int launch_latent_rows_to_nhwc(const float* z, void* out, int out_dtype, int C, int h, int w, int y0, int rows, int cpad,
                                cudaStream_t s);
@@ -51,6 +53,10 @@ int launch_epilogue_phase_a_pre(const void* pre, int dtype, int B, int H, int W,
 int launch_split_hi_lo(const float* w, float* w8, int k, cudaStream_t s);
 int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
                             void* scratch, cudaStream_t s);
+int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride, int n_q, const void* k, long long k_ld,
+                           long long k_img_stride, int k_rows, const void* vt, long long vt_ld, long long vt_img_stride,
+                           int n_keys, void* o, long long o_img_stride, int n_img, int dt, float alpha, int cta_group,
+                           cudaStream_t s);
 int launch_raw_stats_merge(const hdrvae_raw_stats* blocks, int n, hdrvae_raw_stats* dst, cudaStream_t s);
 
 // ---- per-op device timing (diagnostics; enabled by hdrvae_profile_begin) -----------------------------
@@ -78,6 +84,8 @@ struct PackedConv {
   int cin = 0, cin_pad = 0, cout = 0, ks = 0;
   int cout_pad = 0;          // cout rounded up to 32: columns the GEMM computes (bias is allocated to this length)
   int w_dtype = DT_F16;      // operand type of this conv (DT_F32 = tf32 MMA on the raw fp32 stream)
+  int kmul = 1;              // 3: "precision high" — every tap's K range is [hi | hi | lo] (3 * cin_pad), the activations
+                             //    come as [hi | lo | hi] (DT_F16X3)
   bool upsample = false;
 };
 struct NormW {
@@ -103,6 +111,7 @@ struct hdrvae_ctx {
   bool loaded = false;
   int conv_impl = HDRVAE_CONV_TCGEN05;
   int op_dtype = DT_F16;                          // 16-bit tensor-core operand type (HDRVAE_PRECISION_*)
+  bool high = false;                              // HDRVAE_PRECISION_HIGH: fp16 hi + lo split operands (3 MMAs per product)
   int cta_group = 0;                              // 0 = default (CTA pairs), 1 / 2 forced
   struct GraphEntry { int seg, B, h, w, mode, conv_impl, cta_group; float factor, ev; void* ws; cudaGraphExec_t exec; long long n_kernels; };
   std::vector<GraphEntry> graphs;                 // captured whole-decode CUDA graphs (hdrvae_decode)
@@ -157,7 +166,7 @@ bool conv_takes_slab(const PackedConv& pc, const ConvIO& io, int H, int W, int i
 
 int dev_alloc(hdrvae_ctx* ctx, size_t bytes, void** out);
 int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int cin, int ks, bool upsample,
-              float scale, int w_dtype, PackedConv* pc, cudaStream_t s);
+              float scale, int w_dtype, PackedConv* pc, cudaStream_t s, bool split3 = false);
 int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int H, int W, int impl, cudaStream_t s);
 
 }  // namespace hdrvae

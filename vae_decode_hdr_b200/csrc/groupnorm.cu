@@ -60,6 +60,31 @@ template <> struct St8<__half> {
   }
 };
 
+template <> struct St8<float> {
+  static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+// "precision high" operand: [hi | lo | hi] fp16 per pixel (3 C channels), hi = fp16(v), lo = fp16(v - hi)
+struct HalfSplit3 { __half h; };
+// 8 channels of pixel p -> y; vpp = C / 8 vectors per pixel
+template <typename TOut>
+__device__ __forceinline__ void store8(TOut* y, long long p, int vpp, int vi, const float (&v)[8]) {
+  St8<TOut>::st(y + (p * vpp + vi) * 8, v);
+}
+template <>
+__device__ __forceinline__ void store8<HalfSplit3>(HalfSplit3* y, long long p, int vpp, int vi, const float (&v)[8]) {
+  const int C = vpp * 8;
+  __half* o = reinterpret_cast<__half*>(y) + p * 3 * C + vi * 8;
+  float lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = v[j] - __half2float(__float2half_rn(v[j]));
+  St8<__half>::st(o, v);
+  St8<__half>::st(o + C, lo);
+  St8<__half>::st(o + 2 * C, v);
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const TIn* __restrict__ x, float* __restrict__ partial, int HW, int C, int px_per_block) {
@@ -173,7 +198,7 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
         v[u][j] = fmaf(v[u][j], a[j], b[j]);
         if (kSilu) v[u][j] = kMufu ? silu_mufu(v[u][j]) : silu_f(v[u][j]);
       }
-      St8<TOut>::st(yout + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
+      store8<TOut>(yout, (long long)(p + u * p_step), vpp, vi, v[u]);
     }
   }
   for (; p < p1; p += p_step) {
@@ -184,7 +209,7 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
       v[j] = fmaf(v[j], a[j], b[j]);
       if (kSilu) v[j] = kMufu ? silu_mufu(v[j]) : silu_f(v[j]);
     }
-    St8<TOut>::st(yout + ((long long)p * vpp + vi) * 8, v);
+    store8<TOut>(yout, (long long)p, vpp, vi, v);
   }
 }
 
@@ -320,7 +345,9 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
                      const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s) {
   HDRVAE_REQUIRE(C % 32 == 0 && C >= 128 && C <= 2048 && (kGnThreads % (C >> 3)) == 0,
                  "groupnorm: unsupported channel count %d", C);
-  HDRVAE_REQUIRE(y_dtype == DT_BF16 || y_dtype == DT_F16, "groupnorm: output must be a 16-bit operand type");
+  HDRVAE_REQUIRE(y_dtype == DT_BF16 || y_dtype == DT_F16 || y_dtype == DT_F32 || y_dtype == DT_F16X3,
+                 "groupnorm: output must be a 16-bit operand type, fp32 or the fp16 hi|lo|hi operand");
+  HDRVAE_REQUIRE((y_dtype != DT_F32 && y_dtype != DT_F16X3) || x_dtype == DT_F32, "groupnorm: fp32 / split outputs need fp32 input");
   int chunks, ppb;
   gn_chunking(B, HW, C, max_chunks, &chunks, &ppb);
   float* partial = reinterpret_cast<float*>(scratch);
@@ -340,7 +367,12 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
                                        (double)HW * (double)(C / kGroups), 1e-6f);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
-  if (y_dtype == DT_F16) {
+  if (y_dtype == DT_F32) {
+    launch_apply<float, float>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+  } else if (y_dtype == DT_F16X3) {
+    // y_img_stride is counted in HalfSplit3 elements = 2-byte units
+    launch_apply<float, HalfSplit3>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C * 3, s);
+  } else if (y_dtype == DT_F16) {
     if (x_dtype == DT_F32) launch_apply<float, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
     else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
     else launch_apply<__half, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);

@@ -31,6 +31,7 @@ struct PackArgs {
   int cout, cin, ks, ntaps, cin_pad, out_dtype;
   int tap_mask[9];
   float scale;
+  int split3;   // fp16 only: every tap's K range is [hi | hi | lo] (3 * cin_pad) with hi = fp16(w), lo = fp16(w - hi)
 };
 __device__ __forceinline__ void store_as(void* out, long long i, int dtype, float v) {
   if (dtype == DT_F32) {
@@ -55,12 +56,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict
       for (int s = 0; s < kk; ++s)
         if (a.tap_mask[t] & (1 << s)) acc += w[((long long)co * a.cin + ci) * kk + s];
     }
-    store_as(out, i, a.out_dtype, acc * a.scale);
+    const float v = acc * a.scale;
+    if (a.split3) {
+      // "precision high": w = hi + lo to ~2^-22; the activations come as [hi | lo | hi], so the K-concatenated product
+      // is hi*hi + lo*hi + hi*lo (the lo*lo term, ~2^-22 relative, is dropped)
+      __half* o = reinterpret_cast<__half*>(out) + ((long long)co * a.ntaps + t) * 3 * a.cin_pad + ci;
+      const __half hi = __float2half_rn(v);
+      o[0] = hi;
+      o[a.cin_pad] = hi;
+      o[2 * a.cin_pad] = __float2half_rn(v - __half2float(hi));
+    } else {
+      store_as(out, i, a.out_dtype, v);
+    }
   }
 }
 int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
-                       const int* tap_mask, float scale, cudaStream_t s) {
+                       const int* tap_mask, float scale, cudaStream_t s, int split3) {
   PackArgs a;
+  a.split3 = split3;
   a.out_dtype = out_dtype;
   a.cout = cout; a.cin = cin; a.ks = ks; a.ntaps = ntaps; a.cin_pad = cin_pad; a.scale = scale;
   for (int t = 0; t < 9; ++t) a.tap_mask[t] = t < ntaps ? tap_mask[t] : 0;
@@ -83,7 +96,8 @@ __global__ void latent_to_nhwc_kernel(const float* __restrict__ z, void* __restr
     const int hw = (int)(p % HW);
     const int b = (int)(p / HW);
     const float v = c < C ? z[((long long)b * C + c) * HW + hw] : 0.f;
-    if (out_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    if (out_dtype == DT_F32) reinterpret_cast<float*>(out)[i] = v;
+    else if (out_dtype == DT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
     else reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
   }
 }
@@ -190,6 +204,42 @@ int launch_gemm_direct(const GemmParams& p, cudaStream_t s) {
   return 0;
 }
 
+// ------------------------------------------------------------------ fp32 tensor -> K-concatenated fp16 hi / lo operand
+// x [n][C] fp32 (row stride x_ld) -> out [n][3 C] fp16 (row stride out_ld): activation order [hi | lo | hi] (order 0) or
+// weight-side order [hi | hi | lo] (order 1) of scale * x, hi = fp16(v), lo = fp16(v - hi).  "precision high" feeds every
+// GEMM-shaped op with such operands: sum_k a_k b_k over the 3 C columns = hi*hi + lo*hi + hi*lo.
+__global__ void split3_kernel(const float* __restrict__ x, long long x_ld, __half* __restrict__ out, long long out_ld,
+                              long long n, int C, float scale, int order) {
+  const int c4 = C >> 2;
+  const long long total = n * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * x_ld + c);
+    const float f[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { hi[j] = __float2half_rn(f[j]); lo[j] = __float2half_rn(f[j] - __half2float(hi[j])); }
+    __half* o = out + r * out_ld + c;
+    const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(o) = h2;
+    *reinterpret_cast<uint2*>(o + C) = order == 0 ? l2 : h2;
+    *reinterpret_cast<uint2*>(o + 2 * C) = order == 0 ? h2 : l2;
+  }
+}
+int launch_split3(const float* x, long long x_ld, void* out, long long out_ld, long long n, int C, float scale, int order,
+                  cudaStream_t s) {
+  HDRVAE_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0, "split3: channel count / strides must be multiples of 4");
+  if (n == 0) return 0;
+  const long long total = n * (C >> 2);
+  int grid = ceil_div(total, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  split3_kernel<<<grid, 256, 0, s>>>(x, x_ld, reinterpret_cast<__half*>(out), out_ld, n, C, scale, order);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ fp32 weights -> fp16 hi / lo rows
 // w [rows][k] fp32 -> w8 [8][k] fp32: rows 0..2 = w (packs to hi = fp16(w)), rows 4..6 = w - float(fp16(w)) (packs to
 // lo), rows 3 and 7 zero; rows must be 3 (conv_out).  hi + lo carries ~21 mantissa bits of w.
@@ -256,11 +306,27 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     o2.x = pack2(e0, e1, p_dtype);
     o2.y = pack2(e2, e3, p_dtype);
     out4[i] = o2;
+    if (p_dtype == DT_F16X3) {
+      // "precision high": the row is [hi | lo | hi] over the keys (3 * n_pad columns); pack2 wrote hi = fp16(e)
+      const __half2 h01 = *reinterpret_cast<const __half2*>(&o2.x), h23 = *reinterpret_cast<const __half2*>(&o2.y);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      uint2 l2;
+      l2.x = pack2(e0 - f01.x, e1 - f01.y, DT_F16);
+      l2.y = pack2(e2 - f23.x, e3 - f23.y, DT_F16);
+      reinterpret_cast<uint2*>(out + n_pad)[i] = l2;
+      reinterpret_cast<uint2*>(out + 2 * (long long)n_pad)[i] = o2;
+    }
   }
   for (int i = nv * 4 + threadIdx.x; i < n_pad; i += 256) {
     const float e = i < n_valid ? __expf(row[i] - m) : 0.f;
     sum += e;
-    out[i] = (uint16_t)(pack2(e, 0.f, p_dtype) & 0xffffu);
+    const uint16_t hi = (uint16_t)(pack2(e, 0.f, p_dtype) & 0xffffu);
+    out[i] = hi;
+    if (p_dtype == DT_F16X3) {
+      const float fh = __half2float(*reinterpret_cast<const __half*>(&hi));
+      out[n_pad + i] = (uint16_t)(pack2(e - fh, 0.f, DT_F16) & 0xffffu);
+      out[2 * (long long)n_pad + i] = hi;
+    }
   }
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   __syncthreads();

@@ -211,7 +211,30 @@ __global__ void up_local_fix_kernel(const float* __restrict__ img, int B, int H,
       return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, p[0]), __fmul_rn(0.587f, p[1])), __fmul_rn(0.114f, p[2]));
     };
     float ys;
-    if (method == HDRVAE_UPSCALE_NEAREST_EXACT || method == HDRVAE_UPSCALE_AREA) {
+    if (method == HDRVAE_UPSCALE_BISLERP) {
+      // comfy.utils.bislerp on the 1-channel luma (restated in oracle/upscaler_oracle.py): separable, width pass first.
+      // Per axis: the two source pixels bilinear interpolation (align_corners = False) would blend, c1 = floor(src),
+      // c2 = min(c1 + 1, last), ratio r = frac(src) with src = max((dst + 0.5) / scale - 0.5, 0) — exact in fp32 for the
+      // 4x scale — then a SPHERICAL interpolation of the channel vectors; for scalars: same sign -> the first pixel,
+      // opposite signs -> linear, a zero -> sine weights times the linearly interpolated magnitude.
+      auto slerp1 = [](float b1, float b2, float r) {
+        const float n1 = fabsf(b1), n2 = fabsf(b2);
+        const float u1 = n1 == 0.f ? 0.f : b1 / n1, u2 = n2 == 0.f ? 0.f : b2 / n2;
+        const float dot = u1 * u2;
+        if (dot > 1.f - 1e-5f) return b1;
+        if (dot < 1e-5f - 1.f) return __fadd_rn(__fmul_rn(b1, __fsub_rn(1.f, r)), __fmul_rn(b2, r));
+        const float omega = acosf(dot), so = sinf(omega);
+        float res = (sinf((1.f - r) * omega) / so) * u1 + (sinf(r * omega) / so) * u2;
+        return res * (n1 * (1.f - r) + n2 * r);
+      };
+      const float fy = fmaxf((y + 0.5f) / scale - 0.5f, 0.f), fx = fmaxf((x + 0.5f) / scale - 0.5f, 0.f);
+      const int y1 = min((int)fy, H - 1), x1 = min((int)fx, W - 1);
+      const int y2 = min(y1 + 1, H - 1), x2 = min(x1 + 1, W - 1);
+      const float ry = fy - floorf(fy), rx = fx - floorf(fx);
+      const float t1 = slerp1(luma(y1, x1), luma(y1, x2), rx);
+      const float t2 = slerp1(luma(y2, x1), luma(y2, x2), rx);
+      ys = slerp1(t1, t2, ry);
+    } else if (method == HDRVAE_UPSCALE_NEAREST_EXACT || method == HDRVAE_UPSCALE_AREA) {
       // nearest-exact: floor((dst + 0.5) / scale); "area" = adaptive average pooling, whose window for an integer
       // upscale factor is exactly that one source pixel
       ys = luma(min((int)floorf((y + 0.5f) / scale), H - 1), min((int)floorf((x + 0.5f) / scale), W - 1));
@@ -618,8 +641,8 @@ int hdrvae_upscale(hdrvae_upscaler* up, const float* image_bhwc, int B, int H, i
                    void* stream) {
   HDRVAE_REQUIRE(up && up->loaded && image_bhwc && out_bhwc && workspace, "hdrvae_upscale: null argument / no weights");
   HDRVAE_REQUIRE(reversal == 1 || reversal == 2, "hdrvae_upscale: reversal must be 1 (atanh) or 2 (logit)");
-  HDRVAE_REQUIRE(!local_fix || (upscale_method >= HDRVAE_UPSCALE_NEAREST_EXACT && upscale_method <= HDRVAE_UPSCALE_BICUBIC),
-                 "hdrvae_upscale: local_fix supports upscale_method nearest-exact, bilinear, area and bicubic (got %d)", upscale_method);
+  HDRVAE_REQUIRE(!local_fix || (upscale_method >= HDRVAE_UPSCALE_NEAREST_EXACT && upscale_method <= HDRVAE_UPSCALE_BISLERP),
+                 "hdrvae_upscale: local_fix supports upscale_method nearest-exact, bilinear, area, bicubic and bislerp (got %d)", upscale_method);
   HDRVAE_CUDA_OK(cudaSetDevice(up->store.device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const UpTiling t = up_make_tiling(B, H, W);

@@ -20,7 +20,7 @@ MODE_ALIASES = {"moderate": ("conservative", 3.0), "aggressive": ("mathematical_
 _MODE_ID = {m: i for i, m in enumerate(HDR_MODES)}
 _DTYPE_ID = {torch.float32: N.F32, torch.bfloat16: N.BF16, torch.float16: N.F16}
 _ID_DTYPE = {v: k for k, v in _DTYPE_ID.items()}
-PRECISIONS = {"fp16": N.PRECISION_F16, "bf16": N.PRECISION_BF16}
+PRECISIONS = {"fp16": N.PRECISION_F16, "bf16": N.PRECISION_BF16, "high": N.PRECISION_HIGH}
 
 
 def resolve_mode(hdr_mode: str) -> Tuple[int, float]:
@@ -50,8 +50,9 @@ class HdrVaeEngine:
     """One libhdrvae context: packed decoder weights + workspace on one GPU."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", precision: str = "fp16"):
-        """precision: 16-bit tensor-core operand type, "fp16" (default, meets the 1e-2 tolerance) or "bf16";
-        the residual/conv streams are fp32 and raw-stream convs tf32 in both (include/hdrvae.h)."""
+        """precision: "fp16" (default: 16-bit tensor-core operands, meets the 1e-2 image tolerance), "bf16" (same speed,
+        documented 2e-2), or "high" (fp16 hi + lo split operands, 3 MMAs per product: image rel-L2 <= 1e-3 at ~3x the conv
+        time; single-GPU decode only).  The residual / conv streams are fp32 in all three (include/hdrvae.h)."""
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {list(PRECISIONS)}")
         self.precision = precision
@@ -88,6 +89,7 @@ class HdrVaeEngine:
             N.check(self.lib.hdrvae_load_weights(self._ctx, arr, len(descs), PRECISIONS[self.precision]),
                     "hdrvae_load_weights")
         self.operand_dtype = _ID_DTYPE[self.lib.hdrvae_operand_dtype(self._ctx)]
+        self.features_dtype = _ID_DTYPE[self.lib.hdrvae_features_dtype(self._ctx)]
 
     def set_conv_impl(self, impl: int) -> None:
         N.check(self.lib.hdrvae_set_conv_impl(self._ctx, impl), "hdrvae_set_conv_impl")
@@ -227,7 +229,7 @@ class HdrVaeEngine:
         with torch.cuda.device(self.device):
             z = latent.to(device=self.device, dtype=torch.float32).contiguous()
             ws = self._ws(B, h, w)
-            feat = torch.empty((B, 8 * h, 8 * w, 128), dtype=self.operand_dtype, device=self.device)
+            feat = torch.empty((B, 8 * h, 8 * w, 128), dtype=self.features_dtype, device=self.device)
             N.check(self.lib.hdrvae_decode_features(self._ctx, z.data_ptr(), B, h, w, feat.data_ptr(), ws.data_ptr(),
                                                     ws.numel(), self._stream()), "hdrvae_decode_features")
         return feat

@@ -11,8 +11,8 @@ from . import _native as N
 from .engine import _DTYPE_ID, _require_cuda
 
 REVERSAL = {"none": N.REVERSAL_NONE, "atanh": N.REVERSAL_ATANH, "logit": N.REVERSAL_LOGIT}
-# hdr_upscale_with_model.py:64 — the node's enum; the library implements the torch-expressible ones (all but ComfyUI's
-# own "bislerp") for local_fix
+# hdr_upscale_with_model.py:64 — the node's enum; all five are implemented for local_fix (torch semantics for the
+# first four, ComfyUI's own spherical-linear "bislerp" — the node's default — restated in oracle/upscaler_oracle.py)
 UPSCALE_METHODS = ["nearest-exact", "bilinear", "area", "bicubic", "bislerp"]
 
 
@@ -90,8 +90,7 @@ class HdrUpscalerEngine:
         if reversal not in ("atanh", "logit"):
             raise ValueError("reversal must be 'atanh' or 'logit'")
         if local_fix and upscale_method not in N.UPSCALE_METHODS:
-            raise NotImplementedError(f"local_fix with upscale_method={upscale_method!r} is not implemented on the GPU path "
-                                      f"(available: {sorted(N.UPSCALE_METHODS)})")
+            raise ValueError(f"unknown upscale_method {upscale_method!r} (available: {sorted(N.UPSCALE_METHODS)})")
         B, H, W, _ = image_bhwc.shape
         with torch.cuda.device(self.device):
             x = image_bhwc.to(self.device, torch.float32).contiguous()
