@@ -367,17 +367,23 @@ def main():
     lib.hdrvae_profile_begin()
     engine.decode(z_dev, MODE, 1.0, want_stats=False)
     lib.hdrvae_profile_end(prof_path.encode())
-    conv_ms = gn_ms = attn_ms = epi_ms = 0.0
+    conv_ms = gn_ms = attn_ms = epi_ms = gn_bytes = 0.0
+    attn_kernel_ms = None
     n_conv = 0
     with open(prof_path) as f:
         for ln in f:
-            name, t = ln.split("\t")[0].strip(), float(ln.split("\t")[1].split()[0])
+            cols = ln.split("\t")
+            name, t = cols[0].strip(), float(cols[1].split()[0])
             if name.startswith("conv3x3 128->8 "):
                 continue      # conv_out on the tensor cores: nested inside (and counted with) "epilogue phase A"
+            if name.startswith("attention fused kernel"):
+                attn_kernel_ms = t
+                continue      # nested inside (and counted with) "attention core"
             if name.startswith("conv"):
                 conv_ms += t; n_conv += 1
             elif name.startswith("groupnorm"):
                 gn_ms += t
+                gn_bytes += float(cols[3].split()[0]) * 1e9 * t / 1e3      # the scope's own byte count (actual dtypes)
             elif name.startswith("attention"):
                 attn_ms += t
             elif name.startswith("epilogue"):
@@ -401,7 +407,20 @@ def main():
                 "note": "achieved = algorithmic conv FLOPs (SURVEY 8d) / summed conv launch time of one step; "
                         "achieved_executed discounts the 5/9 of the upsample convs' FLOPs that phase decomposition removes",
                 "step_breakdown_ms": {"conv": conv_ms, "groupnorm_silu": gn_ms, "attention": attn_ms, "epilogue": epi_ms},
-                "groupnorm_gbs": (1837.1e6 * B * 6.0 / (gn_ms / 1e3) / 1e9) if gn_ms > 0 else None,
+                # GroupNorm + SiLU (HBM bound).  bytes_moved = what the kernels actually read + write (conv1 outputs are stored
+                # as 16-bit, so half of the layers move 4 B per element, the rest 6); gbs_vs_6B = the same time charged with
+                # the 6 B / element of an fp32-in / 16-bit-out pass over every layer (round-1 definition); SURVEY 8d's
+                # algorithmic minimum is 4 B / element
+                "groupnorm": {"ms": gn_ms, "elements": 1837.1e6 * B, "bytes_moved": gn_bytes,
+                              "gbs_moved": (gn_bytes / (gn_ms / 1e3) / 1e9) if gn_ms > 0 else None,
+                              "frac_of_hbm_peak": (gn_bytes / (gn_ms / 1e3) / 1e9 / peak_gbs) if gn_ms > 0 else None,
+                              "gbs_vs_6B": (1837.1e6 * B * 6.0 / (gn_ms / 1e3) / 1e9) if gn_ms > 0 else None,
+                              "gbs_vs_4B_minimum": (1837.1e6 * B * 4.0 / (gn_ms / 1e3) / 1e9) if gn_ms > 0 else None},
+                "attention_fused_kernel": ({"ms": attn_kernel_ms,
+                                            "tflops_effective": 4.0 * B * (L * L) ** 2 * 512 / (attn_kernel_ms / 1e3) / 1e12,
+                                            "note": "one launch, O = softmax(QK^T)V for all images; effective = 4*T^2*512 per image "
+                                                    "(the kernel executes 1.5x that: S is recomputed for each d_v half)"}
+                                           if attn_kernel_ms else None),
                 "hbm_peak_gbs": peak_gbs}
 
     # ---- e2e through the node API with host buffers: same number of steps as the device-timed value

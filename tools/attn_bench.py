@@ -1,9 +1,9 @@
-"""Attention core alone (hdrvae_attention: q, k, v 16-bit [B, T, 512]) — device time and effective TFLOP/s
-(4 * T^2 * 512 per image).  The transposes / interleaves of the test entry are excluded by timing a second run's
-profile scope... simpler: time the whole entry for large T where they are < 1 %.
-  HDRVAE_ATTN_FUSED=0|1 python tools/attn_bench.py"""
+"""Attention core alone (hdrvae_attention: q, k, v 16-bit [B, T, 512]): device time of the whole test entry (which also
+allocates its workspace and transposes / interleaves the operands) and, for the fused kernel, of the kernel itself
+(library profile scope).  HDRVAE_ATTN_FUSED=0|1 HDRVAE_ATTN_CG=1|2 python tools/attn_bench.py [BxT ...]"""
 import os
 import sys
+import tempfile
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -31,4 +31,13 @@ for B, T in cases:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tf = 4.0 * B * T * T * 512 / (ms / 1e3) / 1e12
-    print(f"fused={os.environ.get('HDRVAE_ATTN_FUSED', '1')} cg={os.environ.get('HDRVAE_ATTN_CG', '-')} B={B} T={T}: {ms:.3f} ms  {tf:.1f} TFLOP/s effective  finite={bool(torch.isfinite(o).all())}", flush=True)
+    kern = ""
+    path = os.path.join(tempfile.gettempdir(), "attn_prof.tsv")
+    eng.lib.hdrvae_profile_begin()
+    eng.attention(q, k, v)
+    eng.lib.hdrvae_profile_end(path.encode())
+    for ln in open(path):
+        if ln.startswith("attention fused kernel"):
+            kms = float(ln.split("\t")[1].split()[0])
+            kern = f"  kernel alone {kms:.3f} ms = {4.0 * B * T * T * 512 / (kms / 1e3) / 1e12:.1f} TFLOP/s"
+    print(f"fused={os.environ.get('HDRVAE_ATTN_FUSED', '1')} cg={os.environ.get('HDRVAE_ATTN_CG', '-')} B={B} T={T}: entry {ms:.3f} ms  {tf:.1f} TFLOP/s effective{kern}", flush=True)

@@ -144,6 +144,7 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   p.n_store = io.n_store > 0 ? io.n_store : (pc.cout_pad != pc.cout ? (pc.cout + 3) / 4 * 4 : 0);
   p.res_scale = io.res_scale; p.lrelu = io.lrelu;
   p.out_dtype = io.y_dtype;
+  p.out_scale = io.y_scale;
   p.bias = pc.bias; p.bias_per_row = 0; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
   p.round_tf32 = io.round_tf32 ? 1 : 0;
   p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
@@ -312,14 +313,23 @@ struct DecState {
 };
 
 static int run_gn(hdrvae_ctx* ctx, const void* x, int x_dtype, void* y, int B, int HW, const NormW& nw, bool silu,
-                  DecState* st, cudaStream_t s, int y_dtype = -1) {
+                  DecState* st, cudaStream_t s, int y_dtype = -1, float in_scale = 1.f) {
   char pname[64];
   snprintf(pname, sizeof pname, "groupnorm%s C=%d @%dx%d", silu ? "+silu" : "", nw.C, B, HW);
   ProfScope prof(pname, 0.0, (double)B * HW * nw.C * (dt_bytes(x_dtype) * (st->pending > 0 ? 1 : 2) + 2.0), s);
   const int partials = st->pending;
   st->pending = 0;
   return launch_groupnorm(x, x_dtype, y, y_dtype >= 0 ? y_dtype : (ctx->high ? DT_F16X3 : ctx->op_dtype), B, HW, nw.C, nw.gamma,
-                          nw.beta, silu, st->gn, st->gn_chunks, partials, s);
+                          nw.beta, silu, st->gn, st->gn_chunks, partials, s, in_scale);
+}
+
+// The block-internal tensor h = conv1(...) is never on the residual path: it is stored ONLY as the scaled 16-bit operand
+// type (2 B instead of 4 written by conv1, 2 instead of 4 read by norm2; its GroupNorm statistics still come from the
+// fp32 accumulators).  HDRVAE_H16=0 keeps it fp32.  Not used by the high-precision mode or the validation kernels.
+static bool h_is_16bit(hdrvae_ctx* ctx) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HDRVAE_H16"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on && !ctx->high && ctx->conv_impl == HDRVAE_CONV_TCGEN05;
 }
 
 static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
@@ -329,19 +339,19 @@ static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
 // GroupNorm + SiLU in front of a conv: either the separate streaming kernel (x -> t, 16-bit) or, when the conv takes
 // the slab form and HDRVAE_FUSE_GN is on, only the statistics -> scale / shift step: the conv then reads the raw fp32
 // tensor and normalises while staging its operand (io->xf_*), and the 16-bit tensor never exists in HBM.
-static int gn_before_conv(hdrvae_ctx* ctx, const float* x, const NormW& nw, const PackedConv& pc, ConvIO* io, DecState* st,
-                          int B, int H, int W, cudaStream_t s) {
+static int gn_before_conv(hdrvae_ctx* ctx, const void* x, const NormW& nw, const PackedConv& pc, ConvIO* io, DecState* st,
+                          int B, int H, int W, cudaStream_t s, int x_dtype = DT_F32, float x_scale = 1.f) {
   static int fuse = -1;
   static int fuse_min_n = 256;      // 128-column convs: the transform (MUFU bound) takes longer than their MMAs
   if (fuse < 0) {
     const char* e = getenv("HDRVAE_FUSE_GN"); fuse = (e && atoi(e) != 0) ? 1 : 0;
     const char* m = getenv("HDRVAE_FUSE_GN_MINN"); if (m) fuse_min_n = atoi(m);
   }
-  const bool fusable = fuse && !ctx->high && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && st->pending > 0 &&
+  const bool fusable = fuse && !ctx->high && x_dtype == DT_F32 && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && st->pending > 0 &&
                        pc.cout_pad >= fuse_min_n && io->y2 == nullptr && conv_takes_slab(pc, *io, H, W, ctx->conv_impl) &&
                        !(pc.cout_pad == 128 && io->residual != nullptr);
   if (!fusable) {
-    HDRVAE_TRY(run_gn(ctx, x, DT_F32, st->t, B, H * W, nw, true, st, s));
+    HDRVAE_TRY(run_gn(ctx, x, x_dtype, st->t, B, H * W, nw, true, st, s, -1, x_scale));
     io->x = st->t;
     return 0;
   }
@@ -359,8 +369,12 @@ static int gn_before_conv(hdrvae_ctx* ctx, const float* x, const NormW& nw, cons
 
 static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, int W, cudaStream_t s) {
   const int impl = ctx->conv_impl;
+  const bool h16 = h_is_16bit(ctx);
+  const int h_dt = h16 ? ctx->op_dtype : DT_F32;
+  const float h_scale = h16 ? kRawOperandScale : 1.f;
   {
     ConvIO io; io.y = st->hbuf; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
+    io.y_dtype = h_dt; io.y_scale = h_scale;
     HDRVAE_TRY(gn_before_conv(ctx, st->x, rw.n1, rw.c1, &io, st, B, H, W, s));
     HDRVAE_TRY(run_conv(ctx, rw.c1, io, B, H, W, impl, s));
   }
@@ -369,7 +383,7 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
   if (rw.has_nin) {
     // norm2 as a separate pass (conv1's output lives in hbuf, which the shortcut is about to overwrite); then the
     // shortcut on the scaled 16-bit copy of x into hbuf, and conv2 accumulates onto it in place
-    HDRVAE_TRY(run_gn(ctx, st->hbuf, DT_F32, st->t, B, H * W, rw.n2, true, st, s));
+    HDRVAE_TRY(run_gn(ctx, st->hbuf, h_dt, st->t, B, H * W, rw.n2, true, st, s, -1, 1.f / h_scale));
     io.x = st->t;
     ConvIO sc; sc.x = st->xb16; sc.y = st->hbuf; sc.alpha = 1.0f / kRawOperandScale;
     HDRVAE_TRY(run_conv(ctx, rw.nin, sc, B, H, W, impl, s));
@@ -378,7 +392,7 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
     std::swap(st->x, st->hbuf);
   } else {
     io.y = st->x; io.residual = st->x;                  // x += conv2(t), in place
-    HDRVAE_TRY(gn_before_conv(ctx, st->hbuf, rw.n2, rw.c2, &io, st, B, H, W, s));
+    HDRVAE_TRY(gn_before_conv(ctx, st->hbuf, rw.n2, rw.c2, &io, st, B, H, W, s, h_dt, 1.f / h_scale));
     HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
   }
   return 0;
@@ -538,6 +552,7 @@ static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, cons
                               cudaStream_t s) {
   if (attention_fused_enabled(ctx)) {
     // all images in one launch
+    ProfScope prof("attention fused kernel", 4.0 * pl.B * (double)pl.T * pl.T * 512, 0.0, s);
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk);
     return launch_attention_fused(q, 1024, (long long)pl.Tp * 1024, pl.T, q + 512, 1024, (long long)pl.Tp * 1024, pl.Tp, vt, pl.Tp,
                                   (long long)512 * pl.Tp, pl.T, o, (long long)pl.T * 512, pl.B, ctx->op_dtype, qk_alpha,
@@ -745,7 +760,8 @@ static int zero_border_halos(hdrvae_rows* st, void* slab, int H, int W, int C, i
 }
 
 // conv epilogue emitted this rank's GroupNorm partials: fold them, then (exchange) all-reduce the sums
-static void rows_stats_and_halo(hdrvae_rows* st, const void* slab_f32, int H, int W, int C, const void* slab16, int C16) {
+static void rows_stats_and_halo(hdrvae_rows* st, const void* slab_f32, int H, int W, int C, const void* slab16, int C16,
+                                int eb = 4) {
   hdrvae_ctx* ctx = st->ctx;
   void* gn = st->ws + st->pl.off_gn;
   const int gn_chunks = st->pl.gn_chunks;
@@ -753,7 +769,7 @@ static void rows_stats_and_halo(hdrvae_rows* st, const void* slab_f32, int H, in
   rows_compute(st, [=](cudaStream_t s) { return launch_gn_reduce_partials(gn, 1, 512, gn_chunks, *pending, s); });
   hdrvae_exchange ex;
   memset(&ex, 0, sizeof ex);
-  add_halo(st, &ex, slab_f32, H, W, C, 4);
+  add_halo(st, &ex, slab_f32, H, W, C, eb);
   if (slab16 != nullptr) add_halo(st, &ex, slab16, H, W, C16, 2);
   ex.kind |= HDRVAE_EX_ALLREDUCE_F64;
   ex.allreduce_off = ws_off(st, gn_sums_ptr(gn, 1, 512, gn_chunks));
@@ -764,7 +780,8 @@ static void rows_stats_and_halo(hdrvae_rows* st, const void* slab_f32, int H, in
 
 // t = [silu](GroupNorm(x)) over the whole slab (halo rows included: GroupNorm is elementwise once the global
 // statistics are known), then restore the zero padding at the image borders
-static void rows_gn(hdrvae_rows* st, const float* x_slab, const NormW& nw, bool silu, int H, int W) {
+static void rows_gn(hdrvae_rows* st, const void* x_slab, const NormW& nw, bool silu, int H, int W, int x_dtype = DT_F32,
+                    float in_scale = 1.f) {
   hdrvae_ctx* ctx = st->ctx;
   void* gn = st->ws + st->pl.off_gn;
   void* t = st->ws + st->pl.off_t;
@@ -773,8 +790,8 @@ static void rows_gn(hdrvae_rows* st, const float* x_slab, const NormW& nw, bool 
   const NormW n = nw;
   rows_compute(st, [=](cudaStream_t s) {
     const long long slab = (long long)(H + 2) * W * n.C;
-    HDRVAE_TRY(launch_gn_apply_from_sums(x_slab, DT_F32, slab, t, ctx->op_dtype, slab, 1, (H + 2) * W, n.C, n.gamma, n.beta,
-                                         silu, gn, gn_chunks, count, s));
+    HDRVAE_TRY(launch_gn_apply_from_sums(x_slab, x_dtype, slab, t, ctx->op_dtype, slab, 1, (H + 2) * W, n.C, n.gamma, n.beta,
+                                         silu, gn, gn_chunks, count, s, in_scale));
     return zero_border_halos(st, t, H, W, n.C, 2, s);
   });
 }
@@ -788,13 +805,17 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
   int* pending = &st->pending;
   float* x = st->x; float* hb = st->hbuf;
   const ResW* r = &rw;
+  const bool h16 = h_is_16bit(ctx);                    // same storage rule as the single-GPU program (bit-identical results)
+  const int h_dt = h16 ? ctx->op_dtype : DT_F32;
+  const float h_scale = h16 ? kRawOperandScale : 1.f;
   rows_gn(st, x, rw.n1, true, H, W);
   rows_compute(st, [=](cudaStream_t s) {
     ConvIO io; io.x = t; io.y = hb; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
+    io.y_dtype = h_dt; io.y_scale = h_scale;
     return run_conv(ctx, r->c1, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
   });
-  rows_stats_and_halo(st, hb, H, W, rw.c1.cout, nullptr, 0);
-  rows_gn(st, hb, rw.n2, true, H, W);
+  rows_stats_and_halo(st, hb, H, W, rw.c1.cout, nullptr, 0, h16 ? 2 : 4);
+  rows_gn(st, hb, rw.n2, true, H, W, h_dt, 1.f / h_scale);
   float* out = rw.has_nin ? hb : x;
   rows_compute(st, [=](cudaStream_t s) {
     if (r->has_nin) {

@@ -78,6 +78,8 @@ struct GemmParams {
   // output
   void* out;
   int out_dtype;
+  float out_scale;   // multiplier of a 16-bit main output (0 is read as 1): un-normalised tensors are stored scaled by a
+                     // power of two so that fp16 cannot overflow (statistics are taken of the un-scaled values)
   long long out_img_stride, out_row_stride, out_px_stride;  // elements
   int sy, sx, py, px;
   const float* bias;

@@ -33,7 +33,8 @@ int launch_quantiles(const float* x, long long n, const unsigned long long* rank
                      cudaStream_t s);
 size_t gn_scratch_bytes(int B, int C, int max_chunks);
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
-                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s);
+                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s,
+                     float in_scale = 1.f);
 int launch_gn_finalize_only(int B, int HW, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
                             int partial_chunks, const float** scale_out, const float** shift_out, cudaStream_t s);
 size_t epilogue_scratch_bytes(int B, int H, int W);
@@ -47,7 +48,7 @@ double* gn_sums_ptr(void* scratch, int B, int C, int max_chunks);
 int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n_partials, cudaStream_t s);
 int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
                               int B, int rows_px, int C, const float* gamma, const float* beta, bool silu, void* scratch,
-                              int max_chunks, double count, cudaStream_t s);
+                              int max_chunks, double count, cudaStream_t s, float in_scale = 1.f);
 int launch_epilogue_phase_a_pre(const void* pre, int dtype, int B, int H, int W, const float* conv8, const float* conv_b,
                                 int* argmax3, void* scratch, cudaStream_t s, long long img_stride);
 int launch_split_hi_lo(const float* w, float* w8, int k, cudaStream_t s);
@@ -135,6 +136,7 @@ struct ConvIO {
   const void* x = nullptr;        // [B,H,W,cin_pad], element type = pc.w_dtype
   void* y = nullptr;              // [B,OH,OW,cout]
   int y_dtype = DT_F32;
+  float y_scale = 1.f;            // multiplier of a 16-bit y (un-normalised tensors are stored scaled by 2^-4)
   const void* residual = nullptr; // y's layout
   int res_dtype = DT_F32;
   bool round_tf32 = false;

@@ -393,6 +393,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float alpha = p.alpha;
     const bool out16_bf = p.out_dtype == DT_BF16, out2_bf = p.out2_dtype == DT_BF16;
     const float s2 = p.out2_scale;
+    const float s16 = p.out_scale != 0.f ? p.out_scale : 1.f;
     float* const outf = reinterpret_cast<float*>(p.out);
     uint16_t* const outh = reinterpret_cast<uint16_t*>(p.out);
     uint16_t* const out2h = reinterpret_cast<uint16_t*>(p.out2);
@@ -610,8 +611,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *reinterpret_cast<float4*>(outf + poff[it] + col) = a;
             } else {
               uint2 o;
-              if (out16_bf) { o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); }
-              else { o.x = pack_f16x2(a.x, a.y); o.y = pack_f16x2(a.z, a.w); }
+              if (out16_bf) { o.x = pack_bf16x2(a.x * s16, a.y * s16); o.y = pack_bf16x2(a.z * s16, a.w * s16); }
+              else { o.x = pack_f16x2(a.x * s16, a.y * s16); o.y = pack_f16x2(a.z * s16, a.w * s16); }
               *reinterpret_cast<uint2*>(outh + poff[it] + col) = o;
             }
             if (has_stats) {
@@ -960,8 +961,8 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (p.out_dtype == DT_F32 && !rowops) {
         epi = (p.residual ? EPI_RES : 0) | (p.out2 ? EPI_OUT2 : 0) | (p.stats ? EPI_STATS : 0);
         if ((epi & EPI_OUT2) && !(epi & EPI_STATS)) epi = -1;        // not a decoder combination
-      } else if (p.out_dtype != DT_F32 && p.residual == nullptr && p.out2 == nullptr && p.stats == nullptr) {
-        epi = EPI_OUT16 | (rowops ? EPI_ROWOPS : 0);
+      } else if (p.out_dtype != DT_F32 && p.residual == nullptr && p.out2 == nullptr && !(p.stats && rowops)) {
+        epi = EPI_OUT16 | (rowops ? EPI_ROWOPS : 0) | (p.stats ? EPI_STATS : 0);
       } else {
         epi = -1;
       }
@@ -991,6 +992,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.slab && n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
       // the decoder's 128-channel 3x3 convs: slab variant, weights in groups of 3 taps
       if (epi == EPI_STATS) return launch_tc<128, false, 2, EPI_STATS, 3>(p, num_sms, stream);
+      if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<128, false, 2, EPI_OUT16 | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_STATS)) return launch_tc<128, false, 2, EPI_RES | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == 0) return launch_tc<128, false, 2, 0, 3>(p, num_sms, stream);
       if (epi == EPI_RES) return launch_tc<128, false, 2, EPI_RES, 3>(p, num_sms, stream);
@@ -998,6 +1000,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.slab && !n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
       // 256-column tiles: slab variant with one tap of weights per stage (experiment switch HDRVAE_SLAB_MAXN)
       if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1>(p, num_sms, stream);
+      if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_STATS, 1>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_STATS, 1>(p, num_sms, stream);
     }
 #define HDRVAE_EPI_CASE(E)                                                                       \
@@ -1011,6 +1014,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       HDRVAE_EPI_CASE(EPI_OUT2 | EPI_STATS)
       HDRVAE_EPI_CASE(EPI_RES | EPI_OUT2 | EPI_STATS)
       HDRVAE_EPI_CASE(EPI_OUT16)
+      HDRVAE_EPI_CASE(EPI_OUT16 | EPI_STATS)
       HDRVAE_EPI_CASE(EPI_OUT16 | EPI_ROWOPS)
       default: break;
     }

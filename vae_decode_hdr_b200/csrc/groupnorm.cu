@@ -166,7 +166,7 @@ template <typename TIn, typename TOut, bool kSilu, bool kMufu = false>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, int HW, int C, int px_per_block, long long x_img_stride,
-                long long y_img_stride) {
+                long long y_img_stride, float in_scale) {
   extern __shared__ float tab[];   // [2][C]
   const int img = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
@@ -182,7 +182,8 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
   const int p1 = min(HW, p0 + px_per_block);
   float a[8], b[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a[j] = tab[vi * 8 + j]; b[j] = tab[C + vi * 8 + j]; }
+  // in_scale: x is stored scaled by 1 / in_scale (a power of two: exact) — folded into the per-channel scale
+  for (int j = 0; j < 8; ++j) { a[j] = tab[vi * 8 + j] * in_scale; b[j] = tab[C + vi * 8 + j]; }
   const TIn* xin = x + (long long)img * x_img_stride;
   TOut* yout = y + (long long)img * y_img_stride;
   // 4 pixels per iteration: all loads are issued before the first use (memory-level parallelism)
@@ -234,7 +235,7 @@ static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* 
 
 template <typename TIn, typename TOut>
 static void launch_apply(const void* x, void* y, const float* scale, const float* shift, int B, int HW, int C, int chunks,
-                         int ppb, bool silu, long long xs, long long ys, cudaStream_t s) {
+                         int ppb, bool silu, long long xs, long long ys, cudaStream_t s, float in_scale = 1.f) {
   const dim3 grid(chunks, B);
   const size_t sm = 2 * C * sizeof(float);
   // exp of the SiLU on the special-function unit (default) or as a polynomial on the FMA pipe (HDRVAE_SILU_MUFU=0).
@@ -244,13 +245,13 @@ static void launch_apply(const void* x, void* y, const float* scale, const float
   if (mufu < 0) { const char* e = getenv("HDRVAE_SILU_MUFU"); mufu = (e && atoi(e) == 0) ? 0 : 1; }
   if (silu && mufu)
     gn_apply_kernel<TIn, TOut, true, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                        scale, shift, HW, C, ppb, xs, ys);
+                                                                        scale, shift, HW, C, ppb, xs, ys, in_scale);
   else if (silu)
     gn_apply_kernel<TIn, TOut, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                  scale, shift, HW, C, ppb, xs, ys);
+                                                                  scale, shift, HW, C, ppb, xs, ys, in_scale);
   else
     gn_apply_kernel<TIn, TOut, false><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                   scale, shift, HW, C, ppb, xs, ys);
+                                                                   scale, shift, HW, C, ppb, xs, ys, in_scale);
 }
 
 // Row tiling: the statistics of a (image, group) are sums over ALL ranks' rows.  gn_reduce_partials folds this
@@ -308,16 +309,23 @@ int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n
 // over ALL ranks
 int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
                               int B, int rows_px, int C, const float* gamma, const float* beta, bool silu, void* scratch,
-                              int max_chunks, double count, cudaStream_t s) {
-  HDRVAE_REQUIRE(x_dtype == DT_F32 && (y_dtype == DT_F16 || y_dtype == DT_BF16), "groupnorm (row tiling): fp32 in, 16-bit out");
+                              int max_chunks, double count, cudaStream_t s, float in_scale) {
+  HDRVAE_REQUIRE((y_dtype == DT_F16 || y_dtype == DT_BF16) && (x_dtype == DT_F32 || x_dtype == y_dtype),
+                 "groupnorm (row tiling): fp32 or operand-typed in, 16-bit out");
   float* scale = gn_scale_ptr(scratch, B, max_chunks);
   float* shift = scale + (size_t)B * C;
   gn_finalize_sums_kernel<<<B, 256, 0, s>>>(gn_sums_ptr(scratch, B, C, max_chunks), gamma, beta, scale, shift, C, count, 1e-6f);
   HDRVAE_LAUNCHED();
   int chunks, ppb;
   gn_chunking(B, rows_px, C, max_chunks, &chunks, &ppb);
-  if (y_dtype == DT_F16) launch_apply<float, __half>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s);
-  else launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s);
+  if (x_dtype == DT_F32) {
+    if (y_dtype == DT_F16) launch_apply<float, __half>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s, in_scale);
+    else launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s, in_scale);
+  } else if (y_dtype == DT_F16) {
+    launch_apply<__half, __half>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s, in_scale);
+  } else {
+    launch_apply<__nv_bfloat16, __nv_bfloat16>(x, y, scale, shift, B, rows_px, C, chunks, ppb, silu, x_img_stride, y_img_stride, s, in_scale);
+  }
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -342,9 +350,11 @@ int launch_gn_finalize_only(int B, int HW, int C, const float* gamma, const floa
 // partial_chunks > 0: the statistics partials [B][partial_chunks][32][2] are already in the scratch buffer
 // (emitted by the producing conv); otherwise a standalone statistics pass over x runs first.
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
-                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s) {
+                     const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s,
+                     float in_scale) {
   HDRVAE_REQUIRE(C % 32 == 0 && C >= 128 && C <= 2048 && (kGnThreads % (C >> 3)) == 0,
                  "groupnorm: unsupported channel count %d", C);
+  HDRVAE_REQUIRE(in_scale == 1.f || partial_chunks > 0, "groupnorm: a scaled input needs the producer's statistics");
   HDRVAE_REQUIRE(y_dtype == DT_BF16 || y_dtype == DT_F16 || y_dtype == DT_F32 || y_dtype == DT_F16X3,
                  "groupnorm: output must be a 16-bit operand type, fp32 or the fp16 hi|lo|hi operand");
   HDRVAE_REQUIRE((y_dtype != DT_F32 && y_dtype != DT_F16X3) || x_dtype == DT_F32, "groupnorm: fp32 / split outputs need fp32 input");
@@ -368,18 +378,18 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   if (y_dtype == DT_F32) {
-    launch_apply<float, float>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    launch_apply<float, float>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
   } else if (y_dtype == DT_F16X3) {
     // y_img_stride is counted in HalfSplit3 elements = 2-byte units
-    launch_apply<float, HalfSplit3>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C * 3, s);
+    launch_apply<float, HalfSplit3>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C * 3, s, in_scale);
   } else if (y_dtype == DT_F16) {
-    if (x_dtype == DT_F32) launch_apply<float, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
-    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
-    else launch_apply<__half, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    if (x_dtype == DT_F32) launch_apply<float, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
+    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
+    else launch_apply<__half, __half>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
   } else {
-    if (x_dtype == DT_F32) launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
-    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
-    else launch_apply<__half, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s);
+    if (x_dtype == DT_F32) launch_apply<float, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
+    else if (x_dtype == DT_BF16) launch_apply<__nv_bfloat16, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
+    else launch_apply<__half, __nv_bfloat16>(x, y, scale, shift, B, HW, C, chunks, ppb, silu, (long long)HW * C, (long long)HW * C, s, in_scale);
   }
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
