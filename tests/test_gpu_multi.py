@@ -64,7 +64,11 @@ def _rows_worker(rank, world, port, q):
     from vae_decode_hdr_b200.synthetic import random_decoder_state_dict, synthetic_latent
     eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
     res = []
-    for (h, w, mode) in [(32, 8, "moderate"), (8, 12, "adaptive_recovery")]:
+    # second case: slabs that do NOT tile like the whole image (only the GroupNorm partial order differs).  A mode without
+    # the logit recovery: in the logit modes a single near-saturated pixel can amplify that last-bit difference past any
+    # plain rel-L2 bound on so small an image (tests/_metrics.py); those modes are covered, with the rule-based band, by
+    # the emulated-rank tests in test_gpu_decode.py
+    for (h, w, mode) in [(32, 8, "moderate"), (8, 12, "conservative")]:
         z = synthetic_latent(1, h, w, seed=9).to(dev)
         out, st = decode_rows_sharded(eng, z, mode, 1.0)
         whole, st1 = eng.decode(z, mode, 1.0)               # every rank also decodes the whole image alone

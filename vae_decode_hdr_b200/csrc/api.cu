@@ -145,7 +145,7 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   p.res_scale = io.res_scale; p.lrelu = io.lrelu;
   p.out_dtype = io.y_dtype;
   p.out_scale = io.y_scale;
-  p.bias = pc.bias; p.bias_per_row = 0; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
+  p.bias = io.bias != nullptr ? io.bias : pc.bias; p.bias_per_row = 0; p.res_dtype = io.res_dtype; p.alpha = io.alpha;
   p.round_tf32 = io.round_tf32 ? 1 : 0;
   p.out2_dtype = io.y2_dtype; p.out2_scale = io.y2_scale;
   p.cta_group = ctx->cta_group;
@@ -154,6 +154,14 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
     p.slab = 1;
     p.tw_log2 = 3; p.TW = 8; p.TH = 16;
     p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;
+  }
+  if (io.x2 != nullptr) {
+    HDRVAE_REQUIRE(p.slab && io.pc2 != nullptr && io.pc2->ks == 1 && io.pc2->w_dtype == pc.w_dtype && io.pc2->kmul == 1 &&
+                   io.pc2->cout == pc.cout && io.xf_scale == nullptr, "run_conv: the fused 1x1 conv needs the slab form");
+    const int c2 = io.pc2->cin_pad;
+    p.a2 = io.x2; p.k2 = c2;
+    p.a2_px_stride = c2; p.a2_row_stride = (long long)W * c2; p.a2_img_stride = (long long)(H + 2 * io.x_pad) * W * c2;
+    p.b2 = io.pc2->w[0]; p.b2_row_stride = c2;
   }
   if (io.xf_scale != nullptr) {
     HDRVAE_REQUIRE(p.slab && pc.w_dtype == DT_F16 && io.x_pad == 0 && io.x_channels == 0,
@@ -332,6 +340,15 @@ static bool h_is_16bit(hdrvae_ctx* ctx) {
   return on && !ctx->high && ctx->conv_impl == HDRVAE_CONV_TCGEN05;
 }
 
+// nin_shortcut fused into conv2 (extra K blocks of the slab conv kernel: K = 9 * Cout + Cin) instead of a separate 1x1 conv
+// whose fp32 output conv2 then reads back as its residual.  HDRVAE_FUSE_NIN=0 keeps the two launches.
+static bool nin_is_fused(hdrvae_ctx* ctx, const ResW& rw, int H, int W) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HDRVAE_FUSE_NIN"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  ConvIO probe;
+  return on && rw.has_nin && !ctx->high && rw.nin_x16.w[0] != nullptr && conv_takes_slab(rw.c2, probe, H, W, ctx->conv_impl);
+}
+
 static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
   return ctx->conv_impl == HDRVAE_CONV_TCGEN05 ? reinterpret_cast<float*>(st->gn) : nullptr;
 }
@@ -385,6 +402,11 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
     // shortcut on the scaled 16-bit copy of x into hbuf, and conv2 accumulates onto it in place
     HDRVAE_TRY(run_gn(ctx, st->hbuf, h_dt, st->t, B, H * W, rw.n2, true, st, s, -1, 1.f / h_scale));
     io.x = st->t;
+    if (nin_is_fused(ctx, rw, H, W)) {
+      // x_new = conv2(t) + nin(x): ONE launch, written over the old x (whose scaled 16-bit copy is what the shortcut reads)
+      io.x2 = st->xb16; io.pc2 = &rw.nin_x16; io.bias = rw.bias_c2_nin; io.y = st->x;
+      return run_conv(ctx, rw.c2, io, B, H, W, impl, s);
+    }
     ConvIO sc; sc.x = st->xb16; sc.y = st->hbuf; sc.alpha = 1.0f / kRawOperandScale;
     HDRVAE_TRY(run_conv(ctx, rw.nin, sc, B, H, W, impl, s));
     io.y = st->hbuf; io.residual = st->hbuf;
@@ -816,8 +838,14 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
   });
   rows_stats_and_halo(st, hb, H, W, rw.c1.cout, nullptr, 0, h16 ? 2 : 4);
   rows_gn(st, hb, rw.n2, true, H, W, h_dt, 1.f / h_scale);
-  float* out = rw.has_nin ? hb : x;
+  const bool fused_nin = nin_is_fused(ctx, rw, H, W);
+  float* out = (rw.has_nin && !fused_nin) ? hb : x;
   rows_compute(st, [=](cudaStream_t s) {
+    if (fused_nin) {
+      ConvIO io; io.x = t; io.y = out; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
+      io.x2 = xb; io.pc2 = &r->nin_x16; io.bias = r->bias_c2_nin;
+      return run_conv(ctx, r->c2, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
+    }
     if (r->has_nin) {
       ConvIO sc; sc.x = xb; sc.y = hb; sc.alpha = 1.0f / kRawOperandScale; sc.x_pad = sc.y_pad = 1;
       HDRVAE_TRY(run_conv(ctx, r->nin, sc, 1, H, W, HDRVAE_CONV_TCGEN05, s));
@@ -829,7 +857,7 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
     return 0;
   });
   rows_stats_and_halo(st, out, H, W, rw.c2.cout, rw.dual_out ? xa : nullptr, rw.c2.cout);
-  if (rw.has_nin) std::swap(st->x, st->hbuf);
+  if (rw.has_nin && !fused_nin) std::swap(st->x, st->hbuf);
 }
 
 static int build_rows_program(hdrvae_rows* st) {
@@ -1070,7 +1098,15 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
     HDRVAE_TRY(norm(k + ".norm2", cout, &rw->n2));
     HDRVAE_TRY(conv(k + ".conv2", cout, cout, 3, false, op, &rw->c2));
     rw->has_nin = cin != cout;
-    if (rw->has_nin) HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, op, &rw->nin));   // reads the scaled 16-bit copy of x
+    if (rw->has_nin) {
+      HDRVAE_TRY(conv(k + ".nin_shortcut", cout, cin, 1, false, op, &rw->nin));   // reads the scaled 16-bit copy of x
+      if (!high) {
+        // the form fused into conv2: weights x 2^4 (undoes the operand scale), bias = conv2.bias + nin_shortcut.bias
+        HDRVAE_TRY(pack_conv(ctx, W(k + ".nin_shortcut.weight"), nullptr, cout, cin, 1, false, 1.0f / kRawOperandScale, op, &rw->nin_x16, s));
+        HDRVAE_TRY(dev_alloc(ctx, rw->c2.cout_pad * sizeof(float), (void**)&rw->bias_c2_nin));
+        HDRVAE_TRY(launch_add_vectors(rw->c2.bias, rw->nin.bias, rw->bias_c2_nin, rw->c2.cout_pad, s));
+      }
+    }
     return 0;
   };
 

@@ -72,6 +72,15 @@ struct GemmParams {
                     // zero-fills the tail of the last K block, the packed weights hold zeros there
   int ntaps;
   int tap_dy[9], tap_dx[9];
+  // Extra K blocks from a SECOND tensor (slab form only): after the 9 taps of A the kernel accumulates
+  //   sum_{c < k2} A2[n, y, x, c] * B2[col][c]
+  // into the same tile — a 1x1 conv of another tensor fused into this conv (the decoder's nin_shortcut, whose output is
+  // the residual of conv2: no separate launch, no fp32 round trip).  A2 has A's spatial shape and halo rows (y_pad).
+  const void* a2;
+  long long a2_img_stride, a2_row_stride, a2_px_stride;
+  int k2;                    // channels of A2 (multiple of 64 elements of 16 bits), 0: none
+  const void* b2;            // [cols][k2] K-major, same element type
+  long long b2_row_stride;
   int n_cols;       // valid output columns (Cout)
   // tiling of the M dimension: TW x TH = 128 pixels
   int tw_log2, TW, TH, tiles_x, tiles_y, n_tiles_n;
@@ -141,6 +150,19 @@ __device__ __forceinline__ float silu_f(float v) {
 }
 // the same with exp on the special-function unit (ex2 + rcp): fewer instructions, two XU operations per element
 __device__ __forceinline__ float silu_mufu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// ONE XU operation per element: ex2 on the special-function unit, the reciprocal of d = 1 + e^-v (d >= 1) by two Newton
+// steps on the FMA pipe from the integer-subtraction first guess (relative error 7.6e-6: far below the 16-bit output
+// rounding).  ncu on the streaming GroupNorm kernel: XU pipe 53 % busy, DRAM 57 %, issue 40 % with ex2 + rcp — neither
+// memory nor any one pipe saturated, the XU latency chain is what the warps wait on.
+__device__ __forceinline__ float silu_nr(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(-v * 1.4426950408889634f, 80.f)));
+  const float d = 1.f + e;
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  return v * r;
+}
 #endif
 
 // cudaFuncSetAttribute is per device: remember per (call site, device) whether the opt-in shared-memory size has
@@ -157,7 +179,7 @@ struct PerDeviceOnce {
 };
 
 struct TensorMapPair {
-  CUtensorMap a, b;
+  CUtensorMap a, b, a2, b2;
 };
 
 }  // namespace hdrvae

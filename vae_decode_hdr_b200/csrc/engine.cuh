@@ -16,6 +16,7 @@ void choose_tile(int H, int W, GemmParams* p);
 int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStream_t s);
 int launch_pack_weight(const float* w, void* out, int out_dtype, int cout, int cin, int ks, int ntaps, int cin_pad,
                        const int* tap_mask, float scale, cudaStream_t s, int split3 = 0);
+int launch_add_vectors(const float* a, const float* b, float* c, int n, cudaStream_t s);
 int launch_split3(const float* x, long long x_ld, void* out, long long out_ld, long long n, int C, float scale, int order,
                   cudaStream_t s);
 int launch_latent_to_nhwc(const float* z, void* out, int out_dtype, int B, int C, int HW, int cpad, cudaStream_t s);
@@ -97,6 +98,9 @@ struct NormW {
 struct ResW {
   NormW n1, n2;
   PackedConv c1, c2, nin;
+  PackedConv nin_x16;        // nin_shortcut weights x 2^4 (its operand is the 2^-4 scaled 16-bit copy of x): the form that is
+                             // fused into conv2 as extra K blocks
+  float* bias_c2_nin = nullptr;   // conv2.bias + nin_shortcut.bias
   bool has_nin = false;
   bool dual_out = false;     // the block's output is also the operand of the next (upsample) conv: emit the scaled 16-bit copy
 };
@@ -161,6 +165,11 @@ struct ConvIO {
   // fused GroupNorm + SiLU: x is the RAW fp32 tensor [B,H,W,cin]; the conv applies silu(x * scale + shift) itself
   const float* xf_scale = nullptr; const float* xf_shift = nullptr;
   bool xf_silu = true;
+  // fused 1x1 conv of a second tensor (slab form): y += conv1x1(x2, *pc2); x2 has x's spatial shape / halo rows and
+  // pc2->cin_pad channels per pixel (dense); `bias` replaces the conv's own bias when set
+  const void* x2 = nullptr;
+  const PackedConv* pc2 = nullptr;
+  const float* bias = nullptr;
 };
 
 // true when run_conv would take the slab form of the tensor-core kernel (needed by the fused GroupNorm path)

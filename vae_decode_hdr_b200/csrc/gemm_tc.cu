@@ -130,7 +130,7 @@ enum : int {
 template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0, bool XF = false>
 __global__ void __launch_bounds__(kNumThreads + (XF ? kXfThreads : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB, XF>;
   constexpr int kAT = Cfg::kATile;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position in the CTA pair (0 = leader)
@@ -162,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (SLAB && p.k2 > 0) { ptx::prefetch_tensormap(&tmA2); ptx::prefetch_tensormap(&tmB2); }
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -194,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int w_first = blockIdx.x / CG, w_step = gridDim.x / CG;
   const int kb_per_tap = p.k_per_tap / kElemsPerRow;
   const int num_kb = p.ntaps * kb_per_tap;
+  const int kb2_blocks = SLAB ? p.k2 / kElemsPerRow : 0;      // extra K blocks from the second tensor (fused 1x1 conv)
 
   // Producer and MMA issuer run as whole (converged) warps with one elected lane issuing: loop state and
   // addresses are then warp-uniform and stay in the uniform datapath that UTMALDG / UTCHMMA read from (a
@@ -237,6 +239,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint8_t* sb = smem_b + stage * Cfg::kBBytes;
               if (CG == 2) ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, tg * SLAB);
               else ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * kElemsPerRow, n0, tg * SLAB);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if constexpr (!XF) {
+          // fused 1x1 conv of the second tensor: per K block its slab (only the centre pixels are used) and ONE tap of
+          // its weights
+          for (int kb = 0; kb < kb2_blocks; ++kb) {
+            ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
+            if (ptx::elect_one()) {
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
+              uint8_t* sa = smem_slab + ss * kSlabBytes;
+              if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA2, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+              else ptx::tma_load_4d(sa, &tmA2, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+            }
+            __syncwarp();
+            if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (ptx::elect_one()) {
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * (BLOCK_N / CG) * kRowBytes));
+              uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+              if (CG == 2) ptx::tma_load_2d_pair(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+              else ptx::tma_load_2d(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -313,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
               if (tg == 9 / SLAB - 1) {
                 if (CG == 2) ptx::umma_commit_pair(&slab_empty_bar[ss]); else ptx::umma_commit(&slab_empty_bar[ss]);
-                if (kb == kb_per_tap - 1) {
+                if (kb == kb_per_tap - 1 && kb2_blocks == 0) {
                   if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
                 }
               }
@@ -321,6 +347,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+        }
+        for (int kb = 0; kb < kb2_blocks; ++kb) {
+          // fused 1x1 conv: the centre tap of the second tensor's slab against one tap of its weights
+          ptx::mbar_wait(&slab_full_bar[ss], sphase);
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
+            const uint32_t sa = ptx::smem_u32(smem_slab + ss * Cfg::kSlabBuf);
+            const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
+            const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + (uint32_t)((Cfg::kPitch + 1) * kRowBytes), Cfg::kPitch * kRowBytes);
+            const uint64_t db = ptx::make_sw128_kmajor_desc(sb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (CG == 2) ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+              else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+            }
+            if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+            if (CG == 2) ptx::umma_commit_pair(&slab_empty_bar[ss]); else ptx::umma_commit(&slab_empty_bar[ss]);
+            if (kb == kb2_blocks - 1) {
+              if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -833,6 +884,29 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int 
     HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (K=%d cols=%d)", (int)r,
                    p.k_per_tap * p.ntaps, p.n_cols);
   }
+  memset(&maps->a2, 0, sizeof maps->a2);
+  memset(&maps->b2, 0, sizeof maps->b2);
+  if (p.k2 > 0) {
+    HDRVAE_REQUIRE(slab && !xf && eb == 2 && p.k2 % row_elems == 0 && p.a2 != nullptr && p.b2 != nullptr,
+                   "gemm_tc: the fused second tensor needs the 16-bit slab form and whole K blocks");
+    HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(p.a2) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.b2) & 15) == 0 &&
+                   p.a2_px_stride % vec == 0 && p.a2_row_stride % vec == 0 && p.a2_img_stride % vec == 0 && p.b2_row_stride % vec == 0,
+                   "gemm_tc: second-tensor pointers / strides must be 16-byte aligned");
+    cuuint64_t dims[4] = {(cuuint64_t)p.k2, (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)p.a2_px_stride * eb, (cuuint64_t)p.a2_row_stride * eb, (cuuint64_t)p.a2_img_stride * eb};
+    cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)kSlabPitch, (cuuint32_t)kSlabRows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&maps->a2, dt, 4, const_cast<void*>(p.a2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A2) failed: %d", (int)r);
+    cuuint64_t bdims[2] = {(cuuint64_t)p.k2, (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols)};
+    cuuint64_t bstrides[1] = {(cuuint64_t)p.b2_row_stride * eb};
+    cuuint32_t bbox[2] = {(cuuint32_t)row_elems, (cuuint32_t)block_n};
+    cuuint32_t bestr[2] = {1, 1};
+    r = enc(&maps->b2, dt, 2, const_cast<void*>(p.b2), bdims, bstrides, bbox, bestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B2) failed: %d", (int)r);
+  }
   return 0;
 }
 
@@ -886,7 +960,8 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, maps.a, maps.b, p));
+  HDRVAE_REQUIRE(p.k2 == 0 || (SLAB > 0 && !XF), "gemm_tc: a fused second tensor needs the slab form");
+  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, maps.a, maps.b, maps.a2, maps.b2, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -11,6 +11,8 @@
 //   gn_apply    : y = silu(x * a[c] + b[c]); x fp32 (residual / conv stream) or 16-bit, y fp16/bf16 (the next
 //                 conv's tensor-core operand), 16-byte accesses.
 // Algorithmic traffic in the decoder: 4 B read + 2 B written per element.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hdrvae {
@@ -162,7 +164,13 @@ gn_finalize_kernel(const float* __restrict__ partial, int n_chunks, const float*
 }
 
 
-template <typename TIn, typename TOut, bool kSilu, bool kMufu = false>
+// kExp: how the SiLU's exp / reciprocal are evaluated — 0 polynomial (FMA pipe only), 1 ex2 + rcp (two XU ops), 2 ex2 +
+// Newton reciprocal (one XU op)
+template <int kExp> __device__ __forceinline__ float silu_sel(float v) {
+  return kExp == 1 ? silu_mufu(v) : kExp == 2 ? silu_nr(v) : silu_f(v);
+}
+
+template <typename TIn, typename TOut, bool kSilu, int kMufu = 0>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, int HW, int C, int px_per_block, long long x_img_stride,
@@ -186,18 +194,20 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
   for (int j = 0; j < 8; ++j) { a[j] = tab[vi * 8 + j] * in_scale; b[j] = tab[C + vi * 8 + j]; }
   const TIn* xin = x + (long long)img * x_img_stride;
   TOut* yout = y + (long long)img * y_img_stride;
-  // 4 pixels per iteration: all loads are issued before the first use (memory-level parallelism)
+  // U pixels per iteration: all loads are issued before the first use (memory-level parallelism).  (8 in flight for
+  // the 16-bit-input layers measured no faster than 4: those layers are bound by the XU latency chain, not by loads.)
+  constexpr int U = 4;
   int p = p0 + p_off;
-  for (; p + 3 * p_step < p1; p += 4 * p_step) {
-    float v[4][8];
+  for (; p + (U - 1) * p_step < p1; p += U * p_step) {
+    float v[U][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Ld8<TIn>::ld(xin + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
+    for (int u = 0; u < U; ++u) Ld8<TIn>::ld(xin + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[u][j] = fmaf(v[u][j], a[j], b[j]);
-        if (kSilu) v[u][j] = kMufu ? silu_mufu(v[u][j]) : silu_f(v[u][j]);
+        if (kSilu) v[u][j] = silu_sel<kMufu>(v[u][j]);
       }
       store8<TOut>(yout, (long long)(p + u * p_step), vpp, vi, v[u]);
     }
@@ -208,7 +218,7 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] = fmaf(v[j], a[j], b[j]);
-      if (kSilu) v[j] = kMufu ? silu_mufu(v[j]) : silu_f(v[j]);
+      if (kSilu) v[j] = silu_sel<kMufu>(v[j]);
     }
     store8<TOut>(yout, (long long)p, vpp, vi, v);
   }
@@ -241,11 +251,17 @@ static void launch_apply(const void* x, void* y, const float* scale, const float
   // exp of the SiLU on the special-function unit (default) or as a polynomial on the FMA pipe (HDRVAE_SILU_MUFU=0).
   // This kernel is not purely HBM bound: same-box A/B of the C2 step 44.3 ms (polynomial) vs 43.4 ms (ex2 + rcp).  The
   // polynomial exists for the experimental fused operand transform, where the XU pipe is the scarce one.
+  // HDRVAE_SILU_MUFU: 0 polynomial exp on the FMA pipe, 1 ex2 + rcp on the special-function unit, 2 (default for 16-bit
+  // outputs) ex2 + Newton reciprocal.  fp32 / hi|lo|hi outputs (high-precision mode) always take ex2 + rcp.
   static int mufu = -1;
-  if (mufu < 0) { const char* e = getenv("HDRVAE_SILU_MUFU"); mufu = (e && atoi(e) == 0) ? 0 : 1; }
-  if (silu && mufu)
-    gn_apply_kernel<TIn, TOut, true, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                        scale, shift, HW, C, ppb, xs, ys, in_scale);
+  if (mufu < 0) { const char* e = getenv("HDRVAE_SILU_MUFU"); mufu = e ? atoi(e) : 2; }
+  const int how = sizeof(TOut) == 2 && !std::is_same<TOut, HalfSplit3>::value ? mufu : 1;
+  if (silu && how == 2)
+    gn_apply_kernel<TIn, TOut, true, 2><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
+                                                                     scale, shift, HW, C, ppb, xs, ys, in_scale);
+  else if (silu && how == 1)
+    gn_apply_kernel<TIn, TOut, true, 1><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
+                                                                     scale, shift, HW, C, ppb, xs, ys, in_scale);
   else if (silu)
     gn_apply_kernel<TIn, TOut, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
                                                                   scale, shift, HW, C, ppb, xs, ys, in_scale);

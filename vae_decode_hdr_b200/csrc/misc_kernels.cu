@@ -22,6 +22,18 @@ int launch_to_f32(const void* src, int dtype, float* dst, long long n, cudaStrea
   return 0;
 }
 
+// ------------------------------------------------------------------ c = a + b (bias vectors)
+__global__ void add_vectors_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) c[i] = a[i] + b[i];
+}
+int launch_add_vectors(const float* a, const float* b, float* c, int n, cudaStream_t s) {
+  add_vectors_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, b, c, n);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ weight repack
 // OIHW fp32 [Cout][Cin][ks][ks] -> K-major bf16 [Cout][ntaps][cin_pad]; output tap t is the SUM of
 // the source kernel positions set in tap_mask[t] (bit ky*ks+kx).  Plain 3x3: mask = 1<<t.
