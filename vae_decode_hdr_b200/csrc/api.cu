@@ -157,19 +157,11 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   }
   if (io.x2 != nullptr) {
     HDRVAE_REQUIRE(p.slab && io.pc2 != nullptr && io.pc2->ks == 1 && io.pc2->w_dtype == pc.w_dtype && io.pc2->kmul == 1 &&
-                   io.pc2->cout == pc.cout && io.xf_scale == nullptr, "run_conv: the fused 1x1 conv needs the slab form");
+                   io.pc2->cout == pc.cout, "run_conv: the fused 1x1 conv needs the slab form");
     const int c2 = io.pc2->cin_pad;
     p.a2 = io.x2; p.k2 = c2;
     p.a2_px_stride = c2; p.a2_row_stride = (long long)W * c2; p.a2_img_stride = (long long)(H + 2 * io.x_pad) * W * c2;
     p.b2 = io.pc2->w[0]; p.b2_row_stride = c2;
-  }
-  if (io.xf_scale != nullptr) {
-    HDRVAE_REQUIRE(p.slab && pc.w_dtype == DT_F16 && io.x_pad == 0 && io.x_channels == 0,
-                   "run_conv: the fused GroupNorm operand needs the fp16 slab form");
-    p.xf_scale = io.xf_scale; p.xf_shift = io.xf_shift; p.xf_C = pc.cin; p.xf_silu = io.xf_silu ? 1 : 0;
-    // the raw fp32 tensor is dense [B,H,W,cin]
-    p.a_px_stride = pc.cin; p.a_row_stride = (long long)W * pc.cin; p.a_img_stride = (long long)H * W * pc.cin;
-    p.a_k_valid = pc.cin;
   }
   const int phases = pc.upsample ? 4 : 1;
   const int OH = pc.upsample ? 2 * H : H, OW = pc.upsample ? 2 * W : W;
@@ -353,34 +345,14 @@ static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
   return ctx->conv_impl == HDRVAE_CONV_TCGEN05 ? reinterpret_cast<float*>(st->gn) : nullptr;
 }
 
-// GroupNorm + SiLU in front of a conv: either the separate streaming kernel (x -> t, 16-bit) or, when the conv takes
-// the slab form and HDRVAE_FUSE_GN is on, only the statistics -> scale / shift step: the conv then reads the raw fp32
-// tensor and normalises while staging its operand (io->xf_*), and the 16-bit tensor never exists in HBM.
+// GroupNorm + SiLU in front of a conv: the streaming kernel x -> t (16-bit operand, or hi|lo|hi in the high-precision mode).
+// (Round 1 also carried an experimental variant that normalised inside the conv's operand path — correct but 10 % slower,
+// DESIGN.md §8 — removed in round 2; last present in commit 93846d6.)
 static int gn_before_conv(hdrvae_ctx* ctx, const void* x, const NormW& nw, const PackedConv& pc, ConvIO* io, DecState* st,
                           int B, int H, int W, cudaStream_t s, int x_dtype = DT_F32, float x_scale = 1.f) {
-  static int fuse = -1;
-  static int fuse_min_n = 256;      // 128-column convs: the transform (MUFU bound) takes longer than their MMAs
-  if (fuse < 0) {
-    const char* e = getenv("HDRVAE_FUSE_GN"); fuse = (e && atoi(e) != 0) ? 1 : 0;
-    const char* m = getenv("HDRVAE_FUSE_GN_MINN"); if (m) fuse_min_n = atoi(m);
-  }
-  const bool fusable = fuse && !ctx->high && x_dtype == DT_F32 && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && st->pending > 0 &&
-                       pc.cout_pad >= fuse_min_n && io->y2 == nullptr && conv_takes_slab(pc, *io, H, W, ctx->conv_impl) &&
-                       !(pc.cout_pad == 128 && io->residual != nullptr);
-  if (!fusable) {
-    HDRVAE_TRY(run_gn(ctx, x, x_dtype, st->t, B, H * W, nw, true, st, s, -1, x_scale));
-    io->x = st->t;
-    return 0;
-  }
-  char pname[64];
-  snprintf(pname, sizeof pname, "groupnorm statistics C=%d @%dx%d", nw.C, B, H * W);
-  ProfScope prof(pname, 0.0, 0.0, s);
-  const int partials = st->pending;
-  st->pending = 0;
-  HDRVAE_TRY(launch_gn_finalize_only(B, H * W, nw.C, nw.gamma, nw.beta, st->gn, st->gn_chunks, partials, &io->xf_scale,
-                                     &io->xf_shift, s));
-  io->x = x;
-  io->xf_silu = true;
+  (void)pc;
+  HDRVAE_TRY(run_gn(ctx, x, x_dtype, st->t, B, H * W, nw, true, st, s, -1, x_scale));
+  io->x = st->t;
   return 0;
 }
 

@@ -118,10 +118,6 @@ struct GemmParams {
   // 32 channel groups: stats[((img * tiles_per_img + m_tile) * 32 + group) * 2 + {0,1}], or null
   float* stats;
   int stats_chunks_per_img, stats_chunk0;
-  // operand transform (slab form): `a` is the RAW fp32 tensor (strides in fp32 elements) and the kernel applies
-  // y = [silu](x * xf_scale[img][c] + xf_shift[img][c]) while staging it as the fp16 operand (fused GroupNorm + SiLU)
-  const float* xf_scale; const float* xf_shift;
-  int xf_C, xf_silu;
   int slab;          // 3x3 conv with narrow output (<= 64 columns): 8x16-pixel tiles whose 10x18 activation slab is loaded
                      // ONCE per K block and read by the 9 taps as shifted descriptors (gemm_tc.cu "slab" variant)
   int cta_group;     // 0 = library default (CTA pairs), 1 = single CTA, 2 = CTA pair (tcgen05 cta_group::2)
@@ -129,11 +125,9 @@ struct GemmParams {
 };
 
 #ifdef __CUDACC__
-// SiLU for the GroupNorm + SiLU paths (the streaming kernel and the fused operand transform use the SAME function, so
-// fused and un-fused decodes agree bit for bit).  exp(-v) is evaluated on the FMA pipe: round-to-nearest split
-// t = n + f by the 1.5 * 2^23 trick, 2^f as a degree-6 polynomial on [-0.5, 0.5] (relative error < 3e-8), exponent
-// inserted with integer arithmetic — the special-function unit is left with the one reciprocal.  (With ex2 + rcp on
-// the XU pipe the fused transform ran that pipe at 83 % and halved the tensor utilisation of the conv: ncu.)
+// SiLU variants of the GroupNorm + SiLU kernel (HDRVAE_SILU_MUFU).  silu_f: exp(-v) on the FMA pipe — round-to-nearest
+// split t = n + f by the 1.5 * 2^23 trick, 2^f as a degree-6 polynomial on [-0.5, 0.5] (relative error < 3e-8), exponent
+// inserted with integer arithmetic — the special-function unit is left with the one reciprocal.
 __device__ __forceinline__ float silu_f(float v) {
   float t = fminf(fmaxf(-v * 1.4426950408889634f, -125.f), 125.f);
   const float tm = t + 12582912.f;                       // n = round(t) sits in the low mantissa bits

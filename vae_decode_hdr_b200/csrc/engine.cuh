@@ -36,8 +36,6 @@ size_t gn_scratch_bytes(int B, int C, int max_chunks);
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
                      const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s,
                      float in_scale = 1.f);
-int launch_gn_finalize_only(int B, int HW, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
-                            int partial_chunks, const float** scale_out, const float** shift_out, cudaStream_t s);
 size_t epilogue_scratch_bytes(int B, int H, int W);
 void* epilogue_raw_stats_ptr(void* scratch, int B, int H, int W);
 hdrvae_stats* epilogue_stats_dev_ptr(void* scratch, int B, int H, int W);
@@ -162,9 +160,6 @@ struct ConvIO {
   const float* residual2 = nullptr;
   float lrelu = 0.f;              // LeakyReLU slope (0: none)
   int n_store = 0;                // channels of y stored (multiple of 4; 0: all)
-  // fused GroupNorm + SiLU: x is the RAW fp32 tensor [B,H,W,cin]; the conv applies silu(x * scale + shift) itself
-  const float* xf_scale = nullptr; const float* xf_shift = nullptr;
-  bool xf_silu = true;
   // fused 1x1 conv of a second tensor (slab form): y += conv1x1(x2, *pc2); x2 has x's spatial shape / halo rows and
   // pc2->cin_pad channels per pixel (dense); `bias` replaces the conv's own bias when set
   const void* x2 = nullptr;
@@ -172,7 +167,7 @@ struct ConvIO {
   const float* bias = nullptr;
 };
 
-// true when run_conv would take the slab form of the tensor-core kernel (needed by the fused GroupNorm path)
+// true when run_conv would take the slab form of the tensor-core kernel (needed by the fused nin_shortcut path)
 bool conv_takes_slab(const PackedConv& pc, const ConvIO& io, int H, int W, int impl);
 
 int dev_alloc(hdrvae_ctx* ctx, size_t bytes, void** out);

@@ -42,37 +42,20 @@ constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 4 * 64 * 4 
 // byte of shared memory keeps in flight doubles, which is what bounds the layers with <= 128 output columns.
 constexpr int kSlabRows = 18, kSlabPitch = 16;
 constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 36 KB
-// XF (slab form only): the A operand is the RAW fp32 tensor; 4 extra warps apply y = silu(x * scale + shift)
-// (GroupNorm + SiLU with the per-(image, channel) scale / shift of gn_finalize) while converting the slab to the fp16
-// swizzled layout the MMAs read, so the normalised 16-bit tensor never goes through HBM.
-constexpr int kXfThreads = 128;
-constexpr int kRawSlabBytes = kSlabRows * 10 * 64 * 4;            // 18 rows x 10 pixels x 64 channels fp32 = 45 KB
-// The transform warps write the fp16 slab themselves, so it can be packed at a 10-line pitch (a TMA box forces 16):
-// 22.5 KB instead of 36 KB, which is what lets a SECOND raw buffer fit (raw TMA of K block k+1 overlaps the transform
-// of k).  Descriptors may start on any 128-byte line, so SBO = 1280 B is as valid as 2048 B.
-constexpr int kXfPitch = 10;
-constexpr int kXfSlabBytes = 23 * 1024;                            // 18 x 10 lines x 128 B = 23 040, padded
-// The raw fp32 pixels are read by the transform warps straight from global memory (6 pixel-lines = 6 x 32 B in flight
-// per thread): staging them in shared memory through TMA was measured first — one 45 KB raw buffer serialises the HBM
-// latency with the transform (ncu: the transform warps spend 43 % of their time waiting for the raw TMA), two leave
-// only 3 weight stages — so no raw buffer at all, three fp16 slabs and the full weight ring instead.
-constexpr int kXfRawStages = 0;
-template <int BLOCK_N, int CG, int KSUB, int SLAB = 0, bool XF = false>
+template <int BLOCK_N, int CG, int KSUB, int SLAB = 0>
 struct TcConfig {
   static constexpr int kATile = kABytes;
   static constexpr int kBBytes = (SLAB ? SLAB : 1) * (BLOCK_N / CG) * kRowBytes;   // one B stage staged by this CTA
   static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block (tap-reload form)
   static constexpr int kStageBytes = SLAB ? kBBytes : KSUB * kSubBytes;
   // narrow tiles have short MMAs (a slab feeds 36 MMAs of 32 cycles): three slabs in flight cover the TMA latency
-  static constexpr int kSlabStages = SLAB ? ((BLOCK_N <= 64 || XF) ? 3 : 2) : 0;
-  static constexpr int kRawBytes = XF ? kXfRawStages * kRawSlabBytes : 0;
-  static constexpr int kSlabBuf = XF ? kXfSlabBytes : kSlabBytes;   // bytes of one fp16 slab buffer
-  static constexpr int kPitch = XF ? kXfPitch : kSlabPitch;          // 128-byte lines per slab row
-  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBuf - kRawBytes) / kStageBytes;
+  static constexpr int kSlabStages = SLAB ? (BLOCK_N <= 64 ? 3 : 2) : 0;
+  static constexpr int kSlabBuf = kSlabBytes;                        // bytes of one fp16 slab buffer
+  static constexpr int kPitch = kSlabPitch;                          // 128-byte lines per slab row
+  static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBuf) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two: 64 ... 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBuf + kRawBytes + kSmemFixed;
-  static_assert(!XF || SLAB > 0, "the operand transform exists in the slab form only");
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBuf + kSmemFixed;
   static_assert(kStages >= (SLAB ? 2 : 3) && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
   static_assert(SLAB == 0 || ((SLAB == 9 || SLAB == 3 || SLAB == 1) && KSUB == 1), "the slab variant stages 9, 3 or 1 taps of B per pipeline slot");
 };
@@ -127,11 +110,11 @@ enum : int {
   EPI_EXPSUM = 512,  // attention pass 2: exp(score - row max) as the 16-bit output + per-row sums (row_mode 2)
 };
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0, bool XF = false>
-__global__ void __launch_bounds__(kNumThreads + (XF ? kXfThreads : 0), 1)
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0>
+__global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
-  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB, XF>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
   constexpr int kAT = Cfg::kATile;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // position in the CTA pair (0 = leader)
   constexpr int kStages = Cfg::kStages;
@@ -168,8 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
-      // XF: a slab is ready when the transform warps of every CTA of the pair have written it
-      ptx::mbar_init(&slab_full_bar[i], XF ? CG * (kXfThreads / 32) : 1);
+      ptx::mbar_init(&slab_full_bar[i], 1);
       ptx::mbar_init(&slab_empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -218,20 +200,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int bk0 = (int)(img * p.b_img_k_stride);       // split-K: this image's K range of B
       if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
-          if constexpr (XF) {
-            // the transform warps fetch the raw pixels themselves; the producer only streams the weights
-          } else {
-            ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
-            if (ptx::elect_one()) {
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
-              uint8_t* sa = smem_slab + ss * kSlabBytes;
-              // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
-              if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-              else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-            }
-            __syncwarp();
-            if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+          ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
+            uint8_t* sa = smem_slab + ss * kSlabBytes;
+            // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
+            if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+            else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
           }
+          __syncwarp();
+          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
           for (int tg = 0; tg < 9 / SLAB; ++tg) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (ptx::elect_one()) {
@@ -244,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
-        if constexpr (!XF) {
+        {
           // fused 1x1 conv of the second tensor: per K block its slab (only the centre pixels are used) and ONE tap of
           // its weights
           for (int kb = 0; kb < kb2_blocks; ++kb) {
@@ -562,9 +540,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         continue;
       }
       // Software pipeline over the warp's chunks: the TMEM load of chunk ci+1 is issued as soon as the registers of
-      // chunk ci have gone to the transpose patch, so it overlaps the store phase.  (Prefetching the next chunk's
-      // residual the same way was measured 13 % SLOWER on the 128-channel layers: it competes with the stores.)
-      float4 rres[8];
+      // chunk ci have gone to the transpose patch, so it overlaps the store phase.  ncu on the in-place-residual
+      // 128 -> 128 conv (profiles/r02_ncu_conv128_residual_summary.txt): tensor pipe 50 %, DRAM 48 %, the epilogue warps
+      // stall on the first use of the second chunk's residual (long scoreboard, 12 % of all samples).  Both ways of
+      // fetching it earlier were measured SLOWER: issuing the next chunk's loads in the middle of a chunk (-13 %, round 1:
+      // they queue behind the stores) and fetching the whole tile's residual before the accumulator wait (kPre = 2:
+      // 1.55 -> 2.0 ms, round 2: 64 more live registers spill at the 168-register cap of a 320-thread CTA).
+      constexpr int kPre = 1;
+      float4 rres_buf[kPre][8];
       auto load_res = [&](int ci, float4 (&dst)[8]) {
         if (!has_res_f32) return;
         const int colx = cbase + ci * 32 + slot * 4;
@@ -573,17 +556,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = 0; it < 8; ++it)
           if (cm >> it & 1) dst[it] = *reinterpret_cast<const float4*>(resf + poff[it] + colx);   // plain load: may alias out
       };
-      load_res(0, rres);
+      load_res(0, rres_buf[0]);
+      if (kPre == 2) load_res(1, rres_buf[kPre - 1]);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after_sync();
       uint32_t v[32];
       ptx::tmem_ld_32x32(t_row + cbase, v);
-#pragma unroll 1
+#pragma unroll(kPre == 2 ? 2 : 1)
       for (int ci = 0; ci < kChunksPerWarp; ++ci) {
         const int c0 = cbase + ci * 32;
         const int col = c0 + slot * 4;                    // first of this lane's 4 columns (tile-relative)
         const uint32_t cmask = (n0 + col) < n_store ? pmask : 0u;   // n_cols % 32 == 0 and n_store % 4 == 0 on every call site
-        if (ci > 0) load_res(ci, rres);                   // residual: issued first, overlaps the TMEM wait / transpose
+        float4 (&rres)[8] = rres_buf[kPre == 2 ? ci : 0];
+        if (ci > 0 && kPre == 1) load_res(ci, rres);      // residual: issued first, overlaps the TMEM wait / transpose
         if (ci > 0 && (p.dbg & 4)) ptx::tmem_ld_32x32(t_row + c0, v);   // diagnostics: un-pipelined TMEM load
         float4 rres2[8];
         if (has_res2) {
@@ -711,95 +696,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
-  if constexpr (XF) {
-    if (warp >= 2 + kEpilogueThreads / 32) {
-      // ---------------------------------------------------------- operand transform (4 warps): raw fp32 slab ->
-      // y = silu(x * scale + shift) -> fp16 slab in the SWIZZLE_128B layout the MMAs read.  Thread t owns the 8
-      // channels 8 (t & 7) .. +7 of every 16th pixel-line it visits, so its scale / shift live in registers.
-      const int xt = threadIdx.x - (kNumThreads);
-      const int c8 = xt & 7;
-      int ss = 0;
-      uint32_t sphase = 0;
-      for (int tile = w_first; tile < num_tiles; tile += w_step) {
-        const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
-        const bool tile_live = mt < m_tiles;
-        const int img = mt / tiles_per_img;
-        const int rem = mt - img * tiles_per_img;
-        const int ty = rem / p.tiles_x;
-        const int tx = rem - ty * p.tiles_x;
-        const int x0 = tx * p.TW, y0 = ty * p.TH;
-        for (int kb = 0; kb < kb_per_tap; ++kb) {
-          float sc[8], sh[8];
-          {
-            const int ch = kb * 64 + c8 * 8;
-            const bool ok = tile_live && ch < p.xf_C;
-            const float4* ps = reinterpret_cast<const float4*>(p.xf_scale + (long long)(tile_live ? img : 0) * p.xf_C + (ok ? ch : 0));
-            const float4* pb = reinterpret_cast<const float4*>(p.xf_shift + (long long)(tile_live ? img : 0) * p.xf_C + (ok ? ch : 0));
-            const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
-            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-            sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
-            if (!ok) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; }
-            }
-          }
-          ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
-          uint8_t* dst = smem_slab + ss * Cfg::kSlabBuf;
-          // 180 pixel-lines (18 rows x 10 pixels of the halo slab), 16 per pass over the 128 threads, kUnroll lines
-          // in flight per thread: 8 threads read the 256 contiguous bytes of one pixel's 64 fp32 channels
-          const bool ch_ok = (kb * 64 + c8 * 8) < p.xf_C;
-          const float* xin = reinterpret_cast<const float*>(p.a) + (long long)(tile_live ? img : 0) * p.a_img_stride +
-                             kb * 64 + c8 * 8;
-          constexpr int kLines = kSlabRows * 10, kStep = kXfThreads / 8, kUnroll = 6;
-          for (int pl0 = xt >> 3; pl0 < kLines; pl0 += kStep * kUnroll) {
-            float4 a0[kUnroll], a1[kUnroll];
-            bool inside[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-              const int pl = pl0 + u * kStep;
-              const int r = pl / 10, pc = pl - r * 10;
-              const int gy = y0 - 1 + r, gx = x0 - 1 + pc;
-              inside[u] = pl < kLines && tile_live && ch_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-              a0[u] = make_float4(0.f, 0.f, 0.f, 0.f); a1[u] = a0[u];
-              if (inside[u]) {
-                const float4* src = reinterpret_cast<const float4*>(xin + (long long)gy * p.a_row_stride + (long long)gx * p.a_px_stride);
-                a0[u] = __ldg(src); a1[u] = __ldg(src + 1);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-              const int pl = pl0 + u * kStep;
-              if (pl >= kLines) break;
-              const int r = pl / 10, pc = pl - r * 10;
-              float v[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
-              uint4 o;
-              uint32_t* w = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[j] = fmaf(v[j], sc[j], sh[j]);
-                if (p.xf_silu) v[j] = silu_f(v[j]);
-                if (!inside[u]) v[j] = 0.f;                 // conv padding is zero AFTER the normalisation
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) w[e] = pack_f16x2(v[2 * e], v[2 * e + 1]);
-              // SWIZZLE_128B is a function of the absolute address: 16-byte chunk index XOR (address bits 7..9)
-              uint8_t* lp = dst + (r * kXfPitch + pc) * kRowBytes;
-              const uint32_t la = ptx::smem_u32(lp);
-              *reinterpret_cast<uint4*>(lp + ((c8 ^ ((la >> 7) & 7)) << 4)) = o;
-            }
-          }
-          ptx::fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core reads
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 2) ptx::mbar_arrive_cluster_release(&slab_full_bar[ss], 0);   // the leader's MMA warp waits on its own barrier
-            else ptx::mbar_arrive(&slab_full_bar[ss]);
-          }
-          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
-        }
-      }
-    }
-  }
-
   ptx::tc_fence_before_sync();
   if (CG == 2) ptx::cluster_sync_all(); else __syncthreads();    // the peer may still be read by the leader's MMAs
   if (warp == 1) {
@@ -827,7 +723,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int slab = 0, bool xf = false) {
+static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int slab = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   HDRVAE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   const int eb = dt_bytes(p.ab_dtype);
@@ -839,19 +735,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int 
                  "gemm_tc: operand pointers must be 16-byte aligned");
   HDRVAE_REQUIRE(p.a_px_stride % vec == 0 && p.a_row_stride % vec == 0 && p.a_img_stride % vec == 0 && p.b_row_stride % vec == 0,
                  "gemm_tc: strides must be multiples of 16 bytes");
-  if (xf) {
-    // A is the raw fp32 tensor: plain (un-swizzled) boxes of 18 rows x 10 pixels x 64 channels for the transform warps
-    HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(p.a) & 15) == 0 && p.a_px_stride % 4 == 0, "gemm_tc: raw operand must be 16-byte aligned");
-    cuuint64_t dims[4] = {(cuuint64_t)(p.a_k_valid > 0 ? p.a_k_valid : p.k_per_tap), (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
-    cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * 4, (cuuint64_t)p.a_row_stride * 4, (cuuint64_t)p.a_img_stride * 4};
-    cuuint32_t box[4] = {64, 10, (cuuint32_t)kSlabRows, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&maps->a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p.a), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    HDRVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, raw fp32) failed: %d (W=%d H=%d N=%d K=%d)", (int)r, p.W, p.H,
-                   p.n_img, p.k_per_tap);
-  } else {
+  {
     // A: {C, W, H, N}; the channel extent visible to TMA is k_per_tap (columns beyond are never addressed)
     cuuint64_t dims[4] = {(cuuint64_t)(p.a_k_valid > 0 ? p.a_k_valid : p.k_per_tap), (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
     cuuint64_t strides[3] = {(cuuint64_t)p.a_px_stride * eb, (cuuint64_t)p.a_row_stride * eb,
@@ -887,7 +771,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int 
   memset(&maps->a2, 0, sizeof maps->a2);
   memset(&maps->b2, 0, sizeof maps->b2);
   if (p.k2 > 0) {
-    HDRVAE_REQUIRE(slab && !xf && eb == 2 && p.k2 % row_elems == 0 && p.a2 != nullptr && p.b2 != nullptr,
+    HDRVAE_REQUIRE(slab && eb == 2 && p.k2 % row_elems == 0 && p.a2 != nullptr && p.b2 != nullptr,
                    "gemm_tc: the fused second tensor needs the 16-bit slab form and whole K blocks");
     HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(p.a2) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.b2) & 15) == 0 &&
                    p.a2_px_stride % vec == 0 && p.a2_row_stride % vec == 0 && p.a2_img_stride % vec == 0 && p.b2_row_stride % vec == 0,
@@ -925,23 +809,23 @@ void choose_tile(int H, int W, GemmParams* p) {
   p->tiles_y = (H + p->TH - 1) / p->TH;
 }
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0, bool XF = false>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0>
 static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
   constexpr int KSUB = SLAB ? 1 : (BLOCK_N <= 128) ? 2 : 1;
   GemmParams p = p_in;
   if (p.res_scale == 0.f) p.res_scale = 1.f;
-  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB, XF>;
+  using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
   {
     const char* d = getenv("HDRVAE_GEMM_DBG");
     p.dbg = d ? atoi(d) : 0;
   }
   p.n_tiles_n = (p.n_cols + BLOCK_N - 1) / BLOCK_N;
   TensorMapPair maps;
-  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB, XF));  // a CTA of a pair stages half of the B rows
+  HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB));  // a CTA of a pair stages half of the B rows
   static PerDeviceOnce attr_once;
   if (attr_once.first())
-    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
   const long long m_tiles = (long long)p.n_img * p.tiles_x * p.tiles_y;
   const long long work = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
@@ -950,7 +834,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(kNumThreads + (XF ? kXfThreads : 0));
+  cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -960,8 +844,8 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HDRVAE_REQUIRE(p.k2 == 0 || (SLAB > 0 && !XF), "gemm_tc: a fused second tensor needs the slab form");
-  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, maps.a, maps.b, maps.a2, maps.b2, p));
+  HDRVAE_REQUIRE(p.k2 == 0 || SLAB > 0, "gemm_tc: a fused second tensor needs the slab form");
+  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, maps.a, maps.b, maps.a2, maps.b2, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1050,19 +934,6 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (p.row_mode == 1) return launch_tc<256, false, 2, EPI_ROWMAX>(p, num_sms, stream);
       HDRVAE_REQUIRE(p.out_dtype != DT_F32 && p.bias != nullptr, "gemm_tc: soft-max pass 2 writes a 16-bit output and needs -max per row");
       return launch_tc<256, false, 2, EPI_OUT16 | EPI_EXPSUM>(p, num_sms, stream);
-    }
-    if (p.xf_scale != nullptr) {
-      // fused GroupNorm + SiLU operand transform (decoder convs without a second output)
-      HDRVAE_REQUIRE(p.slab && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0 && p.ab_dtype == DT_F16 &&
-                     p.y_pad == 0, "gemm_tc: the operand transform needs the fp16 slab form");
-      if (n128) {
-        if (epi == EPI_STATS) return launch_tc<128, false, 2, EPI_STATS, 3, true>(p, num_sms, stream);
-      } else {
-        if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1, true>(p, num_sms, stream);
-        if (epi == (EPI_RES | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_STATS, 1, true>(p, num_sms, stream);
-        if (epi == (EPI_RES | EPI_OUT2 | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_OUT2 | EPI_STATS, 1, true>(p, num_sms, stream);
-      }
-      HDRVAE_REQUIRE(false, "gemm_tc: no operand-transform build for this epilogue (%d)", epi);
     }
     if (p.slab && n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
       // the decoder's 128-channel 3x3 convs: slab variant, weights in groups of 3 taps

@@ -243,31 +243,59 @@ static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* 
 
 static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* px_per_block);
 
+// Grid of the apply kernel: ONE full wave over the whole batch — blocks = SMs x (blocks that are actually resident per SM
+// for this instantiation), split evenly over the images.  (Round 1 launched 148 x 8 blocks while 5 or 6 fit per SM: a
+// second wave one third full, i.e. the last ~25 % of the time with two thirds of the chip idle.)
+template <typename Kernel>
+static void apply_chunking(Kernel kernel, int* cached_per_sm, size_t smem, int B, int HW, int C, int* chunks, int* px_per_block) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  if (*cached_per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kGnThreads, smem) != cudaSuccess || n < 1) n = 4;
+    *cached_per_sm = n;
+  }
+  const int px_per_iter = kGnThreads / (C >> 3);
+  int c = sms * *cached_per_sm / B;
+  int maxc = (HW + px_per_iter * 4 - 1) / (px_per_iter * 4);   // at least 4 iterations per thread
+  if (c > maxc) c = maxc;
+  if (c < 1) c = 1;
+  int ppb = (HW + c - 1) / c;
+  ppb = (ppb + px_per_iter - 1) / px_per_iter * px_per_iter;
+  *px_per_block = ppb;
+  *chunks = (HW + ppb - 1) / ppb;
+}
+
 template <typename TIn, typename TOut>
-static void launch_apply(const void* x, void* y, const float* scale, const float* shift, int B, int HW, int C, int chunks,
-                         int ppb, bool silu, long long xs, long long ys, cudaStream_t s, float in_scale = 1.f) {
-  const dim3 grid(chunks, B);
+static void launch_apply(const void* x, void* y, const float* scale, const float* shift, int B, int HW, int C, int /*chunks*/,
+                         int /*ppb*/, bool silu, long long xs, long long ys, cudaStream_t s, float in_scale = 1.f) {
   const size_t sm = 2 * C * sizeof(float);
-  // exp of the SiLU on the special-function unit (default) or as a polynomial on the FMA pipe (HDRVAE_SILU_MUFU=0).
-  // This kernel is not purely HBM bound: same-box A/B of the C2 step 44.3 ms (polynomial) vs 43.4 ms (ex2 + rcp).  The
-  // polynomial exists for the experimental fused operand transform, where the XU pipe is the scarce one.
+  // This kernel is not purely HBM bound: same-box A/B of the C2 step 44.3 ms (polynomial exp) vs 43.4 ms (ex2 + rcp).
   // HDRVAE_SILU_MUFU: 0 polynomial exp on the FMA pipe, 1 ex2 + rcp on the special-function unit, 2 (default for 16-bit
   // outputs) ex2 + Newton reciprocal.  fp32 / hi|lo|hi outputs (high-precision mode) always take ex2 + rcp.
   static int mufu = -1;
   if (mufu < 0) { const char* e = getenv("HDRVAE_SILU_MUFU"); mufu = e ? atoi(e) : 2; }
   const int how = sizeof(TOut) == 2 && !std::is_same<TOut, HalfSplit3>::value ? mufu : 1;
-  if (silu && how == 2)
-    gn_apply_kernel<TIn, TOut, true, 2><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                     scale, shift, HW, C, ppb, xs, ys, in_scale);
-  else if (silu && how == 1)
-    gn_apply_kernel<TIn, TOut, true, 1><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                     scale, shift, HW, C, ppb, xs, ys, in_scale);
-  else if (silu)
-    gn_apply_kernel<TIn, TOut, true><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                  scale, shift, HW, C, ppb, xs, ys, in_scale);
-  else
-    gn_apply_kernel<TIn, TOut, false><<<grid, kGnThreads, sm, s>>>(reinterpret_cast<const TIn*>(x), reinterpret_cast<TOut*>(y),
-                                                                   scale, shift, HW, C, ppb, xs, ys, in_scale);
+  static int occ[4] = {0, 0, 0, 0};
+  int chunks = 1, ppb = HW;
+  const TIn* xi = reinterpret_cast<const TIn*>(x);
+  TOut* yo = reinterpret_cast<TOut*>(y);
+  if (silu && how == 2) {
+    apply_chunking(gn_apply_kernel<TIn, TOut, true, 2>, &occ[0], sm, B, HW, C, &chunks, &ppb);
+    gn_apply_kernel<TIn, TOut, true, 2><<<dim3(chunks, B), kGnThreads, sm, s>>>(xi, yo, scale, shift, HW, C, ppb, xs, ys, in_scale);
+  } else if (silu && how == 1) {
+    apply_chunking(gn_apply_kernel<TIn, TOut, true, 1>, &occ[1], sm, B, HW, C, &chunks, &ppb);
+    gn_apply_kernel<TIn, TOut, true, 1><<<dim3(chunks, B), kGnThreads, sm, s>>>(xi, yo, scale, shift, HW, C, ppb, xs, ys, in_scale);
+  } else if (silu) {
+    apply_chunking(gn_apply_kernel<TIn, TOut, true, 0>, &occ[2], sm, B, HW, C, &chunks, &ppb);
+    gn_apply_kernel<TIn, TOut, true, 0><<<dim3(chunks, B), kGnThreads, sm, s>>>(xi, yo, scale, shift, HW, C, ppb, xs, ys, in_scale);
+  } else {
+    apply_chunking(gn_apply_kernel<TIn, TOut, false, 0>, &occ[3], sm, B, HW, C, &chunks, &ppb);
+    gn_apply_kernel<TIn, TOut, false, 0><<<dim3(chunks, B), kGnThreads, sm, s>>>(xi, yo, scale, shift, HW, C, ppb, xs, ys, in_scale);
+  }
 }
 
 // Row tiling: the statistics of a (image, group) are sums over ALL ranks' rows.  gn_reduce_partials folds this
@@ -344,22 +372,6 @@ int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride
   }
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// Statistics only: conv-emitted partials (already in the scratch buffer) -> per-(image, channel) scale / shift, which
-// stay in the scratch buffer for a conv that applies them itself while staging its operand (gemm_tc.cu, XF variant).
-int launch_gn_finalize_only(int B, int HW, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
-                            int partial_chunks, const float** scale_out, const float** shift_out, cudaStream_t s) {
-  HDRVAE_REQUIRE(C % 32 == 0 && partial_chunks > 0, "groupnorm (finalize only): needs conv-emitted partials");
-  float* partial = reinterpret_cast<float*>(scratch);
-  float* scale = gn_scale_ptr(scratch, B, max_chunks);
-  float* shift = scale + (size_t)B * C;
-  gn_finalize_kernel<<<dim3(kGroups, B), 256, 0, s>>>(partial, partial_chunks, gamma, beta, scale, shift, C,
-                                                       (double)HW * (double)(C / kGroups), 1e-6f);
-  HDRVAE_LAUNCHED();
-  HDRVAE_CUDA_OK(cudaGetLastError());
-  *scale_out = scale; *shift_out = shift;
   return 0;
 }
 
