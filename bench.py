@@ -193,7 +193,7 @@ def run_reference_arm(args):
     """`--impl reference`: the reference's CPU implementation of the path on the box's host cores, on the B200 arm's
     config.  Every step decodes ONE image of the C2 batch at its full size (1x16x128x128 -> 1024^2, "moderate") with
     the reference node's call structure; MP/s is per pixel, so one image of the batch is a bounded sample of the
-    4-image step.  Warm-up is a single C2-sized call; the timed steps stop once REF_BUDGET_S (default 420 s) would be
+    4-image step.  Warm-up is a single C2-sized call; the timed steps stop once REF_BUDGET_S (default 240 s) would be
     exceeded (reported in `steps`, the request in `steps_requested`).  Three C1-sized calls (1x16x64x64 -> 512^2,
     BASELINE configs[0], the reference's own CPU-runnable case) are timed as well and reported in cpu_baseline."""
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +201,7 @@ def run_reference_arm(args):
         return
     from oracle.flux_decoder import build_decoder
     dec = build_decoder(0)
-    budget = float(os.environ.get("REF_BUDGET_S", "420"))
+    budget = float(os.environ.get("REF_BUDGET_S", "240"))
     c1, c1_per, c1_n = cpu_reference_run(3, 1, 64, dec=dec)
     base, per, done = cpu_reference_run(max(2, args.steps), 1, LATENT, budget_s=budget, dec=dec)
     base["c1_512"] = {"value": c1["value"], "unit": UNIT, "s_per_call": c1_per, "calls": c1_n,

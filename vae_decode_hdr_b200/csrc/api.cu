@@ -255,7 +255,7 @@ struct Plan {
 static constexpr long long kScoreBudgetElems = 1024ll << 20;  // fp32 score chunk <= 4 GiB (K and V^T are re-read once per chunk)
 static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
 
-static Plan make_plan(int B, int h, int w, bool attn_only = false, bool high = false) {
+static Plan make_plan(int B, int h, int w, bool attn_only = false, bool high = false, bool attn_scratch = true) {
   Plan pl;
   const size_t km = high ? 3 : 1;                              // hi|lo|hi operands are 3x as wide
   pl.B = B; pl.h = h; pl.w = w;
@@ -284,10 +284,12 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false, bool high = f
   pl.off_vt = take((size_t)B * 512 * pl.Tp * 2 * km);
   pl.off_o = take((size_t)B * pl.T * 512 * 2 * km);
   pl.off_f32 = take(high ? (size_t)pl.Tp * 1536 * 4 + (size_t)B * 64 * pl.T * 4 : 0);   // high: fp32 q|k, v^T / o of one image; fp32 NHWC latent
-  pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
-  pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2 * km);
-  pl.off_inv = take((size_t)pl.s_rows * 4 * 2);          // 1 / row sum, and -row max of the two-pass soft-max
-  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials of the PV GEMM
+  // score / probability chunks, row partials and split-K partials exist only for the GEMM-level attention (validation
+  // build, HDRVAE_ATTN_FUSED=0, high precision): the fused kernel keeps S and P on the SM (up to 6.1 GiB less at 4096^2)
+  pl.off_s = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 4 : 0);
+  pl.off_p = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 2 * km : 0);
+  pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);      // 1 / row sum, and -row max of the two-pass soft-max
+  pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);   // split-K partials of the PV GEMM
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
   pl.off_lat_in = take(attn_only ? 0 : (size_t)B * 16 * pl.T * 4);          // graph input: fp32 latent copy
   pl.off_img = take(attn_only ? 0 : (size_t)B * 64 * pl.T * 3 * 4);        // graph output: fp32 BHWC image
@@ -661,7 +663,7 @@ struct RowsPlan {
       off_part, off_epi, total;
 };
 
-static RowsPlan make_rows_plan(int h, int w, int world) {
+static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true) {
   RowsPlan pl;
   pl.h = h; pl.w = w; pl.world = world; pl.hl = h / world;
   pl.T = h * w; pl.Tl = pl.hl * w;
@@ -690,10 +692,10 @@ static RowsPlan make_rows_plan(int h, int w, int world) {
   pl.off_v = take((size_t)pl.Tp * 512 * 2);            // gathered v [T][512]
   pl.off_vt = take((size_t)512 * pl.Tp * 2);
   pl.off_o = take((size_t)pl.Tl * 512 * 2);
-  pl.off_s = take((size_t)pl.s_rows * pl.Tp * 4);
-  pl.off_p = take((size_t)pl.s_rows * pl.Tp * 2);
-  pl.off_inv = take((size_t)pl.s_rows * 4 * 2);          // 1 / row sum, and -row max of the two-pass soft-max
-  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);
+  pl.off_s = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 4 : 0);      // GEMM-level attention only (see make_plan)
+  pl.off_p = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 2 : 0);
+  pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);
+  pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);
   pl.off_epi = take(epilogue_scratch_bytes(1, 8 * pl.hl, 8 * w));
   pl.total = off;
   return pl;
@@ -1141,7 +1143,7 @@ int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n,
 int hdrvae_workspace_bytes(hdrvae_ctx* ctx, int B, int h, int w, size_t* bytes) {
   HDRVAE_REQUIRE(ctx != nullptr && bytes != nullptr, "hdrvae_workspace_bytes: null argument");
   HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_workspace_bytes: empty latent batch [%d,16,%d,%d]", B, h, w);
-  *bytes = make_plan(B, h, w, false, ctx->high).total;
+  *bytes = make_plan(B, h, w, false, ctx->high, ctx->high || !attention_fused_enabled(ctx)).total;
   return 0;
 }
 
@@ -1200,7 +1202,7 @@ int hdrvae_decode_begin(hdrvae_ctx* ctx, const float* latent, int B, int h, int 
   HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr, "hdrvae_decode: null argument");
   HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode: empty latent batch [%d,16,%d,%d]", B, h, w);
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w, false, ctx->high);
+  const Plan pl = make_plan(B, h, w, false, ctx->high, ctx->high || !attention_fused_enabled(ctx));
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1227,7 +1229,7 @@ int hdrvae_decode_finish(hdrvae_ctx* ctx, int B, int h, int w, int mode, float e
   HDRVAE_REQUIRE(ctx != nullptr && out_bhwc != nullptr, "hdrvae_decode: null argument");
   HDRVAE_REQUIRE(mode >= 0 && mode <= 3, "hdrvae_decode: bad mode %d", mode);
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w, false, ctx->high);
+  const Plan pl = make_plan(B, h, w, false, ctx->high, ctx->high || !attention_fused_enabled(ctx));
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1271,7 +1273,7 @@ int hdrvae_raw_stats_merge(const void* blocks, int n, void* dst, void* stream) {
 int hdrvae_rows_workspace_bytes(hdrvae_ctx* ctx, int h, int w, int world, size_t* bytes) {
   HDRVAE_REQUIRE(ctx && bytes && h >= 1 && w >= 1 && world >= 1, "hdrvae_rows_workspace_bytes: bad argument");
   HDRVAE_REQUIRE(h % world == 0, "row tiling needs the latent height (%d) to be a multiple of the rank count (%d)", h, world);
-  *bytes = make_rows_plan(h, w, world).total;
+  *bytes = make_rows_plan(h, w, world, !attention_fused_enabled(ctx)).total;
   return 0;
 }
 
@@ -1287,7 +1289,7 @@ int hdrvae_rows_begin(hdrvae_ctx* ctx, const float* latent_full, int h, int w, i
   HDRVAE_REQUIRE(!ctx->high, "row tiling is not available in the high-precision mode");
   hdrvae_rows* st = new hdrvae_rows();
   st->ctx = ctx;
-  st->pl = make_rows_plan(h, w, world);
+  st->pl = make_rows_plan(h, w, world, !attention_fused_enabled(ctx));
   if (ws_bytes < st->pl.total || (reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) {
     set_error("hdrvae_rows_begin: workspace too small or misaligned (%zu < %zu bytes)", ws_bytes, st->pl.total);
     delete st;
@@ -1368,7 +1370,7 @@ int hdrvae_decode_features(hdrvae_ctx* ctx, const float* latent, int B, int h, i
   HDRVAE_REQUIRE(ctx != nullptr && latent != nullptr && features != nullptr, "hdrvae_decode_features: null argument");
   HDRVAE_REQUIRE(B >= 1 && h >= 1 && w >= 1, "hdrvae_decode_features: empty latent batch");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
-  const Plan pl = make_plan(B, h, w, false, ctx->high);
+  const Plan pl = make_plan(B, h, w, false, ctx->high, ctx->high || !attention_fused_enabled(ctx));
   HDRVAE_TRY(check_ws(pl, workspace, ws_bytes));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   void* feat = nullptr;
@@ -1453,7 +1455,7 @@ int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* 
   HDRVAE_REQUIRE(dtype == HDRVAE_BF16 || dtype == HDRVAE_F16, "hdrvae_attention: q/k/v must be bf16 or fp16");
   HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  Plan pl = make_plan(B, 1, T, true);
+  Plan pl = make_plan(B, 1, T, true, false, !attention_fused_enabled(ctx));
   uint8_t* ws = nullptr;
   HDRVAE_CUDA_OK(cudaMalloc((void**)&ws, pl.total));
   uint16_t* qk = reinterpret_cast<uint16_t*>(ws + pl.off_qk);
