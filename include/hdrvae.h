@@ -296,8 +296,12 @@ int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, in
                           const float* beta, int apply_silu, void* y, int y_dtype, const float* gn_partials,
                           int gn_chunks, void* stream);
 
-/* Single-head attention over T tokens, d = 512 (mid.attn_1 core):
- * q,k,v,o device [B,T,512] of dtype HDRVAE_F16 or HDRVAE_BF16; softmax(q k^T / sqrt(512)) v. */
+/* Single-head attention over T tokens, d = 512 (mid.attn_1 core; the reference reaches it through vae.decode,
+ * hdr_vae_decode.py:859,:1022): q,k,v,o device [B,T,512] of dtype HDRVAE_F16 or HDRVAE_BF16; softmax(q k^T / sqrt(512)) v.
+ * ONE fused flash-style kernel launch for all B images (csrc/attention.cu: S and O in tensor memory, P written back to
+ * tensor memory as the PV operand, online soft-max with lazy rescaling; hdrvae_set_cta_group(ctx, 1) selects its
+ * single-CTA build); the CUDA-core validation build (hdrvae_set_conv_impl) computes it as separate GEMMs.  The entry
+ * itself allocates a scratch copy of the operands in the decoder's layout (q|k interleaved, v transposed). */
 int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* v, int dtype, int B, int T,
                      void* o, void* stream);
 
