@@ -526,10 +526,11 @@ def multi_gpu_selftest(engine, dev, rank: int, world: int) -> dict:
     what the sharded paths gave it with its OWN single-GPU decode of the same input; the worst difference over ranks is
     reported.  (a) ragged batch sharding (world + 1 images: the first rank gets two), (b) a batch of ONE image over all
     ranks (every rank but the first holds an empty shard), (c) row tiling of one image with 16 latent rows per rank
-    (conv tiles coincide with the single-GPU tiling, so the result must be identical)."""
+    (conv tiles coincide with the single-GPU tiling, so the result must be identical), over NCCL and over the device-driven
+    transport (sharding.RowsDirect)."""
     import torch
     import torch.distributed as dist
-    from vae_decode_hdr_b200.sharding import decode_batch_sharded, decode_rows_sharded, shard_bounds
+    from vae_decode_hdr_b200.sharding import RowsDirect, decode_batch_sharded, decode_rows_sharded, shard_bounds
     from vae_decode_hdr_b200.synthetic import synthetic_latent
     res = {}
     try:
@@ -556,8 +557,16 @@ def multi_gpu_selftest(engine, dev, rank: int, world: int) -> dict:
         whole, _ = engine.decode(zr, "moderate", 1.0)
         rows = 8 * 16
         res["rows_tiled_rel"] = worst(rel(out, whole[:, rank * rows:(rank + 1) * rows]))
+        direct = RowsDirect(engine, 16 * world, 8)                       # device-driven transport, three decodes back to back
+        d = 0.0
+        for _ in range(3):
+            out, _ = direct.decode(zr, "moderate", 1.0)
+            d = max(d, rel(out, whole[:, rank * rows:(rank + 1) * rows]))
+        direct.close()
+        res["rows_tiled_direct_rel"] = worst(d)
         res["pass"] = bool(res["batch_ragged_rel"] < 1e-6 and res["batch_stats_rel"] < 1e-6 and
-                           res["batch_empty_shards_rel"] < 1e-6 and res["rows_tiled_rel"] < 1e-6)
+                           res["batch_empty_shards_rel"] < 1e-6 and res["rows_tiled_rel"] < 1e-6 and
+                           res["rows_tiled_direct_rel"] < 1e-6)
     except Exception as exc:
         res["error"] = repr(exc)[:300]
         res["pass"] = False
@@ -571,28 +580,40 @@ def aux_c4_rows(engine, dev, rank: int, world: int, args) -> dict:
     compared with the single-GPU decode of the same latent on rank 0."""
     import torch
     import torch.distributed as dist
-    from vae_decode_hdr_b200.sharding import decode_rows_sharded
+    from vae_decode_hdr_b200.sharding import RowsDirect, decode_rows_sharded
     from vae_decode_hdr_b200.synthetic import synthetic_latent
     L4 = int(os.environ.get("HDRVAE_BENCH_C4_LATENT", "512"))
     res = {"workload": f"C4: 1x16x{L4}x{L4} latent -> {8 * L4}x{8 * L4}, aggressive, row-tiled over {world} GPUs "
-                       f"({L4 // world} latent rows per GPU)", "n_gpus": world, "transport": "nccl"}
+                       f"({L4 // world} latent rows per GPU)", "n_gpus": world,
+           "transport": "direct (library-owned IPC workspaces; push / wait kernels over NVLink, no NCCL on the data path)"}
     try:
         engine._workspace = None
         torch.cuda.empty_cache()
         z4 = synthetic_latent(1, L4, L4, seed=1234).to(dev)
-        for _ in range(2):
-            out, _ = decode_rows_sharded(engine, z4, "aggressive", 1.0, want_stats=False)
-        torch.cuda.synchronize(dev); dist.barrier()
         reps = 3
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            out, _ = decode_rows_sharded(engine, z4, "aggressive", 1.0, want_stats=False)
-        e1.record()
-        torch.cuda.synchronize(dev); dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
+
+        def timed(run):
+            for _ in range(2):
+                out, _ = run()
+            torch.cuda.synchronize(dev); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                out, _ = run()
+            e1.record()
+            torch.cuda.synchronize(dev); dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), out
+
+        # host-driven NCCL transport first (its workspace is a torch tensor, freed afterwards)
+        ms_nccl, out_nccl = timed(lambda: decode_rows_sharded(engine, z4, "aggressive", 1.0, want_stats=False))
+        torch.cuda.empty_cache()
+        direct = RowsDirect(engine, L4, L4)
+        ms, out = timed(lambda: direct.decode(z4, "aggressive", 1.0, want_stats=False))
+        res["nccl_transport_ms_per_image"] = ms_nccl
+        res["rel_l2_direct_vs_nccl_transport"] = float((out.double() - out_nccl.double()).norm() / out_nccl.double().norm())
+        del out_nccl
         mp = (8 * L4) ** 2 / 1e6
         res.update({"ms_per_image": ms, "value": mp / (ms / 1e3), "unit": UNIT, "scaling": "strong",
                     "per_gpu_mp_s": mp / (ms / 1e3) / world,
@@ -606,6 +627,7 @@ def aux_c4_rows(engine, dev, rank: int, world: int, args) -> dict:
             del parts
             torch.cuda.empty_cache()
             whole, _ = engine.decode(z4, "aggressive", 1.0, want_stats=False)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             whole, _ = engine.decode(z4, "aggressive", 1.0, want_stats=False)
             e1.record()
@@ -618,6 +640,7 @@ def aux_c4_rows(engine, dev, rank: int, world: int, args) -> dict:
                 d += float(((wch - tch) ** 2).sum()); n += float((wch ** 2).sum())
             res["rel_l2_vs_single_gpu"] = (d / n) ** 0.5
             del whole, tiled
+        direct.close()
         engine._workspace = None
         torch.cuda.empty_cache()
         dist.barrier()

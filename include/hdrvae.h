@@ -192,8 +192,7 @@ int hdrvae_raw_stats_merge(const void* blocks, int n, void* dst, void* stream);
  *   ALLGATHER : in-place all-gather of `gather_bytes_per_rank` bytes per rank (attention K and V: mid.attn_1 is global);
  *   RAW_STATS : MIN/MAX/SUM all-reduce of the hdrvae_raw_stats block (batch-global HDR statistics).
  * All offsets are byte offsets into the rank's workspace (identical on every rank). */
-enum { HDRVAE_EX_END = 0, HDRVAE_EX_HALO = 1, HDRVAE_EX_ALLREDUCE_F64 = 2, HDRVAE_EX_ALLGATHER = 4, HDRVAE_EX_RAW_STATS = 8,
-       HDRVAE_EX_HALO_PUSHED = 16 /* the library already pushed the halo rows to the peers (hdrvae_rows_set_peers) */ };
+enum { HDRVAE_EX_END = 0, HDRVAE_EX_HALO = 1, HDRVAE_EX_ALLREDUCE_F64 = 2, HDRVAE_EX_ALLGATHER = 4, HDRVAE_EX_RAW_STATS = 8 };
 typedef struct hdrvae_exchange {
   int32_t kind;                 /* bitmask of HDRVAE_EX_* ; HDRVAE_EX_END: the program is finished */
   int32_t n_halo;               /* 0..2 buffers */
@@ -215,14 +214,21 @@ int hdrvae_rows_begin(hdrvae_ctx* ctx, const float* latent_full_nchw, int h, int
                       size_t workspace_bytes, hdrvae_rows** state);
 /* Enqueue work up to the next exchange point; *ex describes what the host must exchange before calling again. */
 int hdrvae_rows_run(hdrvae_rows* state, hdrvae_exchange* ex, void* stream);
-/* Optional peer-to-peer halo transport: the workspaces of the rank above (rank - 1) and below (rank + 1), mapped into
- * this process (cudaIpcOpenMemHandle / peer access; NULL where there is no neighbour; all ranks use the same workspace
- * layout).  hdrvae_rows_run then pushes the halo rows itself (stream-ordered copies over NVLink) and reports
- * HDRVAE_EX_HALO_PUSHED instead of HDRVAE_EX_HALO.  Contract for the host: every such point must be followed by a
- * collective that all ranks enqueue on the same stream before they continue (the ALLREDUCE_F64 that accompanies every
- * halo exchange is one): it orders a rank's reads after its neighbours' pushes, and because two pushes into the same
- * halo row are always separated by at least one such collective a push cannot overtake the previous reads. */
-int hdrvae_rows_set_peers(hdrvae_rows* state, void* upper_rank_workspace, void* lower_rank_workspace);
+/* Device-driven transport (no host round trips, no NCCL on the data path): every rank allocates its workspace through
+ * the library (hdrvae_peer_alloc: zero-initialised device memory + a CUDA IPC handle), the host exchanges the 64-byte
+ * handles by any means (one all-gather of bytes), every rank maps every other rank's workspace (hdrvae_peer_open) and hands
+ * the `world` pointers (its own at [rank]) to hdrvae_rows_set_peers.  hdrvae_rows_run_direct then enqueues the WHOLE
+ * program on `stream`: at every exchange point a push kernel stores the halo rows / GroupNorm sums / K,V rows / statistics
+ * straight into the peers' workspaces over NVLink behind a two-phase flag handshake, and a wait kernel folds the received
+ * sums in rank order (csrc/rows_p2p.cu).  Results equal the host-driven exchange up to the fp64 order of 64 sums.  One
+ * process per GPU only: ranks that share a GPU would wait on one another's kernels. */
+typedef struct hdrvae_ipc_handle { unsigned char bytes[64]; } hdrvae_ipc_handle;
+int hdrvae_peer_alloc(hdrvae_ctx* ctx, size_t bytes, void** dev_ptr, hdrvae_ipc_handle* handle);
+int hdrvae_peer_open(hdrvae_ctx* ctx, const hdrvae_ipc_handle* handle, void** mapped);
+int hdrvae_peer_close(hdrvae_ctx* ctx, void* mapped);
+int hdrvae_peer_free(hdrvae_ctx* ctx, void* dev_ptr);
+int hdrvae_rows_set_peers(hdrvae_rows* state, void* const* workspaces_of_all_ranks, int world);
+int hdrvae_rows_run_direct(hdrvae_rows* state, void* stream);
 /* After HDRVAE_EX_END: copy the statistics (global: pre/post/conv/pre3; local slab: out_*, pixel counts) and free. */
 int hdrvae_rows_end(hdrvae_rows* state, hdrvae_stats* stats, void* stream);
 

@@ -78,15 +78,18 @@ def _rows_worker(rank, world, port, q):
         gathered = [torch.empty_like(out) for _ in range(world)]
         dist.all_gather(gathered, out.contiguous())
         full_rel = float((torch.cat(gathered, dim=1) - whole).double().norm() / whole.double().norm())
-        # same decode with the halos pushed over NVLink peer-to-peer (CUDA IPC) instead of NCCL send/recv: the kernels
-        # and their inputs are the same, so the result is bit-identical; three back-to-back decodes reuse the
-        # persistent workspace (write-after-read safety of the pushes)
-        from vae_decode_hdr_b200.sharding import RowsP2P
-        p2p = RowsP2P(eng, h, w)
+        # same decode with the device-driven transport (library-owned IPC workspaces, push / wait kernels, no NCCL on the
+        # data path): same kernels and inputs, the 64 GroupNorm sums folded in rank order instead of NCCL's order, so the
+        # result is identical up to that fp64 summation order; three back-to-back decodes reuse the persistent workspace
+        # (write-after-read safety of the pushes, exchange counter carried in device memory)
+        from vae_decode_hdr_b200.sharding import RowsDirect
+        p2p = RowsDirect(eng, h, w)
         same = True
         for _ in range(3):
             out2, st2 = p2p.decode(z, mode, 1.0)
-            same = same and bool(torch.equal(out2, out)) and st2["hdr_pixels"] == st["hdr_pixels"]
+            d = float((out2 - out).double().norm() / out.double().norm())
+            same = same and d < 1e-6 and st2["hdr_pixels"] == st["hdr_pixels"]
+        p2p.close()
         res.append((h, w, rel, full_rel, abs(st["pre_max"] - st1["pre_max"]) / abs(st1["pre_max"]), same))
     q.put((rank, res))
     dist.destroy_process_group()

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vae_decode_hdr_b200.engine import HdrVaeEngine  # noqa: E402
-from vae_decode_hdr_b200.sharding import RowsP2P, decode_rows_sharded  # noqa: E402
+from vae_decode_hdr_b200.sharding import RowsDirect, decode_rows_sharded  # noqa: E402
 from vae_decode_hdr_b200.synthetic import random_decoder_state_dict, synthetic_latent  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -33,7 +33,7 @@ dist.init_process_group("nccl", device_id=dev)
 eng = HdrVaeEngine(random_decoder_state_dict(0), dev)
 z = synthetic_latent(1, a.h, a.w, seed=3).to(dev)
 
-p2p = RowsP2P(eng, a.h, a.w) if a.transport == "p2p" else None
+p2p = RowsDirect(eng, a.h, a.w) if a.transport == "p2p" else None
 
 
 def run(want_stats):

@@ -50,7 +50,11 @@ class HdrvaeExchange(C.Structure):
                 ("gather_off", C.c_uint64 * 2), ("gather_bytes_per_rank", C.c_uint64 * 2), ("raw_stats_off", C.c_uint64)]
 
 
-EX_END, EX_HALO, EX_ALLREDUCE_F64, EX_ALLGATHER, EX_RAW_STATS, EX_HALO_PUSHED = 0, 1, 2, 4, 8, 16
+EX_END, EX_HALO, EX_ALLREDUCE_F64, EX_ALLGATHER, EX_RAW_STATS = 0, 1, 2, 4, 8
+
+
+class HdrvaeIpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
 
 
 class HdrvaeRawStats(C.Structure):
@@ -78,7 +82,12 @@ SIGNATURES = {
     "hdrvae_rows_begin": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, C.POINTER(_vp)]),
     "hdrvae_rows_run": (_i, [_vp, C.POINTER(HdrvaeExchange), _vp]),
     "hdrvae_rows_end": (_i, [_vp, C.POINTER(HdrvaeStats), _vp]),
-    "hdrvae_rows_set_peers": (_i, [_vp, _vp, _vp]),
+    "hdrvae_peer_alloc": (_i, [_vp, _sz, C.POINTER(_vp), C.POINTER(HdrvaeIpcHandle)]),
+    "hdrvae_peer_open": (_i, [_vp, C.POINTER(HdrvaeIpcHandle), C.POINTER(_vp)]),
+    "hdrvae_peer_close": (_i, [_vp, _vp]),
+    "hdrvae_peer_free": (_i, [_vp, _vp]),
+    "hdrvae_rows_set_peers": (_i, [_vp, C.POINTER(_vp), _i]),
+    "hdrvae_rows_run_direct": (_i, [_vp, _vp]),
     "hdrvae_decode_features": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "hdrvae_epilogue_scratch_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "hdrvae_epilogue": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _vp, C.POINTER(HdrvaeStats),

@@ -660,7 +660,7 @@ static int check_ws(const Plan& pl, void* ws, size_t bytes) {
 struct RowsPlan {
   int h, w, hl, world, T, Tl, Tp, s_rows, gn_chunks;
   size_t off_lat, off_x, off_h, off_t, off_xa, off_xb, off_gn, off_qk, off_v, off_vt, off_o, off_s, off_p, off_inv,
-      off_part, off_epi, total;
+      off_part, off_epi, off_mail, total;
 };
 
 static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true) {
@@ -697,6 +697,7 @@ static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true
   pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);
   pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);
   pl.off_epi = take(epilogue_scratch_bytes(1, 8 * pl.hl, 8 * w));
+  pl.off_mail = take(sizeof(RowsMailbox));              // flags / tables of the device-driven exchanges (rows_p2p.cu)
   pl.total = off;
   return pl;
 }
@@ -717,8 +718,8 @@ struct hdrvae_rows {
   // layer-program state while the op list is being built
   float* x = nullptr; float* hbuf = nullptr;
   int H = 0, W = 0, pending = 0;
-  // neighbour ranks' workspaces mapped into this process (CUDA IPC / peer access), or null: hdrvae_rows_set_peers
-  uint8_t* peer_up = nullptr; uint8_t* peer_down = nullptr;
+  // every rank's workspace as mapped into this process (hdrvae_peer_open; own pointer at [rank]): hdrvae_rows_set_peers
+  uint8_t* peers[kRowsMaxRanks] = {};
   bool peers_set = false;
 };
 
@@ -1314,23 +1315,6 @@ int hdrvae_rows_run(hdrvae_rows* st, hdrvae_exchange* ex, void* stream) {
     hdrvae_rows::Op& op = st->ops[st->pc++];
     if (op.exchange) {
       *ex = op.ex;
-      if ((ex->kind & HDRVAE_EX_HALO) && st->peers_set) {
-        // push the halo rows straight into the neighbours' workspaces over NVLink (peer copies, stream-ordered after the
-        // conv that produced the rows); the host is left with the all-reduce.  The copy engine is used on purpose: SM
-        // stores to a CUDA-IPC mapping opened by another framework faulted here (peer access for kernels is not
-        // guaranteed by the lazy IPC open), while peer copies work on any mapping.
-        for (int i = 0; i < ex->n_halo; ++i) {
-          const size_t n = ex->halo_row_bytes[i];
-          if (st->rank > 0)
-            HDRVAE_CUDA_OK(cudaMemcpyAsync(st->peer_up + ex->halo_bottom_off[i], st->ws + ex->halo_first_row_off[i], n,
-                                           cudaMemcpyDefault, s));
-          if (st->rank < st->pl.world - 1)
-            HDRVAE_CUDA_OK(cudaMemcpyAsync(st->peer_down + ex->halo_top_off[i], st->ws + ex->halo_last_row_off[i], n,
-                                           cudaMemcpyDefault, s));
-        }
-        ex->kind &= ~HDRVAE_EX_HALO;
-        ex->kind |= HDRVAE_EX_HALO_PUSHED;
-      }
       return 0;
     }
     HDRVAE_TRY(op.fn(s));
@@ -1339,15 +1323,102 @@ int hdrvae_rows_run(hdrvae_rows* st, hdrvae_exchange* ex, void* stream) {
   return 0;
 }
 
-int hdrvae_rows_set_peers(hdrvae_rows* st, void* upper_rank_workspace, void* lower_rank_workspace) {
-  HDRVAE_REQUIRE(st != nullptr, "hdrvae_rows_set_peers: null state");
-  HDRVAE_REQUIRE((st->rank == 0) == (upper_rank_workspace == nullptr) &&
-                 (st->rank == st->pl.world - 1) == (lower_rank_workspace == nullptr),
-                 "hdrvae_rows_set_peers: rank %d of %d needs exactly the workspaces of its existing neighbours", st->rank,
-                 st->pl.world);
-  st->peer_up = reinterpret_cast<uint8_t*>(upper_rank_workspace);
-  st->peer_down = reinterpret_cast<uint8_t*>(lower_rank_workspace);
+// ---- device-driven transport (rows_p2p.cu): library-owned, IPC-shared workspaces ---------------------------------
+int hdrvae_peer_alloc(hdrvae_ctx* ctx, size_t bytes, void** dev_ptr, hdrvae_ipc_handle* handle) {
+  HDRVAE_REQUIRE(ctx && dev_ptr && handle && bytes > 0, "hdrvae_peer_alloc: bad argument");
+  static_assert(sizeof(hdrvae_ipc_handle) == sizeof(cudaIpcMemHandle_t), "IPC handle size");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  HDRVAE_CUDA_OK(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);              // the mailbox must start at zero (exchange counter, flags)
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle), p);
+  if (e != cudaSuccess) { cudaFree(p); set_error("hdrvae_peer_alloc: %s", cudaGetErrorString(e)); return -1; }
+  *dev_ptr = p;
+  return 0;
+}
+int hdrvae_peer_open(hdrvae_ctx* ctx, const hdrvae_ipc_handle* handle, void** mapped) {
+  HDRVAE_REQUIRE(ctx && handle && mapped, "hdrvae_peer_open: bad argument");
+  HDRVAE_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  HDRVAE_CUDA_OK(cudaIpcOpenMemHandle(mapped, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int hdrvae_peer_close(hdrvae_ctx* ctx, void* mapped) {
+  if (ctx == nullptr || mapped == nullptr) return 0;
+  cudaSetDevice(ctx->device);
+  HDRVAE_CUDA_OK(cudaIpcCloseMemHandle(mapped));
+  return 0;
+}
+int hdrvae_peer_free(hdrvae_ctx* ctx, void* dev_ptr) {
+  if (ctx == nullptr || dev_ptr == nullptr) return 0;
+  cudaSetDevice(ctx->device);
+  HDRVAE_CUDA_OK(cudaFree(dev_ptr));
+  return 0;
+}
+
+int hdrvae_rows_set_peers(hdrvae_rows* st, void* const* workspaces, int world) {
+  HDRVAE_REQUIRE(st != nullptr && workspaces != nullptr && world == st->pl.world && world <= kRowsMaxRanks,
+                 "hdrvae_rows_set_peers: need the workspaces of all %d ranks (at most %d)", st ? st->pl.world : 0, kRowsMaxRanks);
+  for (int r = 0; r < world; ++r) {
+    HDRVAE_REQUIRE(workspaces[r] != nullptr, "hdrvae_rows_set_peers: workspace of rank %d is null", r);
+    st->peers[r] = reinterpret_cast<uint8_t*>(workspaces[r]);
+  }
+  HDRVAE_REQUIRE(st->peers[st->rank] == st->ws, "hdrvae_rows_set_peers: entry [rank] must be this rank's own workspace");
   st->peers_set = true;
+  return 0;
+}
+
+// The whole program in one call: compute steps and exchanges are enqueued on `stream` back to back; nothing returns to
+// the host in between.
+int hdrvae_rows_run_direct(hdrvae_rows* st, void* stream) {
+  HDRVAE_REQUIRE(st != nullptr && st->peers_set, "hdrvae_rows_run_direct: call hdrvae_rows_set_peers first");
+  HDRVAE_CUDA_OK(cudaSetDevice(st->ctx->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int rank = st->rank, world = st->pl.world;
+  while (st->pc < st->ops.size()) {
+    hdrvae_rows::Op& op = st->ops[st->pc++];
+    if (!op.exchange) { HDRVAE_TRY(op.fn(s)); continue; }
+    const hdrvae_exchange& ex = op.ex;
+    RowsPushArgs a;
+    memset(&a, 0, sizeof a);
+    a.ws = st->ws; a.off_mail = st->pl.off_mail; a.rank = rank; a.world = world;
+    for (int r = 0; r < world; ++r) a.peers[r] = st->peers[r];
+    size_t total = 0;
+    auto seg = [&](int peer, int kind, size_t dst, size_t src, size_t bytes) -> int {
+      HDRVAE_REQUIRE(a.n_seg < 72 && (dst & 15) == 0 && (src & 15) == 0 && (bytes & 15) == 0 && bytes < (1ull << 32),
+                     "rows exchange: segment not 16-byte aligned or too many segments");
+      RowsSegment& g = a.seg[a.n_seg++];
+      g.peer = peer; g.kind = kind; g.dst_off = dst; g.src_off = src; g.bytes = (unsigned int)bytes;
+      total += bytes;
+      return 0;
+    };
+    if (ex.kind & HDRVAE_EX_HALO) {
+      for (int i = 0; i < ex.n_halo; ++i) {
+        if (rank > 0) HDRVAE_TRY(seg(rank - 1, 0, ex.halo_bottom_off[i], ex.halo_first_row_off[i], ex.halo_row_bytes[i]));
+        if (rank < world - 1) HDRVAE_TRY(seg(rank + 1, 0, ex.halo_top_off[i], ex.halo_last_row_off[i], ex.halo_row_bytes[i]));
+      }
+    }
+    if (ex.kind & HDRVAE_EX_ALLREDUCE_F64) {
+      HDRVAE_REQUIRE(ex.allreduce_count <= 64, "rows exchange: at most 64 sums");
+      for (int r = 0; r < world; ++r) HDRVAE_TRY(seg(r, 1, 0, ex.allreduce_off, ex.allreduce_count * 8));
+    }
+    if (ex.kind & HDRVAE_EX_ALLGATHER) {
+      for (int i = 0; i < ex.n_gather; ++i) {
+        const size_t n = ex.gather_bytes_per_rank[i], mine = ex.gather_off[i] + (size_t)rank * n;
+        for (int r = 0; r < world; ++r)
+          if (r != rank) HDRVAE_TRY(seg(r, 0, mine, mine, n));
+      }
+    }
+    if (ex.kind & HDRVAE_EX_RAW_STATS)
+      for (int r = 0; r < world; ++r) HDRVAE_TRY(seg(r, 2, 0, ex.raw_stats_off, sizeof(hdrvae_raw_stats)));
+    // all blocks of the push kernel wait on flags: the grid must be co-resident (one block per SM at most)
+    int blocks = (int)std::min<size_t>(std::max<size_t>(total / 32768, 1), (size_t)st->ctx->num_sms);
+    HDRVAE_TRY(launch_rows_push(a, blocks, s));
+    HDRVAE_TRY(launch_rows_wait(st->ws, st->pl.off_mail, world, ex.allreduce_off,
+                                (ex.kind & HDRVAE_EX_ALLREDUCE_F64) ? (int)ex.allreduce_count : 0, ex.raw_stats_off,
+                                (ex.kind & HDRVAE_EX_RAW_STATS) != 0, s));
+  }
   return 0;
 }
 

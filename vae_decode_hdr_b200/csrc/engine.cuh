@@ -59,6 +59,37 @@ int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride
                            cudaStream_t s);
 int launch_raw_stats_merge(const hdrvae_raw_stats* blocks, int n, hdrvae_raw_stats* dst, cudaStream_t s);
 
+// ---- device-driven exchanges of the row-tiled decode (rows_p2p.cu) --------------------------------------------
+constexpr int kRowsMaxRanks = 16;
+struct RowsRawSlot { hdrvae_raw_stats s; unsigned char pad[32]; };      // 128 bytes
+// lives at RowsPlan::off_mail of every rank's workspace; zero-initialised by hdrvae_peer_alloc
+struct RowsMailbox {
+  unsigned int arrived[64];     // [src rank]: src has reached exchange number ...
+  unsigned int data[64];        // [src rank]: src's contribution to exchange number ... has landed here
+  unsigned int seq;             // exchanges completed by THIS rank (advanced by the wait kernel)
+  unsigned int ticket;          // block counter of the push kernel
+  unsigned int pad[2];
+  double sums[2][kRowsMaxRanks][64];            // [parity of the exchange number][src rank]: GroupNorm sums
+  RowsRawSlot raw[2][kRowsMaxRanks];            // [parity][src rank]: HDR raw statistics blocks
+};
+struct RowsSegment {
+  unsigned long long dst_off, src_off;          // byte offsets into the peer's / this rank's workspace
+  unsigned int bytes;                           // multiple of 16
+  int peer;                                     // destination rank
+  int kind;                                     // 0 plain, 1 GroupNorm sums -> table slot, 2 raw statistics -> table slot
+  int pad;
+};
+struct RowsPushArgs {
+  uint8_t* ws;
+  uint8_t* peers[kRowsMaxRanks];                // every rank's workspace as mapped into this process (own included)
+  unsigned long long off_mail;
+  int rank, world, n_seg, pad;
+  RowsSegment seg[72];
+};
+int launch_rows_push(const RowsPushArgs& a, int blocks, cudaStream_t s);
+int launch_rows_wait(uint8_t* ws, size_t off_mail, int world, size_t allreduce_off, int allreduce_count, size_t raw_off,
+                     bool has_raw, cudaStream_t s);
+
 // ---- per-op device timing (diagnostics; enabled by hdrvae_profile_begin) -----------------------------
 struct ProfEntry { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
 extern bool g_prof_on;

@@ -204,10 +204,12 @@ class HdrVaeEngine:
             z = latent_full.to(device=self.device, dtype=torch.float32).contiguous()
             need = self.rows_workspace_bytes(h, w, world)
             ws = workspace if workspace is not None else torch.empty(need, dtype=torch.uint8, device=self.device)
+            # `workspace` may also be a (device pointer, bytes) pair: a library-owned, IPC-shared allocation (sharding.RowsDirect)
+            ws_ptr, ws_bytes = (ws if isinstance(ws, tuple) else (ws.data_ptr(), ws.numel()))
             out = torch.empty((1, 8 * h // world, 8 * w, 3), dtype=torch.float32, device=self.device)
             state = C.c_void_p()
             N.check(self.lib.hdrvae_rows_begin(self._ctx, z.data_ptr(), h, w, rank, world, mode, factor, float(ev_multiplier),
-                                               out.data_ptr(), ws.data_ptr(), ws.numel(), C.byref(state)), "hdrvae_rows_begin")
+                                               out.data_ptr(), ws_ptr, ws_bytes, C.byref(state)), "hdrvae_rows_begin")
         return state, ws, out, z
 
     def rows_run(self, state) -> "N.HdrvaeExchange":

@@ -151,6 +151,8 @@ def decode_batch_sharded(engine, latent_local: torch.Tensor, hdr_mode: str, ev_m
 # all-reduced.  Here the exchanges are NCCL collectives / point-to-point (torch.distributed) on views of the
 # workspace; `decode_rows_emulated` performs the same exchanges with plain copies between R workspaces of ONE
 # process, which is how the path is tested on a single GPU.
+import ctypes as C  # noqa: E402
+
 from . import _native as _N  # noqa: E402
 
 
@@ -240,68 +242,63 @@ def decode_rows_emulated(engine, latent_full: torch.Tensor, world: int, hdr_mode
     return torch.cat(outs, dim=1), stats[0]
 
 
-class RowsP2P:
-    """Row-tiled decode with the conv halos pushed straight into the neighbours' workspaces over NVLink peer-to-peer
-    (CUDA IPC mappings of the neighbour ranks' workspace; the library issues one stream-ordered peer copy per halo row
-    right after the conv that produced it: hdrvae_rows_set_peers) instead of NCCL send/recv.  The GroupNorm all-reduce that accompanies every halo exchange doubles as the synchronisation: a
-    rank's all-reduce kernel is stream-ordered after its pushes, so when the all-reduce completes on a rank every
-    neighbour's push into that rank has landed; two writes of the same halo row are always separated by at least one
-    all-reduce, so a push can never overtake the neighbour's last read of the previous contents.  One NCCL call per
-    exchange point instead of three.  K/V all-gather and the HDR statistics stay on NCCL.
-
-    The mappings use torch's CUDA-IPC plumbing (`UntypedStorage._share_cuda_` / `_new_shared_cuda`, the private calls
-    behind torch.multiprocessing's tensor sharing) — the one place this package leans on a private torch API; the C ABI
-    itself only sees raw pointers (any cudaIpcOpenMemHandle mapping will do).
-    The workspace is persistent (the IPC handles are exchanged once, in the constructor); `decode` may be called any
-    number of times for latents of the shape given at construction."""
+class RowsDirect:
+    """Row-tiled decode with DEVICE-DRIVEN exchanges (csrc/rows_p2p.cu): every rank's workspace is allocated by the
+    library and shared over CUDA IPC (hdrvae_peer_alloc / hdrvae_peer_open — no private torch API; torch.distributed is
+    used once, to all-gather the 64-byte handles); `decode` then enqueues the WHOLE step program in one C call: at every
+    exchange point a push kernel stores this rank's halo rows, GroupNorm sums, attention K / V rows and HDR statistics
+    straight into the peers' workspaces over NVLink behind a two-phase flag handshake, and a wait kernel folds the sums in
+    rank order.  No NCCL call and no host round trip on the data path (the NCCL transport returns to Python ~35 times per
+    decode).  One process per GPU; the workspace is persistent, `decode` may be called any number of times for latents of
+    the shape given at construction."""
 
     def __init__(self, engine, h: int, w: int, group=None):
         self.engine, self.group, self.h, self.w = engine, group, h, w
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        need = engine.rows_workspace_bytes(h, w, self.world)
+        lib, ctx = engine.lib, engine._ctx
+        self.bytes = engine.rows_workspace_bytes(h, w, self.world)
+        self._own = C.c_void_p()
+        handle = _N.HdrvaeIpcHandle()
         with torch.cuda.device(engine.device):
-            self.ws = torch.empty(need, dtype=torch.uint8, device=engine.device)
-            torch.cuda.synchronize(engine.device)
-        info = (self.ws.untyped_storage()._share_cuda_(), self.ws.storage_offset(), need)
-        infos = [None] * self.world
-        dist.all_gather_object(infos, info, group=group)
-        self.peers = {}
-        for r in (self.rank - 1, self.rank + 1):
-            if 0 <= r < self.world:
-                share, offset, size = infos[r]
-                storage = torch.UntypedStorage._new_shared_cuda(*share)
-                t = torch.empty(0, dtype=torch.uint8, device=torch.device("cuda", share[0])).set_(storage)
-                self.peers[r] = t[offset:offset + size]
-        dist.barrier(group=group)       # nobody frees or reuses its workspace before every mapping exists
-
-    def _exchange(self, ex) -> None:
-        ws, rank, world = self.ws, self.rank, self.world
-        if ex.kind & _N.EX_HALO:
-            raise RuntimeError("the library did not push the halo rows (hdrvae_rows_set_peers not in effect)")
-        if ex.kind & _N.EX_ALLREDUCE_F64:
-            buf = ws[ex.allreduce_off:ex.allreduce_off + 8 * ex.allreduce_count].view(torch.float64)
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-        elif ex.kind & _N.EX_HALO_PUSHED:
-            dist.barrier(group=self.group)      # no all-reduce at this point: explicit synchronisation
-        if ex.kind & _N.EX_ALLGATHER:
-            for i in range(ex.n_gather):
-                n = ex.gather_bytes_per_rank[i]
-                full = ws[ex.gather_off[i]:ex.gather_off[i] + n * world]
-                dist.all_gather_into_tensor(full, full[rank * n:(rank + 1) * n].clone(), group=self.group)
-        if ex.kind & _N.EX_RAW_STATS:
-            allreduce_raw_stats(*_raw_views(ws, ex.raw_stats_off), group=self.group)
+            _N.check(lib.hdrvae_peer_alloc(ctx, self.bytes, C.byref(self._own), C.byref(handle)), "hdrvae_peer_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.bytes), group=group)
+        self._mapped = {}
+        ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = self._own.value
+                continue
+            h_r = _N.HdrvaeIpcHandle()
+            C.memmove(h_r.bytes, handles[r], 64)
+            m = C.c_void_p()
+            _N.check(lib.hdrvae_peer_open(ctx, C.byref(h_r), C.byref(m)), "hdrvae_peer_open")
+            self._mapped[r] = m
+            ptrs[r] = m.value
+        self._ptrs = ptrs
+        dist.barrier(group=group)       # nobody starts pushing before every mapping exists
 
     def decode(self, latent_full: torch.Tensor, hdr_mode: str, ev_multiplier: float = 1.0, want_stats: bool = True):
         if tuple(latent_full.shape[-2:]) != (self.h, self.w):
-            raise ValueError(f"this RowsP2P was built for {self.h}x{self.w} latents, got {tuple(latent_full.shape)}")
+            raise ValueError(f"this RowsDirect was built for {self.h}x{self.w} latents, got {tuple(latent_full.shape)}")
         eng = self.engine
-        state, _ws, out, _keep = eng.rows_begin(latent_full, self.rank, self.world, hdr_mode, ev_multiplier, workspace=self.ws)
-        up = self.peers[self.rank - 1].data_ptr() if self.rank > 0 else None
-        down = self.peers[self.rank + 1].data_ptr() if self.rank < self.world - 1 else None
-        _N.check(eng.lib.hdrvae_rows_set_peers(state, up, down), "hdrvae_rows_set_peers")
-        while True:
-            ex = eng.rows_run(state)
-            if ex.kind == _N.EX_END:
-                break
-            self._exchange(ex)
+        state, _ws, out, _keep = eng.rows_begin(latent_full, self.rank, self.world, hdr_mode, ev_multiplier,
+                                                workspace=(self._own.value, self.bytes))
+        _N.check(eng.lib.hdrvae_rows_set_peers(state, self._ptrs, self.world), "hdrvae_rows_set_peers")
+        with torch.cuda.device(eng.device):
+            _N.check(eng.lib.hdrvae_rows_run_direct(state, eng._stream()), "hdrvae_rows_run_direct")
         return out, eng.rows_end(state, want_stats)
+
+    def close(self) -> None:
+        """Collective: every rank must call it (a rank may only free its workspace once nobody maps it any more)."""
+        if getattr(self, "_own", None) is None:
+            return
+        lib, ctx = self.engine.lib, self.engine._ctx
+        torch.cuda.synchronize(self.engine.device)
+        dist.barrier(group=self.group)
+        for m in self._mapped.values():
+            lib.hdrvae_peer_close(ctx, m)
+        self._mapped = {}
+        dist.barrier(group=self.group)
+        lib.hdrvae_peer_free(ctx, self._own)
+        self._own = None
