@@ -250,7 +250,7 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
-  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_f32, off_s, off_p, off_inv, off_part, off_epi, off_lat_in, off_img, total;
+  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_f32, off_s, off_p, off_inv, off_part, off_ml, off_epi, off_lat_in, off_img, total;
 };
 static constexpr long long kScoreBudgetElems = 1024ll << 20;  // fp32 score chunk <= 4 GiB (K and V^T are re-read once per chunk)
 static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
@@ -289,7 +289,8 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false, bool high = f
   pl.off_s = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 4 : 0);
   pl.off_p = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 2 * km : 0);
   pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);      // 1 / row sum, and -row max of the two-pass soft-max
-  pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);   // split-K partials of the PV GEMM
+  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials: PV GEMM (GEMM-level form) / key splits (fused kernel)
+  pl.off_ml = take((size_t)kSplitRowsBudget * 2 * 4);          // key splits of the fused kernel: (m, l) per row and split
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
   pl.off_lat_in = take(attn_only ? 0 : (size_t)B * 16 * pl.T * 4);          // graph input: fp32 latent copy
   pl.off_img = take(attn_only ? 0 : (size_t)B * 64 * pl.T * 3 * 4);        // graph output: fp32 BHWC image
@@ -411,12 +412,14 @@ static int attention_cta_group(hdrvae_ctx* ctx) {
 // Attention of n_q query rows (q: 16-bit, row stride 1024) against T keys (k: row stride 1024, rows >= T zero up to
 // Tp) and v^T [512][Tp]; o: 16-bit [n_q][512].  Scratch (S, P, 1/sum, split-K partials) comes from the plan.
 static int attention_rows(hdrvae_ctx* ctx, uint8_t* ws, size_t off_s, size_t off_p, size_t off_inv, size_t off_part,
-                          int s_rows, const uint16_t* q, int n_q, const uint16_t* k, const uint16_t* v, int T, int Tp,
+                          size_t off_ml, int s_rows, const uint16_t* q, int n_q, const uint16_t* k, const uint16_t* v, int T, int Tp,
                           uint16_t* o, float qk_alpha, cudaStream_t s) {
   const int impl = ctx->conv_impl, dt = ctx->op_dtype;
   if (attention_fused_enabled(ctx)) {
     // ONE launch: flash-style kernel, scores and probabilities never leave the SM (attention.cu)
-    return launch_attention_fused(q, 1024, 0, n_q, k, 1024, 0, Tp, v, Tp, 0, T, o, 0, 1, dt, qk_alpha, attention_cta_group(ctx), s);
+    return launch_attention_fused(q, 1024, 0, n_q, k, 1024, 0, Tp, v, Tp, 0, T, o, (long long)n_q * 512, 1, dt, qk_alpha,
+                                  attention_cta_group(ctx), ctx->num_sms, reinterpret_cast<float*>(ws + off_part),
+                                  reinterpret_cast<float*>(ws + off_ml), kSplitRowsBudget, s);
   }
   float* S = reinterpret_cast<float*>(ws + off_s);
   uint16_t* P = reinterpret_cast<uint16_t*>(ws + off_p);
@@ -552,11 +555,12 @@ static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, cons
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk);
     return launch_attention_fused(q, 1024, (long long)pl.Tp * 1024, pl.T, q + 512, 1024, (long long)pl.Tp * 1024, pl.Tp, vt, pl.Tp,
                                   (long long)512 * pl.Tp, pl.T, o, (long long)pl.T * 512, pl.B, ctx->op_dtype, qk_alpha,
-                                  attention_cta_group(ctx), s);
+                                  attention_cta_group(ctx), ctx->num_sms, reinterpret_cast<float*>(ws + pl.off_part),
+                                  reinterpret_cast<float*>(ws + pl.off_ml), kSplitRowsBudget, s);
   }
   for (int b = 0; b < pl.B; ++b) {
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk) + (size_t)b * pl.Tp * 1024;
-    HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.s_rows, q, pl.T, q + 512,
+    HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.off_ml, pl.s_rows, q, pl.T, q + 512,
                               reinterpret_cast<const uint16_t*>(vt) + (size_t)b * 512 * pl.Tp, pl.T, pl.Tp,
                               reinterpret_cast<uint16_t*>(o) + (size_t)b * pl.T * 512, qk_alpha, s));
   }
@@ -660,7 +664,7 @@ static int check_ws(const Plan& pl, void* ws, size_t bytes) {
 struct RowsPlan {
   int h, w, hl, world, T, Tl, Tp, s_rows, gn_chunks;
   size_t off_lat, off_x, off_h, off_t, off_xa, off_xb, off_gn, off_qk, off_v, off_vt, off_o, off_s, off_p, off_inv,
-      off_part, off_epi, off_mail, total;
+      off_part, off_ml, off_epi, off_mail, total;
 };
 
 static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true) {
@@ -695,7 +699,8 @@ static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true
   pl.off_s = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 4 : 0);      // GEMM-level attention only (see make_plan)
   pl.off_p = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 2 : 0);
   pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);
-  pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);
+  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);
+  pl.off_ml = take((size_t)kSplitRowsBudget * 2 * 4);
   pl.off_epi = take(epilogue_scratch_bytes(1, 8 * pl.hl, 8 * w));
   pl.off_mail = take(sizeof(RowsMailbox));              // flags / tables of the device-driven exchanges (rows_p2p.cu)
   pl.total = off;
@@ -891,7 +896,7 @@ static int build_rows_program(hdrvae_rows* st) {
     rows_exchange(st, ex);
     rows_compute(st, [=](cudaStream_t s) {
       HDRVAE_TRY(launch_transpose_pad(vb, vt, pl.T, 512, pl.Tp, s));
-      HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.s_rows, qk + (size_t)rank * pl.Tl * 1024,
+      HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.off_ml, pl.s_rows, qk + (size_t)rank * pl.Tl * 1024,
                                 pl.Tl, qk + 512, vt, pl.T, pl.Tp, o, 1.0f, s));
       ConvIO io; io.x = o; io.y = x; io.residual = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = 0; io.y_pad = 1;
       return run_conv(ctx, ctx->proj_out, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);

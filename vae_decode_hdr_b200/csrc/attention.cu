@@ -19,6 +19,8 @@
 // fp16 and the O correction runs a handful of times per row instead of once per key block.
 //
 // Tensor-pipe order: S_0, S_1, PV_0, S_2, PV_1, ...: soft-max of block j overlaps S_{j+1} and PV_{j-1}.
+#include <algorithm>
+
 #include "engine.cuh"
 #include "ptx.cuh"
 
@@ -44,6 +46,12 @@ struct AttnParams {
   uint16_t* o;        // [n_img][n_q][512] 16-bit
   long long o_img_stride;
   int bf16;
+  // key splitting (few work units: small images, or one rank's share of a row-tiled image): the key blocks are divided
+  // over `key_splits` units per (query group, d_v half); every unit writes its UN-normalised fp32 O rows and its
+  // (reference maximum, row sum) and attn_merge_kernel combines them.  1: one unit sees all keys and stores O / l itself.
+  int key_splits, blocks_per_split;
+  float* o_part;      // [key_splits][n_img][n_q][512] fp32
+  float* ml_part;     // [key_splits][n_img][n_q][2]   (m in the log2 domain, l)
 };
 
 __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -130,12 +138,15 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   // work item: (image, 256-row (CG = 2) or 128-row (CG = 1) query group, d_v half); the two halves are neighbours in the
   // grid so that they stream the same K tiles through L2 at the same time
-  const int unit = blockIdx.x / CG;
+  const int unit0 = blockIdx.x / CG;
+  const int split = unit0 % p.key_splits;
+  const int unit = unit0 / p.key_splits;
   const int half = unit & 1;
   const int groups_per_img = CG == 2 ? p.q_pairs : p.q_pairs * 2;
   const int grp = (unit >> 1) % groups_per_img;
   const int img = (unit >> 1) / groups_per_img;
   const int row0 = grp * (128 * CG) + (int)rank * 128;
+  const int kb0 = split * p.blocks_per_split;                  // first key block of this unit
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
@@ -153,7 +164,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t tmem_o = tmem_base + 256;
-  const int nblk = p.n_blocks;
+  const int nblk = min(p.blocks_per_split, p.n_blocks - kb0);
 
   // Ring slot contents (16 KB each).  K slot: 128 d of a key block — CG = 2: this CTA's 64 keys x (2 x 64 d), two 8 KB
   // boxes; CG = 1: 128 keys x 64 d, one box (then 8 K slots per block instead of 4).  V slot: 128 d_v rows x 64 keys —
@@ -181,10 +192,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * kASlotBytes));
             uint8_t* dst = smem_ring + stage * kASlotBytes;
             if (CG == 2) {
-              ptx::tma_load_3d_pair(dst, &tmK, &full_bar[stage], s4 * 128, i * kABlockKeys + (int)rank * 64, img);
-              ptx::tma_load_3d_pair(dst + 8192, &tmK, &full_bar[stage], s4 * 128 + 64, i * kABlockKeys + (int)rank * 64, img);
+              ptx::tma_load_3d_pair(dst, &tmK, &full_bar[stage], s4 * 128, (kb0 + i) * kABlockKeys + (int)rank * 64, img);
+              ptx::tma_load_3d_pair(dst + 8192, &tmK, &full_bar[stage], s4 * 128 + 64, (kb0 + i) * kABlockKeys + (int)rank * 64, img);
             } else {
-              ptx::tma_load_3d(dst, &tmK, &full_bar[stage], s4 * 64, i * kABlockKeys, img);
+              ptx::tma_load_3d(dst, &tmK, &full_bar[stage], s4 * 64, (kb0 + i) * kABlockKeys, img);
             }
           }
           __syncwarp();
@@ -200,8 +211,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             // CG = 2: v = key chunk, rows = this CTA's 128 of the pair's 256 d_v; CG = 1: v = (key chunk, d_v quarter)
             const int kc = CG == 2 ? v : (v >> 1);
             const int vrow = half * 256 + (CG == 2 ? (int)rank * 128 : (v & 1) * 128);
-            if (CG == 2) ptx::tma_load_3d_pair(dst, &tmV, &full_bar[stage], (i - 1) * kABlockKeys + kc * 64, vrow, img);
-            else ptx::tma_load_3d(dst, &tmV, &full_bar[stage], (i - 1) * kABlockKeys + kc * 64, vrow, img);
+            if (CG == 2) ptx::tma_load_3d_pair(dst, &tmV, &full_bar[stage], (kb0 + i - 1) * kABlockKeys + kc * 64, vrow, img);
+            else ptx::tma_load_3d(dst, &tmV, &full_bar[stage], (kb0 + i - 1) * kABlockKeys + kc * 64, vrow, img);
           }
           __syncwarp();
           if (++stage == kASlots) { stage = 0; phase ^= 1; }
@@ -294,7 +305,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       ptx::mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       ptx::tc_fence_after_sync();
       const uint32_t t_s = tmem_base + lane_addr + (j & 1) * 128;
-      const int nvalid = p.n_keys - j * kABlockKeys;           // >= 128 except in the last block
+      const int nvalid = p.n_keys - (kb0 + j) * kABlockKeys;   // >= 128 except in the last block of the image
       // pass 1: block maximum of this row
       float bm = -INFINITY;
 #pragma unroll 1
@@ -358,24 +369,40 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (CG == 2) ptx::mbar_arrive_cluster(&p_full[j & 1], 0); else ptx::mbar_arrive(&p_full[j & 1]);
       }
     }
-    // output: O / l
+    // output: O / l — or, with key splitting, the un-normalised fp32 rows plus (m, l) for the merge kernel
     ptx::mbar_wait(o_full, (uint32_t)((nblk - 1) & 1));
     ptx::tc_fence_after_sync();
-    const float inv = 1.0f / l;
-    uint16_t* orow = p.o + (long long)img * p.o_img_stride + (long long)grow * 512 + half * 256;
+    if (p.key_splits > 1) {
+      const long long prow = ((long long)split * p.n_img + img) * p.n_q + grow;
+      float* orow = p.o_part + prow * 512 + half * 256;
+      if (half == 0 && grow < p.n_q) *reinterpret_cast<float2*>(p.ml_part + prow * 2) = make_float2(m_ref, l);
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      ptx::tmem_ld_32x32(tmem_o + lane_addr + c * 32, v);
-      ptx::tmem_ld_wait(v);
-      if (grow < p.n_q) {
+      for (int c = 0; c < 8; ++c) {
+        ptx::tmem_ld_32x32(tmem_o + lane_addr + c * 32, v);
+        ptx::tmem_ld_wait(v);
+        if (grow < p.n_q) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint4 o4;
-          o4.x = pack16(__uint_as_float(v[8 * e + 0]) * inv, __uint_as_float(v[8 * e + 1]) * inv, bf16);
-          o4.y = pack16(__uint_as_float(v[8 * e + 2]) * inv, __uint_as_float(v[8 * e + 3]) * inv, bf16);
-          o4.z = pack16(__uint_as_float(v[8 * e + 4]) * inv, __uint_as_float(v[8 * e + 5]) * inv, bf16);
-          o4.w = pack16(__uint_as_float(v[8 * e + 6]) * inv, __uint_as_float(v[8 * e + 7]) * inv, bf16);
-          *reinterpret_cast<uint4*>(orow + c * 32 + e * 8) = o4;
+          for (int e = 0; e < 8; ++e)
+            *reinterpret_cast<uint4*>(orow + c * 32 + e * 4) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+      }
+    } else {
+      const float inv = 1.0f / l;
+      uint16_t* orow = p.o + (long long)img * p.o_img_stride + (long long)grow * 512 + half * 256;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        ptx::tmem_ld_32x32(tmem_o + lane_addr + c * 32, v);
+        ptx::tmem_ld_wait(v);
+        if (grow < p.n_q) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint4 o4;
+            o4.x = pack16(__uint_as_float(v[8 * e + 0]) * inv, __uint_as_float(v[8 * e + 1]) * inv, bf16);
+            o4.y = pack16(__uint_as_float(v[8 * e + 2]) * inv, __uint_as_float(v[8 * e + 3]) * inv, bf16);
+            o4.z = pack16(__uint_as_float(v[8 * e + 4]) * inv, __uint_as_float(v[8 * e + 5]) * inv, bf16);
+            o4.w = pack16(__uint_as_float(v[8 * e + 6]) * inv, __uint_as_float(v[8 * e + 7]) * inv, bf16);
+            *reinterpret_cast<uint4*>(orow + c * 32 + e * 8) = o4;
+          }
         }
       }
     }
@@ -387,6 +414,29 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     ptx::tc_fence_after_sync();
     if (CG == 2) ptx::tmem_dealloc_pair<512>(tmem_base); else ptx::tmem_dealloc<512>(tmem_base);
   }
+}
+
+// Key splitting, second step: o[row] = sum_s 2^(m_s - M) O_s[row] / sum_s 2^(m_s - M) l_s with M = max_s m_s.
+// One block of 128 threads per query row, 4 columns per thread; splits in ascending order (deterministic).
+__global__ void __launch_bounds__(128) attn_merge_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part,
+                                                         int splits, long long rows, uint16_t* __restrict__ o, int bf16) {
+  const long long row = blockIdx.x;
+  float M = -INFINITY;
+  for (int s = 0; s < splits; ++s) M = fmaxf(M, ml_part[(s * rows + row) * 2]);
+  float L = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float2 ml = *reinterpret_cast<const float2*>(ml_part + (s * rows + row) * 2);
+    const float w = exp2f(ml.x - M);
+    L = fmaf(w, ml.y, L);
+    const float4 v = *reinterpret_cast<const float4*>(o_part + (s * rows + row) * 512 + threadIdx.x * 4);
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+  }
+  const float inv = 1.0f / L;
+  uint2 r;
+  r.x = pack16(acc.x * inv, acc.y * inv, bf16 != 0);
+  r.y = pack16(acc.z * inv, acc.w * inv, bf16 != 0);
+  *reinterpret_cast<uint2*>(o + row * 512 + threadIdx.x * 4) = r;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -429,7 +479,7 @@ int map3d(CUtensorMap* m, const void* base, int dt, long long d0, long long d1, 
 int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride, int n_q, const void* k, long long k_ld,
                            long long k_img_stride, int k_rows, const void* vt, long long vt_ld, long long vt_img_stride,
                            int n_keys, void* o, long long o_img_stride, int n_img, int dt, float alpha, int cta_group,
-                           cudaStream_t s) {
+                           int num_sms, float* part, float* ml, long long part_rows, cudaStream_t s) {
   HDRVAE_REQUIRE(n_q >= 1 && n_keys >= 1 && n_img >= 1 && k_rows >= n_keys && vt_ld >= n_keys, "attention: bad shape");
   HDRVAE_REQUIRE(dt == DT_F16 || dt == DT_BF16, "attention: 16-bit operands only");
   const int CG = cta_group == 1 ? 1 : 2;
@@ -442,6 +492,31 @@ int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride
   p.q_pairs = (n_q + 255) / 256; p.n_img = n_img;
   p.alpha_log2 = alpha * 1.4426950408889634f;
   p.o = reinterpret_cast<uint16_t*>(o); p.o_img_stride = o_img_stride; p.bf16 = dt == DT_BF16 ? 1 : 0;
+  // Key splitting when the work units do not fill whole waves of the chip (a unit = one CTA pair / CTA streaming all the
+  // keys for 256 / 128 query rows and one d_v half): e.g. one rank's 32 768 query rows of a row-tiled 4096^2 image are
+  // 256 pair units = 3.46 waves of 74 pairs (86 % efficiency); two key splits make 6.9 waves (99 %).  HDRVAE_ATTN_SPLITS
+  // forces a count (1 disables).  Needs the caller's scratch (`part`: rows x splits x 512 fp32) and dense [n_img][n_q] output.
+  const long long base_units = (long long)n_img * (CG == 2 ? p.q_pairs : p.q_pairs * 2) * 2;
+  int splits = 1;
+  {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("HDRVAE_ATTN_SPLITS"); forced = e ? atoi(e) : 0; }
+    const long long conc = std::max(1, num_sms / CG);
+    auto eff = [&](int sp) { const long long u = base_units * sp; return (double)u / (double)(((u + conc - 1) / conc) * conc); };
+    const bool can = part != nullptr && ml != nullptr && o_img_stride == (long long)n_q * 512;
+    if (can) {
+      double best = eff(1);
+      for (int sp = 2; sp <= 8; sp *= 2) {
+        if (p.n_blocks / sp < 8 || (long long)n_img * n_q * sp > part_rows) break;
+        if (forced == 0 && eff(sp) > best + 0.04) { best = eff(sp); splits = sp; }
+        if (forced == sp) splits = sp;
+      }
+      if (forced == 1) splits = 1;
+    }
+  }
+  p.key_splits = splits;
+  p.blocks_per_split = (p.n_blocks + splits - 1) / splits;
+  p.o_part = part; p.ml_part = ml;
   static PerDeviceOnce once1, once2;
   if (CG == 2) {
     if (once2.first())
@@ -451,7 +526,7 @@ int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  const long long units = (long long)n_img * (CG == 2 ? p.q_pairs : p.q_pairs * 2) * 2;
+  const long long units = base_units * splits;
   cfg.gridDim = dim3((unsigned)(units * CG));
   cfg.blockDim = dim3(kAThreads);
   cfg.dynamicSmemBytes = kASmemBytes;
@@ -464,6 +539,12 @@ int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride
   else HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_fused_kernel<1>, tmQ, tmK, tmV, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
+  if (splits > 1) {
+    const long long rows = (long long)n_img * n_q;
+    attn_merge_kernel<<<(unsigned)rows, 128, 0, s>>>(part, ml, splits, rows, reinterpret_cast<uint16_t*>(o), p.bf16);
+    HDRVAE_LAUNCHED();
+    HDRVAE_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 

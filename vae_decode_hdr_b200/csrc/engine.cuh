@@ -56,7 +56,7 @@ int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float e
 int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride, int n_q, const void* k, long long k_ld,
                            long long k_img_stride, int k_rows, const void* vt, long long vt_ld, long long vt_img_stride,
                            int n_keys, void* o, long long o_img_stride, int n_img, int dt, float alpha, int cta_group,
-                           cudaStream_t s);
+                           int num_sms, float* part, float* ml, long long part_rows, cudaStream_t s);
 int launch_raw_stats_merge(const hdrvae_raw_stats* blocks, int n, hdrvae_raw_stats* dst, cudaStream_t s);
 
 // ---- device-driven exchanges of the row-tiled decode (rows_p2p.cu) --------------------------------------------
