@@ -76,12 +76,14 @@ def test_known_ill_conditioned_sweep_case(setup):
         assert rel_l2(got, pre.permute(0, 2, 3, 1)) < 3e-3
 
 
-def test_attention_T262144_sampled_rows_vs_fp64(setup):
-    """mid.attn_1 at config C4's size: T = 512 x 512 = 262 144 tokens, d = 512.  hdrvae_attention against an fp64
-    soft-max(q k^T / sqrt(d)) v on 1 024 sampled query rows against ALL keys.  q is scaled so that the soft-max is
-    peaked (scores ~ N(0, 9)): a near-uniform soft-max over 262 144 random keys averages v to ~0 and would test nothing."""
+@pytest.mark.parametrize("T", [512 * 512, 32768 + 64, 65536])
+def test_attention_large_T_sampled_rows_vs_fp64(setup, T):
+    """mid.attn_1 at config C4's size: T = 512 x 512 = 262 144 tokens, d = 512 (and at 32 832 / 65 536 tokens).
+    hdrvae_attention against an fp64 soft-max(q k^T / sqrt(d)) v on 1 024 sampled query rows against ALL keys.  q is
+    scaled so that the soft-max is peaked (scores ~ N(0, 9)): a near-uniform soft-max over 262 144 random keys averages
+    v to ~0 and would test nothing.  T = 262 144 runs the fused kernel with 2 key splits + the merge pass
+    (attention_key_splits: a function of T only); T = 32 832 has a masked tail block."""
     _, eng = setup
-    T = 512 * 512
     g = torch.Generator(device=DEV).manual_seed(7)
     q = (torch.randn(1, T, 512, generator=g, device=DEV) * 3.0).half()
     k = torch.randn(1, T, 512, generator=g, device=DEV).half()

@@ -250,7 +250,7 @@ static int run_gemm(hdrvae_ctx* ctx, int ab_dtype, const void* A, long long lda,
 // ---- workspace plan -----------------------------------------------------------------------------
 struct Plan {
   int B, h, w, T, Tp, s_rows, gn_chunks;
-  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_f32, off_s, off_p, off_inv, off_part, off_ml, off_epi, off_lat_in, off_img, total;
+  size_t off_lat, off_x, off_h, off_t, off_x16, off_x16b, off_gn, off_qk, off_vt, off_o, off_f32, off_s, off_p, off_inv, off_part, off_kpart, kpart_bytes, off_epi, off_lat_in, off_img, total;
 };
 static constexpr long long kScoreBudgetElems = 1024ll << 20;  // fp32 score chunk <= 4 GiB (K and V^T are re-read once per chunk)
 static constexpr int kSplitRowsBudget = 65536;                // rows x splits of fp32 PV partials (128 MiB)
@@ -289,8 +289,12 @@ static Plan make_plan(int B, int h, int w, bool attn_only = false, bool high = f
   pl.off_s = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 4 : 0);
   pl.off_p = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 2 * km : 0);
   pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);      // 1 / row sum, and -row max of the two-pass soft-max
-  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);      // split-K partials: PV GEMM (GEMM-level form) / key splits (fused kernel)
-  pl.off_ml = take((size_t)kSplitRowsBudget * 2 * 4);          // key splits of the fused kernel: (m, l) per row and split
+  pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);   // split-K partials of the PV GEMM
+  // key splits of the fused kernel (fp32 O partials + (m, l) per row and split): the decoder lends its idle fp32 buffer
+  // (off_h: nothing of a ResnetBlock is live across mid.attn_1); the stand-alone attention entry has no such buffer
+  const size_t ksp = (size_t)attention_key_splits(pl.T);
+  pl.kpart_bytes = attn_only && ksp > 1 ? (size_t)B * pl.T * (512 + 2) * 4 * ksp : 0;
+  pl.off_kpart = take(pl.kpart_bytes);
   pl.off_epi = take(attn_only ? 0 : epilogue_scratch_bytes(B, 8 * h, 8 * w));
   pl.off_lat_in = take(attn_only ? 0 : (size_t)B * 16 * pl.T * 4);          // graph input: fp32 latent copy
   pl.off_img = take(attn_only ? 0 : (size_t)B * 64 * pl.T * 3 * 4);        // graph output: fp32 BHWC image
@@ -412,14 +416,19 @@ static int attention_cta_group(hdrvae_ctx* ctx) {
 // Attention of n_q query rows (q: 16-bit, row stride 1024) against T keys (k: row stride 1024, rows >= T zero up to
 // Tp) and v^T [512][Tp]; o: 16-bit [n_q][512].  Scratch (S, P, 1/sum, split-K partials) comes from the plan.
 static int attention_rows(hdrvae_ctx* ctx, uint8_t* ws, size_t off_s, size_t off_p, size_t off_inv, size_t off_part,
-                          size_t off_ml, int s_rows, const uint16_t* q, int n_q, const uint16_t* k, const uint16_t* v, int T, int Tp,
+                          void* ksplit_scratch, size_t ksplit_bytes, int s_rows, const uint16_t* q, int n_q, const uint16_t* k, const uint16_t* v, int T, int Tp,
                           uint16_t* o, float qk_alpha, cudaStream_t s) {
   const int impl = ctx->conv_impl, dt = ctx->op_dtype;
   if (attention_fused_enabled(ctx)) {
     // ONE launch: flash-style kernel, scores and probabilities never leave the SM (attention.cu)
+    // key-split scratch: [splits][n_q][512] fp32 partials, then [splits][n_q][2] (m, l)
+    const int ksp = attention_key_splits(T);
+    const size_t need = (size_t)ksp * n_q * (512 + 2) * 4;
+    float* part = (ksp > 1 && ksplit_scratch != nullptr && ksplit_bytes >= need) ? reinterpret_cast<float*>(ksplit_scratch) : nullptr;
+    HDRVAE_REQUIRE(ksp == 1 || part != nullptr, "attention: key-split scratch too small (%zu < %zu bytes)", ksplit_bytes, need);
     return launch_attention_fused(q, 1024, 0, n_q, k, 1024, 0, Tp, v, Tp, 0, T, o, (long long)n_q * 512, 1, dt, qk_alpha,
-                                  attention_cta_group(ctx), ctx->num_sms, reinterpret_cast<float*>(ws + off_part),
-                                  reinterpret_cast<float*>(ws + off_ml), kSplitRowsBudget, s);
+                                  attention_cta_group(ctx), ctx->num_sms, part, part ? part + (size_t)ksp * n_q * 512 : nullptr,
+                                  (long long)ksp * n_q, s);
   }
   float* S = reinterpret_cast<float*>(ws + off_s);
   uint16_t* P = reinterpret_cast<uint16_t*>(ws + off_p);
@@ -546,21 +555,27 @@ static int run_attention_high(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, cons
   return launch_split3(of, 512, o3, 1536, T, 512, 1.f, 0, s);
 }
 
+// ksplit_scratch: idle memory for the fused kernel's key-split partials ([splits][B*T][512] fp32 + [splits][B*T][2])
 static int run_attention_core(hdrvae_ctx* ctx, const Plan& pl, uint8_t* ws, const void* qk /*[B][Tp][1024]*/,
                               const void* vt /*[B][512][Tp]*/, void* o /*[B][T][512]*/, float qk_alpha,
-                              cudaStream_t s) {
+                              void* ksplit_scratch, size_t ksplit_bytes, cudaStream_t s) {
   if (attention_fused_enabled(ctx)) {
     // all images in one launch
     ProfScope prof("attention fused kernel", 4.0 * pl.B * (double)pl.T * pl.T * 512, 0.0, s);
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk);
+    const int ksp = attention_key_splits(pl.T);
+    const size_t rows = (size_t)pl.B * pl.T, need = (size_t)ksp * rows * (512 + 2) * 4;
+    HDRVAE_REQUIRE(ksp == 1 || (ksplit_scratch != nullptr && ksplit_bytes >= need),
+                   "attention: key-split scratch too small (%zu < %zu bytes)", ksplit_bytes, need);
+    float* part = ksp > 1 ? reinterpret_cast<float*>(ksplit_scratch) : nullptr;
     return launch_attention_fused(q, 1024, (long long)pl.Tp * 1024, pl.T, q + 512, 1024, (long long)pl.Tp * 1024, pl.Tp, vt, pl.Tp,
                                   (long long)512 * pl.Tp, pl.T, o, (long long)pl.T * 512, pl.B, ctx->op_dtype, qk_alpha,
-                                  attention_cta_group(ctx), ctx->num_sms, reinterpret_cast<float*>(ws + pl.off_part),
-                                  reinterpret_cast<float*>(ws + pl.off_ml), kSplitRowsBudget, s);
+                                  attention_cta_group(ctx), ctx->num_sms, part, part ? part + (size_t)ksp * rows * 512 : nullptr,
+                                  (long long)ksp * rows, s);
   }
   for (int b = 0; b < pl.B; ++b) {
     const uint16_t* q = reinterpret_cast<const uint16_t*>(qk) + (size_t)b * pl.Tp * 1024;
-    HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.off_ml, pl.s_rows, q, pl.T, q + 512,
+    HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, nullptr, 0, pl.s_rows, q, pl.T, q + 512,
                               reinterpret_cast<const uint16_t*>(vt) + (size_t)b * 512 * pl.Tp, pl.T, pl.Tp,
                               reinterpret_cast<uint16_t*>(o) + (size_t)b * pl.T * 512, qk_alpha, s));
   }
@@ -624,7 +639,8 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
     }
     {
       ProfScope prof("attention core (QK^T, softmax, PV)", 4.0 * B * (double)pl.T * pl.T * 512, 10.0 * B * (double)pl.T * pl.Tp, s);
-      HDRVAE_TRY(run_attention_core(ctx, pl, ws, qk, vt, o, 1.0f, s));
+      // key-split partials borrow the block-internal fp32 buffer: nothing of a ResnetBlock is live across mid.attn_1
+      HDRVAE_TRY(run_attention_core(ctx, pl, ws, qk, vt, o, 1.0f, st.hbuf, (size_t)B * pl.T * 64 * 256 * 4, s));
     }
     }
     ConvIO io; io.x = o; io.y = st.x; io.residual = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
@@ -664,7 +680,7 @@ static int check_ws(const Plan& pl, void* ws, size_t bytes) {
 struct RowsPlan {
   int h, w, hl, world, T, Tl, Tp, s_rows, gn_chunks;
   size_t off_lat, off_x, off_h, off_t, off_xa, off_xb, off_gn, off_qk, off_v, off_vt, off_o, off_s, off_p, off_inv,
-      off_part, off_ml, off_epi, off_mail, total;
+      off_part, off_epi, off_mail, total;
 };
 
 static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true) {
@@ -699,8 +715,7 @@ static RowsPlan make_rows_plan(int h, int w, int world, bool attn_scratch = true
   pl.off_s = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 4 : 0);      // GEMM-level attention only (see make_plan)
   pl.off_p = take(attn_scratch ? (size_t)pl.s_rows * pl.Tp * 2 : 0);
   pl.off_inv = take(attn_scratch ? (size_t)pl.s_rows * 4 * 2 : 0);
-  pl.off_part = take((size_t)kSplitRowsBudget * 512 * 4);
-  pl.off_ml = take((size_t)kSplitRowsBudget * 2 * 4);
+  pl.off_part = take(attn_scratch ? (size_t)kSplitRowsBudget * 512 * 4 : 0);
   pl.off_epi = take(epilogue_scratch_bytes(1, 8 * pl.hl, 8 * w));
   pl.off_mail = take(sizeof(RowsMailbox));              // flags / tables of the device-driven exchanges (rows_p2p.cu)
   pl.total = off;
@@ -875,6 +890,8 @@ static int build_rows_program(hdrvae_rows* st) {
     uint16_t* vt = reinterpret_cast<uint16_t*>(ws + pl.off_vt);
     uint16_t* o = reinterpret_cast<uint16_t*>(ws + pl.off_o);
     float* x = st->x;
+    float* hscr = st->hbuf;                                   // idle across the attention: lends its memory to the key-split partials
+    const size_t hscr_bytes = (size_t)(8 * pl.hl + 2) * 8 * pl.w * 256 * 4;
     rows_gn(st, x, ctx->attn_norm, false, H, W);
     rows_compute(st, [=](cudaStream_t s) {
       const uint16_t* tl = reinterpret_cast<const uint16_t*>(t) + (size_t)W * 512;      // interior rows of the slab
@@ -896,8 +913,8 @@ static int build_rows_program(hdrvae_rows* st) {
     rows_exchange(st, ex);
     rows_compute(st, [=](cudaStream_t s) {
       HDRVAE_TRY(launch_transpose_pad(vb, vt, pl.T, 512, pl.Tp, s));
-      HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, pl.off_ml, pl.s_rows, qk + (size_t)rank * pl.Tl * 1024,
-                                pl.Tl, qk + 512, vt, pl.T, pl.Tp, o, 1.0f, s));
+      HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, hscr, hscr_bytes, pl.s_rows,
+                                qk + (size_t)rank * pl.Tl * 1024, pl.Tl, qk + 512, vt, pl.T, pl.Tp, o, 1.0f, s));
       ConvIO io; io.x = o; io.y = x; io.residual = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = 0; io.y_pad = 1;
       return run_conv(ctx, ctx->proj_out, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
     });
@@ -1551,7 +1568,7 @@ int hdrvae_attention(hdrvae_ctx* ctx, const void* q, const void* k, const void* 
   }
   const int saved = ctx->op_dtype;
   ctx->op_dtype = dtype;
-  if (r == 0) r = run_attention_core(ctx, pl, ws, qk, vt, o, scale, s);
+  if (r == 0) r = run_attention_core(ctx, pl, ws, qk, vt, o, scale, ws + pl.off_kpart, pl.kpart_bytes, s);
   ctx->op_dtype = saved;
   cudaStreamSynchronize(s);
   cudaFree(ws);

@@ -474,6 +474,24 @@ int map3d(CUtensorMap* m, const void* base, int dt, long long d0, long long d1, 
 
 }  // namespace
 
+// Key splits of the fused kernel, a function of the key count ONLY (never of the query count, the batch or the GPU): a
+// row-tiled decode (few query rows per rank, all keys) and the single-GPU decode of the same image then run the same
+// arithmetic per query row and stay bit-identical.  One split per 1024 key blocks (131 072 keys), at most 8: 1 up to
+// 2048^2, 2 at 4096^2.  It exists for wave quantisation: one rank's 32 768 query rows of a 4096^2 image row-tiled over 8
+// GPUs are 256 pair units = 3.46 waves of the 74 concurrent pairs (86 %); with 2 splits 6.9 waves (99 %).  More splits
+// than needed cost: every unit loads its Q tile and ramps its pipeline again (measured at T = 65 536: 4 splits 9.20 ms
+// against 8.57 ms unsplit), so the rule is as coarse as the C4 case allows.  HDRVAE_ATTN_SPLITS forces a count.
+int attention_key_splits(int n_keys) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("HDRVAE_ATTN_SPLITS"); forced = e ? atoi(e) : 0; }
+  const int n_blocks = (n_keys + kABlockKeys - 1) / kABlockKeys;
+  int splits = 1;
+  while (splits < 8 && n_blocks / (splits * 2) >= 1024) splits *= 2;
+  if (forced >= 1) splits = forced;
+  while (splits > 1 && n_blocks / splits < 8) splits /= 2;
+  return splits;
+}
+
 // q: [n_img][>= n_q rows][q_ld] 16-bit (512 columns used), k: [n_img][k_rows][k_ld] (rows >= n_keys are ignored),
 // vt: [n_img][512][vt_ld] (V transposed: keys contiguous), o: [n_img][n_q][512].  alpha scales q k^T before the soft-max.
 int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride, int n_q, const void* k, long long k_ld,
@@ -492,28 +510,12 @@ int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride
   p.q_pairs = (n_q + 255) / 256; p.n_img = n_img;
   p.alpha_log2 = alpha * 1.4426950408889634f;
   p.o = reinterpret_cast<uint16_t*>(o); p.o_img_stride = o_img_stride; p.bf16 = dt == DT_BF16 ? 1 : 0;
-  // Key splitting when the work units do not fill whole waves of the chip (a unit = one CTA pair / CTA streaming all the
-  // keys for 256 / 128 query rows and one d_v half): e.g. one rank's 32 768 query rows of a row-tiled 4096^2 image are
-  // 256 pair units = 3.46 waves of 74 pairs (86 % efficiency); two key splits make 6.9 waves (99 %).  HDRVAE_ATTN_SPLITS
-  // forces a count (1 disables).  Needs the caller's scratch (`part`: rows x splits x 512 fp32) and dense [n_img][n_q] output.
+  // Key splitting: see attention_key_splits().  Needs the caller's scratch (`part`: splits x rows x 512 fp32, `ml`) and a
+  // dense [n_img][n_q] output; without them one unit streams all the keys.
   const long long base_units = (long long)n_img * (CG == 2 ? p.q_pairs : p.q_pairs * 2) * 2;
-  int splits = 1;
-  {
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("HDRVAE_ATTN_SPLITS"); forced = e ? atoi(e) : 0; }
-    const long long conc = std::max(1, num_sms / CG);
-    auto eff = [&](int sp) { const long long u = base_units * sp; return (double)u / (double)(((u + conc - 1) / conc) * conc); };
-    const bool can = part != nullptr && ml != nullptr && o_img_stride == (long long)n_q * 512;
-    if (can) {
-      double best = eff(1);
-      for (int sp = 2; sp <= 8; sp *= 2) {
-        if (p.n_blocks / sp < 8 || (long long)n_img * n_q * sp > part_rows) break;
-        if (forced == 0 && eff(sp) > best + 0.04) { best = eff(sp); splits = sp; }
-        if (forced == sp) splits = sp;
-      }
-      if (forced == 1) splits = 1;
-    }
-  }
+  (void)num_sms;
+  int splits = attention_key_splits(n_keys);
+  if (part == nullptr || ml == nullptr || o_img_stride != (long long)n_q * 512 || (long long)n_img * n_q * splits > part_rows) splits = 1;
   p.key_splits = splits;
   p.blocks_per_split = (p.n_blocks + splits - 1) / splits;
   p.o_part = part; p.ml_part = ml;

@@ -53,6 +53,7 @@ int launch_epilogue_phase_a_pre(const void* pre, int dtype, int B, int H, int W,
 int launch_split_hi_lo(const float* w, float* w8, int k, cudaStream_t s);
 int launch_epilogue_phase_b(int B, int H, int W, int mode, float factor, float ev, float* out, hdrvae_stats* host_stats,
                             void* scratch, cudaStream_t s);
+int attention_key_splits(int n_keys);
 int launch_attention_fused(const void* q, long long q_ld, long long q_img_stride, int n_q, const void* k, long long k_ld,
                            long long k_img_stride, int k_rows, const void* vt, long long vt_ld, long long vt_img_stride,
                            int n_keys, void* o, long long o_img_stride, int n_img, int dt, float alpha, int cta_group,
