@@ -398,11 +398,11 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv, all conv layers of one step)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained",
-                # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 61 gemm_tc launches of one C2 step
-                # (profiles/r01_step9_ncu_launch_summary_c2.json, captured on this workload with the final build: 37.1 GB
-                # read + 40.3 GB written; includes the attention GEMMs and conv_out).  The kernel is tensor bound; the
-                # figure shows there is no re-read waste (GroupNorm: 43.2 GB measured vs 44.1 GB algorithmic)
-                "traffic": (77.41e9 if (B, L) == (4, 128) else None), "traffic_unit": "bytes per step, all conv launches (ncu)",
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 51 gemm_tc launches of one C2 step
+                # (profiles/r02_ncu_dram_traffic_c2_summary.json, captured on this workload with the round-2 build: 31.7 GB
+                # read + 27.4 GB written; round 1: 79.3 GB over 61 launches).  The kernel is tensor bound; the figure shows
+                # there is no re-read waste (GroupNorm: 36.9 GB measured vs 38.1 GB by the kernels' own byte count)
+                "traffic": (59.13e9 if (B, L) == (4, 128) else None), "traffic_unit": "bytes per step, all conv launches (ncu)",
                 "achieved_executed": executed_tf, "frac_executed": executed_tf / peak_tf,
                 "note": "achieved = algorithmic conv FLOPs (SURVEY 8d) / summed conv launch time of one step; "
                         "achieved_executed discounts the 5/9 of the upsample convs' FLOPs that phase decomposition removes",

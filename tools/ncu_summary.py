@@ -58,5 +58,39 @@ def launches(path, out):
         f.write(f"TOTAL\t{sum(t[0] for t in tot.values())}\t{total:.1f}\t1.0\n")
 
 
+def traffic(path, out):
+    """per-kernel duration + DRAM bytes of ONE decode: the launches between the last two latent_to_nhwc launches of a
+    `--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` CSV (graphs off)."""
+    import json
+    lines = [ln for ln in open(path) if not ln.startswith("==")]
+    rows = list(csv.reader(lines))
+    hdr = rows[0]
+    idi, ki, mi, ui, vi = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+    per = OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= vi:
+            continue
+        d = per.setdefault(int(r[idi]), {"name": r[ki]})
+        v = float(r[vi].replace(",", ""))
+        u = r[ui]
+        scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}.get(u, 1.0)
+        d[r[mi]] = v * scale
+    ids = sorted(per)
+    starts = [i for i in ids if per[i]["name"].startswith("latent_to_nhwc")]
+    lo, hi = starts[-2], starts[-1]
+    summ = OrderedDict()
+    for i in ids:
+        if not (lo <= i < hi):
+            continue
+        d = per[i]
+        name = d["name"].split("<")[0].split("(")[0].replace("void ", "")
+        t = summ.setdefault(name, {"launches": 0, "ms": 0.0, "dram_read_gb": 0.0, "dram_write_gb": 0.0})
+        t["launches"] += 1
+        t["ms"] += d.get("gpu__time_duration.sum", 0.0)
+        t["dram_read_gb"] += d.get("dram__bytes_read.sum", 0.0)
+        t["dram_write_gb"] += d.get("dram__bytes_write.sum", 0.0)
+    json.dump(summ, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"rep": rep, "launches": launches}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"rep": rep, "launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
