@@ -49,12 +49,18 @@ LEGACY_IGNORED_INPUTS = ("max_range", "scale_factor", "enable_negatives")
 MAX_CACHED_ENGINES = 2
 
 
+_IN_COMFYUI: Optional[bool] = None
+
+
 def _in_comfyui() -> bool:
-    try:
-        import comfy.model_management  # noqa: F401
-        return True
-    except Exception:
-        return False
+    global _IN_COMFYUI
+    if _IN_COMFYUI is None:          # probed once: a failed import is not cached by Python and would be retried per call
+        try:
+            import comfy.model_management  # noqa: F401
+            _IN_COMFYUI = True
+        except Exception:
+            _IN_COMFYUI = False
+    return _IN_COMFYUI
 
 
 class HDRVAEDecode:
