@@ -148,7 +148,8 @@ int hdrvae_profile_end(const char* path_or_null);
 int hdrvae_load_weights(hdrvae_ctx* ctx, const hdrvae_weight_desc* descs, int n, int precision);
 
 /* Bytes of caller-provided device workspace hdrvae_decode needs for a latent
- * batch [B,16,h,w]. */
+ * batch [B,16,h,w].  The workspace pointer must be 256-byte aligned (what
+ * cudaMalloc and torch's allocator return). */
 int hdrvae_workspace_bytes(hdrvae_ctx* ctx, int B, int h, int w, size_t* bytes);
 
 /* ---- the hot path ---------------------------------------------------------

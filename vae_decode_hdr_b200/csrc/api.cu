@@ -104,10 +104,12 @@ int pack_conv(hdrvae_ctx* ctx, const float* w, const float* bias, int cout, int 
 
 // Upper bound of the m-tiles (= GroupNorm partial chunks) a conv over an H x W image is split into: the 128-pixel
 // patch choose_tile picks, or the 8 x 16 tiles of the slab variant.
+// A conv writes one partial record per (m-tile, TMEM lane quarter = 32 pixels): 4 per tile (gemm_tc.cu epilogue).
+constexpr int kStatRecordsPerTile = 4;
 static int tiles_for(int H, int W) {
   GemmParams p;
   choose_tile(H, W, &p);
-  return std::max(p.tiles_x * p.tiles_y, ((W + 7) / 8) * ((H + 15) / 16));
+  return kStatRecordsPerTile * std::max(p.tiles_x * p.tiles_y, ((W + 7) / 8) * ((H + 15) / 16));
 }
 
 
@@ -182,7 +184,7 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
       p.out2 = io.y2 ? reinterpret_cast<uint8_t*>(io.y2) + skip * 2 : nullptr;
     }
   }
-  const int tiles = p.tiles_x * p.tiles_y;
+  const int tiles = p.tiles_x * p.tiles_y * kStatRecordsPerTile;      // GroupNorm partial records of one phase
   p.stats = io.stats;
   p.stats_chunks_per_img = phases * tiles;
   if (io.stats_chunks != nullptr) *io.stats_chunks = io.stats != nullptr ? phases * tiles : 0;
@@ -211,18 +213,25 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
   return 0;
 }
 
-// Which convs take the slab form (gemm_tc.cu): every narrow one (<= 64 columns: the upscaler, conv_out); the decoder's
-// 128-column convs unless they add the residual in place (measured slower on 8 x 16 tiles: 1.76 vs 1.57 ms); the
-// 256-column tiles of the 256- and 512-channel levels with or without residual (same-box A/B of the C2 step: 44.3 ->
-// 43.4 ms; the chip runs at its power cap, so the 4x lower L2 -> SM operand traffic also buys clock).  HDRVAE_SLAB=0
-// keeps the tap-reload form everywhere; HDRVAE_SLAB_MAXN / HDRVAE_SLAB_RES move the two thresholds for experiments.
+// Which convs take the slab form (gemm_tc.cu): every 3x3 conv of the decoder and the upscaler that is not an upsample
+// conv (same-box A/B of the C2 step: 44.3 -> 43.4 ms; the chip runs at its power cap, so the 4x lower L2 -> SM operand
+// traffic also buys clock).  The 128-column convs that add the residual in place were the exception in round 1 (8 x 16
+// tiles: 1.76 vs 1.57 ms, their epilogue was the bound); with the round-2 epilogue the slab form wins there too
+// (1.21 vs 1.44 ms).  HDRVAE_SLAB=0 keeps the tap-reload form everywhere; HDRVAE_SLAB_MAXN / HDRVAE_SLAB_RES=0 move
+// the thresholds for experiments.
 bool conv_takes_slab(const PackedConv& pc, const ConvIO& io, int H, int W, int impl) {
   static int slab_on = -1, slab_maxn = -1, slab_res = -1;
   if (slab_on < 0) { const char* e = getenv("HDRVAE_SLAB"); slab_on = (e && atoi(e) == 0) ? 0 : 1; }
   if (slab_maxn < 0) { const char* e = getenv("HDRVAE_SLAB_MAXN"); slab_maxn = e ? atoi(e) : 512; }
-  if (slab_res < 0) { const char* e = getenv("HDRVAE_SLAB_RES"); slab_res = e ? atoi(e) : 0; }
+  if (slab_res < 0) { const char* e = getenv("HDRVAE_SLAB_RES"); slab_res = e ? atoi(e) : 1; }
+  static int slab_up = -1;
+  if (slab_up < 0) { const char* e = getenv("HDRVAE_SLAB_UP"); slab_up = (e && atoi(e) == 0) ? 0 : 1; }
   const bool res_ok = io.residual == nullptr || pc.cout_pad > 128 || slab_res != 0;
-  return slab_on && pc.ks == 3 && !pc.upsample && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
+  if (pc.upsample)    // the decoder's upsample convs (256-column tiles, statistics [+ scaled operand copy] epilogues)
+    return slab_on && slab_up && pc.ks == 3 && pc.w_dtype != DT_F32 && pc.kmul == 1 && impl == HDRVAE_CONV_TCGEN05 && H * W >= 128 &&
+           pc.cout_pad >= 256 && pc.cout_pad <= slab_maxn && io.residual == nullptr && io.stats != nullptr && io.y_dtype == DT_F32 &&
+           io.lrelu == 0.f && io.residual2 == nullptr;
+  return slab_on && pc.ks == 3 && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
          (pc.cout_pad <= 64 || (pc.cout_pad <= slab_maxn && res_ok));
 }
 
@@ -597,6 +606,7 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
   st.gn = ws + pl.off_gn;
   st.gn_chunks = pl.gn_chunks;
   st.pending = 0;
+  HDRVAE_TRY(gn_scratch_reset(st.gn, B, pl.gn_chunks, s));
 
   if (ctx->high) {
     float* latf = reinterpret_cast<float*>(ws + pl.off_f32) + (size_t)pl.Tp * 1536;
@@ -668,7 +678,9 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
 
 static int check_ws(const Plan& pl, void* ws, size_t bytes) {
   HDRVAE_REQUIRE(ws != nullptr && bytes >= pl.total, "hdrvae: workspace too small (%zu < %zu bytes)", bytes, pl.total);
-  HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "hdrvae: workspace must be 1024-byte aligned");
+  // every plan offset is a multiple of 1024; TMA and the vector loads need 16 bytes, cudaMalloc gives 256 and torch's
+  // caching allocator 512 (a 1024-byte demand made small workspaces fail depending on the allocator's history)
+  HDRVAE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "hdrvae: workspace must be 256-byte aligned");
   return 0;
 }
 
@@ -877,6 +889,7 @@ static int build_rows_program(hdrvae_rows* st) {
     rows_compute(st, [=](cudaStream_t s) {
       // latent rows of this rank plus one neighbour row each side (rows outside the image are zero)
       HDRVAE_TRY(launch_latent_rows_to_nhwc(latent, lat, dt, 16, pl.h, pl.w, rank * pl.hl - 1, pl.hl + 2, 64, s));
+      HDRVAE_TRY(gn_scratch_reset(stats, 1, pl.gn_chunks, s));
       ConvIO io; io.x = lat; io.y = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
       return run_conv(ctx, ctx->conv_in, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
     });
@@ -1532,11 +1545,12 @@ int hdrvae_groupnorm_silu(hdrvae_ctx* ctx, const void* x, int x_dtype, int B, in
   const int max_chunks = std::max(1184, gn_chunks);
   void* scratch = nullptr;
   HDRVAE_CUDA_OK(cudaMalloc(&scratch, gn_scratch_bytes(B, C, max_chunks)));
-  int r = 0;
+  int r = gn_scratch_reset(scratch, B, max_chunks, s);
   if (gn_partials != nullptr && gn_chunks > 0)
     HDRVAE_CUDA_OK(cudaMemcpyAsync(scratch, gn_partials, (size_t)B * gn_chunks * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  r = launch_groupnorm(x, x_dtype, y, y_dtype, B, HW, C, gamma, beta, apply_silu != 0, scratch, max_chunks,
-                       gn_partials != nullptr ? gn_chunks : 0, s);
+  if (r == 0)
+    r = launch_groupnorm(x, x_dtype, y, y_dtype, B, HW, C, gamma, beta, apply_silu != 0, scratch, max_chunks,
+                         gn_partials != nullptr ? gn_chunks : 0, s);
   cudaStreamSynchronize(s);
   cudaFree(scratch);
   return r;

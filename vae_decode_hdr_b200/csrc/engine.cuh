@@ -33,6 +33,7 @@ size_t quantile_scratch_bytes();
 int launch_quantiles(const float* x, long long n, const unsigned long long* ranks_host, int nq, float* out, void* scratch,
                      cudaStream_t s);
 size_t gn_scratch_bytes(int B, int C, int max_chunks);
+int gn_scratch_reset(void* scratch, int B, int max_chunks, cudaStream_t s);   // once before a scratch buffer's first use
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
                      const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s,
                      float in_scale = 1.f);

@@ -10,8 +10,8 @@
 // Operands: fp16 or bf16 (kind::f16) for normalised activations x weights, or fp32 read as tf32
 // (kind::tf32) where a conv consumes the raw fp32 residual stream.  Accumulation fp32 in TMEM.
 //
-// Roles (320 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05.mma issuer,
-// warps 2..9 = epilogue (TMEM -> registers -> scale/bias/residual -> global, + GroupNorm partial
+// Roles (384 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05.mma issuer, warps 2..3 idle,
+// warps 4..11 = epilogue (TMEM -> registers -> scale/bias/residual -> global, + GroupNorm partial
 // statistics of the output).  Two TMEM accumulator stages let the epilogue of tile i overlap the
 // MMAs of tile i+1.
 //
@@ -26,10 +26,14 @@ constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;                    // K extent of one stage row (64 x 16-bit or 32 x tf32)
 constexpr int kABytes = kBlockM * kRowBytes;      // 16 KB
 constexpr int kEpilogueThreads = 256;             // 8 warps: 2 per TMEM lane quarter, each taking half of the columns
-constexpr int kNumThreads = 64 + kEpilogueThreads;
+// Warpgroup 0 = warps 0..3: TMA producer, MMA issuer, two idle warps; warpgroups 1 and 2 = the epilogue.  The register
+// file is allotted per 4 warps anyway (a 320-thread CTA got the 168 registers per thread of a 384-thread one), and whole
+// warpgroups let setmaxnreg move registers from the two single-thread roles to the epilogue: 56 + 2 x 224 per thread.
+constexpr int kNumThreads = 128 + kEpilogueThreads;
+constexpr int kRegsControl = 56, kRegsEpilogue = 224;   // 128 * 56 + 256 * 224 = 384 * 168
 
 constexpr int kSmemLimit = 232448;                // 227 KB opt-in shared memory per CTA on sm_100
-constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 4 * 64 * 4 /*stats*/ + 256 /*barriers*/ +
+constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 256 /*barriers*/ +
                            1024 /*align slack*/;
 
 // CG = CTAs cooperating on one MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256-pixel x BLOCK_N
@@ -58,6 +62,7 @@ struct TcConfig {
   static constexpr int kSmemBytes = kStages * kStageBytes + kSlabStages * kSlabBuf + kSmemFixed;
   static_assert(kStages >= (SLAB ? 2 : 3) && kSmemBytes <= kSmemLimit, "shared memory plan does not fit");
   static_assert(SLAB == 0 || ((SLAB == 9 || SLAB == 3 || SLAB == 1) && KSUB == 1), "the slab variant stages 9, 3 or 1 taps of B per pipeline slot");
+  static constexpr bool kFusedTensorFits = kBBytes >= kABytes && kStages >= 4;   // a ring slot holds a 16 KB centre tile
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -67,6 +72,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot per two lanes of epilogue arithmetic.
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
 }
 __device__ __forceinline__ float round_tf32(float v) {
   uint32_t r;
@@ -123,14 +147,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kElemsPerRow = kTf32 ? 32 : 64;   // K elements per stage
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage buffers.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler then knows every derived
+  // pointer is shared memory and emits LDS / STS for the epilogue patches instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   // tap-reload form: [A stages][B stages]; slab form: [B stages][slab ring]
   uint8_t* smem_b = SLAB ? smem : smem + kStages * KSUB * kAT;
   uint8_t* smem_slab = smem + kStages * Cfg::kStageBytes;
   float* stage_s = reinterpret_cast<float*>(smem_slab + Cfg::kSlabStages * Cfg::kSlabBuf);   // [8 warps][32 rows][32 floats]
-  float* stat_s = stage_s + 8 * 1024;                                               // [4 quarters][32 groups][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 64);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + 8 * 1024);
   uint64_t* full_bar = bars;                      // [kStages]
   uint64_t* empty_bar = bars + kStages;           // [kStages]
   uint64_t* tmem_full_bar = bars + 2 * kStages;   // [2]
@@ -178,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_per_tap = p.k_per_tap / kElemsPerRow;
   const int num_kb = p.ntaps * kb_per_tap;
   const int kb2_blocks = SLAB ? p.k2 / kElemsPerRow : 0;      // extra K blocks from the second tensor (fused 1x1 conv)
+  const int ntg = SLAB ? p.ntaps / SLAB : 0;                  // slab form: B stages per K block (taps in groups of SLAB)
 
   // Producer and MMA issuer run as whole (converged) warps with one elected lane issuing: loop state and
   // addresses are then warp-uniform and stay in the uniform datapath that UTMALDG / UTCHMMA read from (a
@@ -185,6 +211,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // A pipeline stage holds KSUB k-sub-blocks (128 bytes of K each), so one full/empty handshake (~380 cycles
   // of latency in the issuing thread) is amortised over 4*KSUB MMAs.
   const int num_groups = (num_kb + KSUB - 1) / KSUB;
+  // (each role's code sits INSIDE the branch that changed its register budget: ptxas applies the smaller budget to
+  // everything after a join of the two)
+  if (warp < 4) {
+  ptx::reg_dec<kRegsControl>();
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0, ss = 0;
@@ -210,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();
           if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
-          for (int tg = 0; tg < 9 / SLAB; ++tg) {
+          for (int tg = 0; tg < ntg; ++tg) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (ptx::elect_one()) {
               if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * Cfg::kBBytes));
@@ -222,29 +252,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
-        {
-          // fused 1x1 conv of the second tensor: per K block its slab (only the centre pixels are used) and ONE tap of
-          // its weights
-          for (int kb = 0; kb < kb2_blocks; ++kb) {
-            ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
-            if (ptx::elect_one()) {
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
-              uint8_t* sa = smem_slab + ss * kSlabBytes;
-              if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA2, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-              else ptx::tma_load_4d(sa, &tmA2, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-            }
-            __syncwarp();
-            if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (ptx::elect_one()) {
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * (BLOCK_N / CG) * kRowBytes));
-              uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-              if (CG == 2) ptx::tma_load_2d_pair(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
-              else ptx::tma_load_2d(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        // fused 1x1 conv of the second tensor: per K block the 8 x 16 centre pixels (a dense 16 KB A tile, no halo) and
+        // ONE tap of its weights, each in a slot of the B-stage ring — the ring is 5 to 7 slots deep, so these short K
+        // blocks (4 MMAs each) stream; through the two-slot slab ring (round-2 first version: a whole 36 KB halo slab per
+        // block) the issuer waited for them longer than it computed (nin-fused 128-column conv: 2.32 M cycles against
+        // 1.25 M of MMA work).
+        for (int kb = 0; kb < kb2_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * kABytes));
+            uint8_t* sa = smem_b + stage * Cfg::kBBytes;
+            if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA2, &full_bar[stage], kb * kElemsPerRow, x0, y0 + p.y_pad, img);
+            else ptx::tma_load_4d(sa, &tmA2, &full_bar[stage], kb * kElemsPerRow, x0, y0 + p.y_pad, img);
           }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * (BLOCK_N / CG) * kRowBytes));
+            uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+            if (CG == 2) ptx::tma_load_2d_pair(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+            else ptx::tma_load_2d(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         continue;
       }
@@ -287,24 +318,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0, sphase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // HDRVAE_GEMM_DBG & 32: CTA 0 reports where its issuer warp waited (cycles) — accumulator hand-back, slab, B stage
+    const bool tim = (p.dbg & 32) != 0;
+    long long w_acc = 0, w_slab = 0, w_b = 0, tq = 0;
+    const long long t_begin = clock64();
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
+      if (tim) tq = clock64();
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      if (tim) w_acc += clock64() - tq;
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
+          if (tim) tq = clock64();
           ptx::mbar_wait(&slab_full_bar[ss], sphase);
+          if (tim) w_slab += clock64() - tq;
           const uint32_t sa = ptx::smem_u32(smem_slab + ss * Cfg::kSlabBuf);
-          for (int tg = 0; tg < 9 / SLAB; ++tg) {
+          for (int tg = 0; tg < ntg; ++tg) {
+            if (tim) tq = clock64();
             ptx::mbar_wait(&full_bar[stage], phase);
+            if (tim) w_b += clock64() - tq;
             ptx::tc_fence_after_sync();
             if (ptx::elect_one()) {
               const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
               for (int tt = 0; tt < SLAB; ++tt) {
                 // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
+                // (9 taps of a 3x3 conv, or the 4 taps of one output phase of an upsample conv)
                 const int t = tg * SLAB + tt;
-                const uint32_t a_off = (uint32_t)(((t / 3) * Cfg::kPitch + (t % 3)) * kRowBytes);
+                const uint32_t a_off = (uint32_t)(((p.tap_dy[t] + 1) * Cfg::kPitch + (p.tap_dx[t] + 1)) * kRowBytes);
                 const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, Cfg::kPitch * kRowBytes);
                 const uint64_t db = ptx::make_sw128_kmajor_desc(sb + tt * (BLOCK_N / CG) * kRowBytes);
 #pragma unroll
@@ -315,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
               if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
-              if (tg == 9 / SLAB - 1) {
+              if (tg == ntg - 1) {
                 if (CG == 2) ptx::umma_commit_pair(&slab_empty_bar[ss]); else ptx::umma_commit(&slab_empty_bar[ss]);
                 if (kb == kb_per_tap - 1 && kb2_blocks == 0) {
                   if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
@@ -328,35 +370,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
         }
         for (int kb = 0; kb < kb2_blocks; ++kb) {
-          // fused 1x1 conv: the centre tap of the second tensor's slab against one tap of its weights
-          ptx::mbar_wait(&slab_full_bar[ss], sphase);
+          // fused 1x1 conv: the second tensor's centre tile (ring slot `sa_stage`) against one tap of its weights (next slot)
+          if (tim) tq = clock64();
           ptx::mbar_wait(&full_bar[stage], phase);
+          const int sa_stage = stage;
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          ptx::mbar_wait(&full_bar[stage], phase);
+          if (tim) w_b += clock64() - tq;
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
-            const uint32_t sa = ptx::smem_u32(smem_slab + ss * Cfg::kSlabBuf);
-            const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
-            const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + (uint32_t)((Cfg::kPitch + 1) * kRowBytes), Cfg::kPitch * kRowBytes);
-            const uint64_t db = ptx::make_sw128_kmajor_desc(sb);
+            const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + sa_stage * Cfg::kBBytes));
+            const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (CG == 2) ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
               else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
             }
-            if (CG == 2) ptx::umma_commit_pair(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
-            if (CG == 2) ptx::umma_commit_pair(&slab_empty_bar[ss]); else ptx::umma_commit(&slab_empty_bar[ss]);
+            if (CG == 2) { ptx::umma_commit_pair(&empty_bar[sa_stage]); ptx::umma_commit_pair(&empty_bar[stage]); }
+            else { ptx::umma_commit(&empty_bar[sa_stage]); ptx::umma_commit(&empty_bar[stage]); }
             if (kb == kb2_blocks - 1) {
               if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
             }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
-          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       for (int g = 0; g < num_groups; ++g) {
+        if (tim) tq = clock64();
         ptx::mbar_wait(&full_bar[stage], phase);
+        if (tim) w_b += clock64() - tq;
         ptx::tc_fence_after_sync();
         const int nsub = min(KSUB, num_kb - g * KSUB);
         if (ptx::elect_one()) {
@@ -389,7 +434,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 2 && (warp - 2) < kActiveEpiWarps) {
+    if (tim && blockIdx.x == 0 && lane == 0)
+      printf("gemm_tc<%d,cg%d,epi%d,slab%d> issuer: %lld cycles, %d tiles x %d k-blocks; waited: accumulator %lld, slab %lld, B stage %lld\n",
+             BLOCK_N, CG, EPI, SLAB, clock64() - t_begin, (num_tiles - w_first + w_step - 1) / w_step, num_kb, w_acc, w_slab, w_b);
+  }
+  } else {
+  ptx::reg_inc<kRegsEpilogue>();
+  if ((warp - 4) < kActiveEpiWarps) {
     // ------------------------------------------------------------ epilogue (8 warps; 128 TMEM lanes x 2 column halves)
     // TMEM hands every thread one accumulator ROW (pixel).  Writing rows straight to global memory makes each
     // warp-level access touch 32 different 128-byte lines (ncu: 31 sectors/request, LSU wavefront bound), so
@@ -411,10 +462,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float lrelu = p.lrelu, res_scale = p.res_scale;
     const int n_store = p.n_store > 0 ? p.n_store : p.n_cols;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int we = warp - 2;                // 0..7
+    const int we = warp - 4;                // 0..7
     const int half = we >> 2;               // which half of the tile's columns this warp drains
-    const int et = threadIdx.x - 64;        // 0..255
-    const int cpg = p.n_cols >> 5;          // channels per GroupNorm group (stats only; n_cols % 128 == 0 there)
+    const int cpg = p.n_cols >> 5;          // channels per GroupNorm group (stats only: 4, 8 or 16 there)
+    const int cpg_log2 = cpg >= 16 ? 4 : cpg >= 8 ? 3 : 2;
+    const int slots_per_group = cpg >> 2;   // 1, 2 or 4
     const int slot = lane & 7;              // 4-channel slot inside the 32-column chunk
     const int sr = lane >> 3;               // pixel sub-row 0..3 handled by this lane in each iteration
     float4* patch = reinterpret_cast<float4*>(stage_s) + we * 256;      // [32 rows][8 float4], XOR-swizzled
@@ -434,8 +486,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long long o2_row = out2_own ? p.out2_row_stride : p.out_row_stride;
     const long long o2_px = out2_own ? p.out2_px_stride : p.out_px_stride;
     const bool wide = p.tw_log2 >= 5;       // a warp's 32 pixels are consecutive in x (all but tiny images)
+    // Fast path (specialised builds, tiles that lie wholly inside the image): the element offset of this lane's 4 columns
+    // of pixel `it` relative to the tile origin is the same for every tile, so it is computed once per kernel; a tile
+    // then costs one (warp-uniform) origin and no per-pixel address arithmetic or bounds masks.
+    constexpr bool kFastBuild = !kGen && (EPI & (EPI_ROWOPS | EPI_ROWMAX | EPI_EXPSUM)) == 0;
+    uint32_t lo[8], lo2[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = q * 32 + it * 4 + sr;
+      const int yy = (row >> p.tw_log2) * p.sy, xx = (row & (p.TW - 1)) * p.sx;
+      lo[it] = (uint32_t)((long long)yy * p.out_row_stride + (long long)xx * p.out_px_stride) + half * (BLOCK_N / 2) + slot * 4;
+      lo2[it] = (uint32_t)((long long)yy * o2_row + (long long)xx * o2_px) + half * (BLOCK_N / 2) + slot * 4;
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool tim = (p.dbg & 32) != 0;     // CTA 0, first epilogue warp: cycles waiting for accumulators / draining them
+    long long w_full = 0, w_drain = 0, tq = 0;
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
       const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
@@ -447,6 +513,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BLOCK_N;
       const int cbase = half * (BLOCK_N / 2);
       const long long img_off = (long long)img * p.out_img_stride + n0;
+      // GroupNorm partial record of this warp: one per (tile, TMEM lane quarter), [32 groups][2]
+      float* const stat_rec = has_stats ? p.stats + (((long long)img * p.stats_chunks_per_img + p.stats_chunk0 + rem * 4 + q) * 32) * 2 : nullptr;
+
+      if constexpr (kFastBuild) {
+        if (tile_live && (ty + 1) * p.TH <= p.H && (tx + 1) * p.TW <= p.W && n0 + BLOCK_N <= n_store) {
+          const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + cbase;
+          const long long ty_off = (long long)(ty * p.TH * p.sy + p.py), tx_off = (long long)(tx * p.TW * p.sx + p.px);
+          const long long org = img_off + ty_off * p.out_row_stride + tx_off * p.out_px_stride;
+          const long long org2 = (long long)img * o2_img + n0 + ty_off * o2_row + tx_off * o2_px;
+          float4 rres[8], rres2[8];
+          auto fetch_res = [&](int ci) {
+            if constexpr ((EPI & EPI_RES) != 0) {
+              const float* r = resf + org + ci * 32;      // plain loads: the residual may alias the output
+#pragma unroll
+              for (int it = 0; it < 8; ++it) rres[it] = *reinterpret_cast<const float4*>(r + lo[it]);
+            }
+            if constexpr ((EPI & EPI_RES2) != 0) {
+              const float* r = p.residual2 + org + ci * 32;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) rres2[it] = *reinterpret_cast<const float4*>(r + lo[it]);
+            }
+          };
+          fetch_res(0);
+          if (tim) tq = clock64();
+          ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+          if (tim) { const long long now = clock64(); w_full += now - tq; tq = now; }
+          ptx::tc_fence_after_sync();
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc, v);
+          const float2 alpha2 = make_float2(alpha, alpha), rs2 = make_float2(res_scale, res_scale);
+          const float2 s16_2 = make_float2(s16, s16), s2_2 = make_float2(s2, s2);
+#pragma unroll 1
+          for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+            if (ci > 0) fetch_res(ci);                    // issued first: overlaps the TMEM wait and the transpose
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cbase + ci * 32 + slot * 4));
+            const float2 b01 = make_float2(bias4.x, bias4.y), b23 = make_float2(bias4.z, bias4.w);
+            ptx::tmem_ld_wait(v);
+            __syncwarp();                                 // previous chunk's readers are done with the patch
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              patch[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            if (ci + 1 < kChunksPerWarp) {
+              ptx::tmem_ld_32x32(t_acc + (ci + 1) * 32, v);   // v has been consumed: start the next chunk's loads now
+            } else {
+              ptx::tc_fence_before_sync();                // the accumulator has been read out: hand it back already
+            }
+            __syncwarp();
+            if (ci + 1 == kChunksPerWarp && lane == 0) {
+              if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+              else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            float4 a[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sr;
+              a[it] = patch[rr * 8 + (slot ^ (rr & 7))];
+            }
+            float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+            const long long ob = org + ci * 32, ob2 = org2 + ci * 32;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float2 t01 = f2_fma(make_float2(a[it].x, a[it].y), alpha2, b01);
+              float2 t23 = f2_fma(make_float2(a[it].z, a[it].w), alpha2, b23);
+              if constexpr ((EPI & EPI_RES) != 0) {
+                t01 = f2_fma(make_float2(rres[it].x, rres[it].y), rs2, t01);
+                t23 = f2_fma(make_float2(rres[it].z, rres[it].w), rs2, t23);
+              }
+              if constexpr ((EPI & EPI_RES2) != 0) {
+                t01 = f2_add(t01, make_float2(rres2[it].x, rres2[it].y));
+                t23 = f2_add(t23, make_float2(rres2[it].z, rres2[it].w));
+              }
+              if constexpr ((EPI & EPI_LRELU) != 0) {
+                t01.x = t01.x < 0.f ? t01.x * lrelu : t01.x; t01.y = t01.y < 0.f ? t01.y * lrelu : t01.y;
+                t23.x = t23.x < 0.f ? t23.x * lrelu : t23.x; t23.y = t23.y < 0.f ? t23.y * lrelu : t23.y;
+              }
+              if constexpr ((EPI & EPI_OUT2) != 0) {
+                const float2 u01 = f2_mul(t01, s2_2), u23 = f2_mul(t23, s2_2);
+                uint2 o2;
+                if (out2_bf) { o2.x = pack_bf16x2(u01.x, u01.y); o2.y = pack_bf16x2(u23.x, u23.y); }
+                else { o2.x = pack_f16x2(u01.x, u01.y); o2.y = pack_f16x2(u23.x, u23.y); }
+                *reinterpret_cast<uint2*>(out2h + ob2 + lo2[it]) = o2;
+              }
+              if constexpr ((EPI & EPI_OUT16) != 0) {
+                const float2 u01 = f2_mul(t01, s16_2), u23 = f2_mul(t23, s16_2);
+                uint2 o;
+                if (out16_bf) { o.x = pack_bf16x2(u01.x, u01.y); o.y = pack_bf16x2(u23.x, u23.y); }
+                else { o.x = pack_f16x2(u01.x, u01.y); o.y = pack_f16x2(u23.x, u23.y); }
+                *reinterpret_cast<uint2*>(outh + ob + lo[it]) = o;
+              } else {
+                *reinterpret_cast<float4*>(outf + ob + lo[it]) = make_float4(t01.x, t01.y, t23.x, t23.y);
+              }
+              if constexpr ((EPI & EPI_STATS) != 0) {
+                sum2 = f2_add(sum2, t01); sum2 = f2_add(sum2, t23);
+                sq2 = f2_fma(t01, t01, sq2); sq2 = f2_fma(t23, t23, sq2);
+              }
+            }
+            if constexpr ((EPI & EPI_STATS) != 0) {
+              // this lane: (sum, sum of squares) of 4 channels x 8 pixels; fold the 4 pixel sub-rows (lanes +8, +16, +24),
+              // then the slots that share a group; the group's first slot writes the warp's partial straight to its record
+              float s_acc = sum2.x + sum2.y, q_acc = sq2.x + sq2.y;
+              s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 8);  q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 8);
+              s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 16); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 16);
+              if (cpg >= 8) { s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 1); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 1); }
+              if (cpg >= 16) { s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 2); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 2); }
+              if (lane < 8 && (slot & (slots_per_group - 1)) == 0) {
+                const int gg = (n0 + cbase + ci * 32 + slot * 4) >> cpg_log2;      // group index in the layer
+                if (gg < 32) *reinterpret_cast<float2*>(stat_rec + gg * 2) = make_float2(s_acc, q_acc);
+              }
+            }
+          }
+          if (tim) w_drain += clock64() - tq;
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+      }
 
       // coalesced-layout geometry of the 8 pixels this lane touches per chunk
       long long poff[8];
@@ -554,11 +737,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t cm = (n0 + colx) < n_store ? pmask : 0u;
 #pragma unroll
         for (int it = 0; it < 8; ++it)
-          if (cm >> it & 1) dst[it] = *reinterpret_cast<const float4*>(resf + poff[it] + colx);   // plain load: may alias out
+          dst[it] = (cm >> it & 1) ? *reinterpret_cast<const float4*>(resf + poff[it] + colx)   // plain load: may alias out
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       load_res(0, rres_buf[0]);
       if (kPre == 2) load_res(1, rres_buf[kPre - 1]);
+      if (tim) tq = clock64();
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (tim) { const long long now = clock64(); w_full += now - tq; tq = now; }
       ptx::tc_fence_after_sync();
       uint32_t v[32];
       ptx::tmem_ld_32x32(t_row + cbase, v);
@@ -574,7 +760,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (has_res2) {
 #pragma unroll
           for (int it = 0; it < 8; ++it)
-            if (cmask >> it & 1) rres2[it] = *reinterpret_cast<const float4*>(p.residual2 + poff[it] + col);
+            rres2[it] = (cmask >> it & 1) ? *reinterpret_cast<const float4*>(p.residual2 + poff[it] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!(row_ops && p.bias_per_row) && p.bias != nullptr && cmask != 0u) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
@@ -588,73 +774,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tmem_ld_32x32(t_row + c0 + 32, v);
         }
         __syncwarp();
-        float s_acc = 0.f, q_acc = 0.f;
+        // All 8 patch reads are issued back to back and the arithmetic is branch-free (only the stores are predicated):
+        // with a branch per pixel the compiler serialised load -> use 8 times per chunk and the two epilogue warps of
+        // a scheduler could not cover the latency (ncu round 2: 22 % of all stall samples on the first use of each read;
+        // the 128 -> 128 convs were epilogue-paced at 72 % tensor-pipe activity while 256 -> 128 reached 92 %).
+        float4 a[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + sr;
-          float4 a = patch[rr * 8 + (slot ^ (rr & 7))];
-          if (cmask >> it & 1) {
-            float scale = alpha;
-            if (row_ops) {
-              // per-row scale / bias (attention GEMMs); x of this pixel: rows are consecutive there (H = 1)
-              const int xr = x_first + it * 4;
-              if (p.row_scale != nullptr) scale *= __ldg(p.row_scale + xr);
-              if (p.bias_per_row) {
-                const float rb = p.bias != nullptr ? __ldg(p.bias + xr) : 0.f;
-                bias4 = make_float4(rb, rb, rb, rb);
-              }
+          a[it] = patch[rr * 8 + (slot ^ (rr & 7))];
+        }
+        float s_acc = 0.f, q_acc = 0.f;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const bool live = (cmask >> it & 1) != 0;
+          float4 t = a[it];
+          float scale = alpha;
+          if (row_ops && live) {
+            // per-row scale / bias (attention GEMMs); x of this pixel: rows are consecutive there (H = 1)
+            const int xr = x_first + it * 4;
+            if (p.row_scale != nullptr) scale *= __ldg(p.row_scale + xr);
+            if (p.bias_per_row) {
+              const float rb = p.bias != nullptr ? __ldg(p.bias + xr) : 0.f;
+              bias4 = make_float4(rb, rb, rb, rb);
             }
-            a.x = fmaf(a.x, scale, bias4.x); a.y = fmaf(a.y, scale, bias4.y);
-            a.z = fmaf(a.z, scale, bias4.z); a.w = fmaf(a.w, scale, bias4.w);
-            if (has_res_f32) {
-              a.x = fmaf(rres[it].x, res_scale, a.x); a.y = fmaf(rres[it].y, res_scale, a.y);
-              a.z = fmaf(rres[it].z, res_scale, a.z); a.w = fmaf(rres[it].w, res_scale, a.w);
-            }
-            if (has_res2) { a.x += rres2[it].x; a.y += rres2[it].y; a.z += rres2[it].z; a.w += rres2[it].w; }
-            if (has_res_16) {
-              // 16-bit residual (test entry only); plain load: the residual may alias the output
-              const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + poff[it] + col);
-              float2 lo, hi;
-              if (p.res_dtype == DT_BF16) {
-                lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
-                hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
-              } else {
-                lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-                hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-              }
-              a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
-            }
-            if (has_lrelu) {
-              a.x = a.x < 0.f ? a.x * lrelu : a.x; a.y = a.y < 0.f ? a.y * lrelu : a.y;
-              a.z = a.z < 0.f ? a.z * lrelu : a.z; a.w = a.w < 0.f ? a.w * lrelu : a.w;
-            }
-            if (has_out2) {
-              // second, scaled 16-bit copy of the output: the tensor-core operand of a conv that consumes this
-              // (un-normalised) tensor directly; the power-of-two scale keeps fp16 far from overflow
-              uint2 o2;
-              if (out2_bf) { o2.x = pack_bf16x2(a.x * s2, a.y * s2); o2.y = pack_bf16x2(a.z * s2, a.w * s2); }
-              else { o2.x = pack_f16x2(a.x * s2, a.y * s2); o2.y = pack_f16x2(a.z * s2, a.w * s2); }
-              long long off2 = poff[it];
-              if (out2_own) {
-                const int row = wide ? q * 32 + sr + it * 4 : q * 32 + it * 4 + sr;
-                const int y2 = ty * p.TH + (row >> p.tw_log2), x2 = tx * p.TW + (row & (p.TW - 1));
-                off2 = (long long)img * o2_img + n0 + (long long)(y2 * p.sy + p.py) * o2_row + (long long)(x2 * p.sx + p.px) * o2_px;
-              }
-              *reinterpret_cast<uint2*>(out2h + off2 + col) = o2;
-            }
-            if (out_f32) {
-              if (do_round) { a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w); }
-              *reinterpret_cast<float4*>(outf + poff[it] + col) = a;
+          }
+          t.x = fmaf(t.x, scale, bias4.x); t.y = fmaf(t.y, scale, bias4.y);
+          t.z = fmaf(t.z, scale, bias4.z); t.w = fmaf(t.w, scale, bias4.w);
+          if (has_res_f32) {
+            t.x = fmaf(rres[it].x, res_scale, t.x); t.y = fmaf(rres[it].y, res_scale, t.y);
+            t.z = fmaf(rres[it].z, res_scale, t.z); t.w = fmaf(rres[it].w, res_scale, t.w);
+          }
+          if (has_res2) { t.x += rres2[it].x; t.y += rres2[it].y; t.z += rres2[it].z; t.w += rres2[it].w; }
+          if (has_res_16 && live) {
+            // 16-bit residual (test entry only); plain load: the residual may alias the output
+            const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + poff[it] + col);
+            float2 lo, hi;
+            if (p.res_dtype == DT_BF16) {
+              lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+              hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
             } else {
-              uint2 o;
-              if (out16_bf) { o.x = pack_bf16x2(a.x * s16, a.y * s16); o.y = pack_bf16x2(a.z * s16, a.w * s16); }
-              else { o.x = pack_f16x2(a.x * s16, a.y * s16); o.y = pack_f16x2(a.z * s16, a.w * s16); }
-              *reinterpret_cast<uint2*>(outh + poff[it] + col) = o;
+              lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+              hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
             }
-            if (has_stats) {
-              s_acc += (a.x + a.y) + (a.z + a.w);
-              q_acc += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+            t.x += lo.x; t.y += lo.y; t.z += hi.x; t.w += hi.y;
+          }
+          if (has_lrelu) {
+            t.x = t.x < 0.f ? t.x * lrelu : t.x; t.y = t.y < 0.f ? t.y * lrelu : t.y;
+            t.z = t.z < 0.f ? t.z * lrelu : t.z; t.w = t.w < 0.f ? t.w * lrelu : t.w;
+          }
+          if (has_out2) {
+            // second, scaled 16-bit copy of the output: the tensor-core operand of a conv that consumes this
+            // (un-normalised) tensor directly; the power-of-two scale keeps fp16 far from overflow
+            uint2 o2;
+            if (out2_bf) { o2.x = pack_bf16x2(t.x * s2, t.y * s2); o2.y = pack_bf16x2(t.z * s2, t.w * s2); }
+            else { o2.x = pack_f16x2(t.x * s2, t.y * s2); o2.y = pack_f16x2(t.z * s2, t.w * s2); }
+            long long off2 = poff[it];
+            if (out2_own) {
+              const int row = wide ? q * 32 + sr + it * 4 : q * 32 + it * 4 + sr;
+              const int y2 = ty * p.TH + (row >> p.tw_log2), x2 = tx * p.TW + (row & (p.TW - 1));
+              off2 = (long long)img * o2_img + n0 + (long long)(y2 * p.sy + p.py) * o2_row + (long long)(x2 * p.sx + p.px) * o2_px;
             }
+            if (live) *reinterpret_cast<uint2*>(out2h + off2 + col) = o2;
+          }
+          if (out_f32) {
+            if (do_round) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+            if (live) *reinterpret_cast<float4*>(outf + poff[it] + col) = t;
+          } else {
+            uint2 o;
+            if (out16_bf) { o.x = pack_bf16x2(t.x * s16, t.y * s16); o.y = pack_bf16x2(t.z * s16, t.w * s16); }
+            else { o.x = pack_f16x2(t.x * s16, t.y * s16); o.y = pack_f16x2(t.z * s16, t.w * s16); }
+            if (live) *reinterpret_cast<uint2*>(outh + poff[it] + col) = o;
+          }
+          if (has_stats) {
+            const float s4 = (t.x + t.y) + (t.z + t.w);
+            const float q4 = (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+            s_acc += live ? s4 : 0.f;
+            q_acc += live ? q4 : 0.f;
           }
         }
         if (has_stats) {
@@ -664,11 +860,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 16); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 16);
           if (cpg >= 8) { s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 1); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 1); }
           if (cpg >= 16) { s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 2); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 2); }
-          const int slots_per_group = cpg >> 2;           // 1, 2 or 4
-          if (lane < 8 && (slot % slots_per_group) == 0) {
-            const int gl = (c0 + slot * 4) / cpg;          // group index inside this tile (< 32)
-            stat_s[(q * 32 + gl) * 2 + 0] = s_acc;
-            stat_s[(q * 32 + gl) * 2 + 1] = q_acc;
+          if (lane < 8 && (slot & (slots_per_group - 1)) == 0 && tile_live) {
+            const int gg = (n0 + c0 + slot * 4) >> cpg_log2;       // group index in the layer
+            if (gg < 32) *reinterpret_cast<float2*>(stat_rec + gg * 2) = make_float2(s_acc, q_acc);
           }
         }
       }
@@ -678,22 +872,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread owns the accumulators
         else ptx::mbar_arrive(&tmem_empty_bar[acc]);
       }
-      if (has_stats) {
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        const int groups_in_tile = BLOCK_N / cpg;        // 32 or 16
-        if (et < groups_in_tile * 2) {
-          const int gl = et >> 1, k = et & 1;
-          const int gg = n0 / cpg + gl;                  // group index in the layer
-          if (gg < 32 && tile_live) {
-            const float t = ((stat_s[(0 * 32 + gl) * 2 + k] + stat_s[(1 * 32 + gl) * 2 + k]) +
-                             (stat_s[(2 * 32 + gl) * 2 + k] + stat_s[(3 * 32 + gl) * 2 + k]));
-            p.stats[(((long long)img * p.stats_chunks_per_img + p.stats_chunk0 + rem) * 32 + gg) * 2 + k] = t;
-          }
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");   // stat_s is rewritten by the next tile
-      }
+      if (tim) w_drain += clock64() - tq;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (tim && blockIdx.x == 0 && warp == 4 && lane == 0)
+      printf("gemm_tc<%d,cg%d,epi%d,slab%d> epilogue warp 0: waited for accumulators %lld cycles, drained them in %lld\n",
+             BLOCK_N, CG, EPI, SLAB, w_full, w_drain);
+  }
   }
 
   ptx::tc_fence_before_sync();
@@ -750,7 +935,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int 
   }
   if (slab) {
     // B as {K of one tap, Cout rows, 9 taps}: one box brings the 9 taps' [rows][64] tiles of a K block, tap-major
-    cuuint64_t dims[3] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols), 9};
+    cuuint64_t dims[3] = {(cuuint64_t)p.k_per_tap, (cuuint64_t)(p.b_rows > 0 ? p.b_rows : p.n_cols), (cuuint64_t)p.ntaps};
     cuuint64_t strides[2] = {(cuuint64_t)p.b_row_stride * eb, (cuuint64_t)p.k_per_tap * eb};
     cuuint32_t box[3] = {(cuuint32_t)row_elems, (cuuint32_t)block_n, (cuuint32_t)slab};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -778,7 +963,7 @@ static int make_maps(const GemmParams& p, int block_n, TensorMapPair* maps, int 
                    "gemm_tc: second-tensor pointers / strides must be 16-byte aligned");
     cuuint64_t dims[4] = {(cuuint64_t)p.k2, (cuuint64_t)p.W, (cuuint64_t)(p.H + 2 * p.y_pad), (cuuint64_t)p.n_img};
     cuuint64_t strides[3] = {(cuuint64_t)p.a2_px_stride * eb, (cuuint64_t)p.a2_row_stride * eb, (cuuint64_t)p.a2_img_stride * eb};
-    cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)kSlabPitch, (cuuint32_t)kSlabRows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)row_elems, 8, 16, 1};      // the tile's own 8 x 16 pixels: a 1x1 conv needs no halo
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&maps->a2, dt, 4, const_cast<void*>(p.a2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -844,7 +1029,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HDRVAE_REQUIRE(p.k2 == 0 || SLAB > 0, "gemm_tc: a fused second tensor needs the slab form");
+  HDRVAE_REQUIRE(p.k2 == 0 || (SLAB > 0 && Cfg::kFusedTensorFits), "gemm_tc: a fused second tensor needs the slab form with >= 16 KB ring slots");
   HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, maps.a, maps.b, maps.a2, maps.b2, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
@@ -860,6 +1045,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
   HDRVAE_REQUIRE(!(p.bias_per_row || p.row_scale) || p.tw_log2 >= 5, "gemm_tc: per-row bias/scale needs row-major tiles");
   HDRVAE_REQUIRE(p.stats == nullptr || (p.n_cols % 128 == 0 && p.n_cols <= 512),
                  "gemm_tc: GroupNorm statistics need 128/256/512 output channels");
+  HDRVAE_REQUIRE(p.stats == nullptr || (p.n_cols & (p.n_cols - 1)) == 0, "gemm_tc: GroupNorm statistics need 128/256/512 output channels");
   const bool tf32 = p.ab_dtype == DT_F32;
   HDRVAE_REQUIRE(p.row_mode == 0 || (!tf32 && p.cta_group != 1), "gemm_tc: the soft-max passes exist for 16-bit CTA-pair builds");
   static int cg = -1;                                       // CTA pairs by default; HDRVAE_CTA_GROUP=1 selects single CTAs
@@ -940,14 +1126,23 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (epi == EPI_STATS) return launch_tc<128, false, 2, EPI_STATS, 3>(p, num_sms, stream);
       if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<128, false, 2, EPI_OUT16 | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_STATS)) return launch_tc<128, false, 2, EPI_RES | EPI_STATS, 3>(p, num_sms, stream);
+      if (epi == (EPI_RES | EPI_OUT2 | EPI_STATS)) return launch_tc<128, false, 2, EPI_RES | EPI_OUT2 | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == 0) return launch_tc<128, false, 2, 0, 3>(p, num_sms, stream);
       if (epi == EPI_RES) return launch_tc<128, false, 2, EPI_RES, 3>(p, num_sms, stream);
+    }
+    if (p.slab && !n128 && p.ntaps == 4 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
+      // one output phase of an upsample conv: 4 taps of the same halo slab (tap-reload form: L2 -> SM bound, the issuer
+      // waited for operands 60 % of the time)
+      if (epi == (EPI_OUT2 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT2 | EPI_STATS, 1>(p, num_sms, stream);
+      if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1>(p, num_sms, stream);
+      HDRVAE_REQUIRE(false, "gemm_tc: no slab build for this upsample epilogue (%d)", epi);
     }
     if (p.slab && !n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
       // 256-column tiles: slab variant with one tap of weights per stage (experiment switch HDRVAE_SLAB_MAXN)
       if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1>(p, num_sms, stream);
       if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_STATS, 1>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_STATS, 1>(p, num_sms, stream);
+      if (epi == (EPI_RES | EPI_OUT2 | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_OUT2 | EPI_STATS, 1>(p, num_sms, stream);
     }
 #define HDRVAE_EPI_CASE(E)                                                                       \
     case E:                                                                                      \

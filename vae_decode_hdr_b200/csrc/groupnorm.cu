@@ -129,38 +129,78 @@ gn_stats_kernel(const TIn* __restrict__ x, float* __restrict__ partial, int HW, 
   }
 }
 
-// one block per (group, image): fixed-order double reduction over the chunks, then the group's channels get
-// their scale / shift.  (One block per image was 47 us per layer at 8192 chunks: B x 32 blocks are ~10x faster.)
+// Partial records are reduced by up to kGnSlices blocks per image; the last block to finish (a ticket per image)
+// folds the slices in slice order, so the result does not depend on which block that is.
+constexpr int kGnSlices = 128;
+// Reduction of the partial records [B][n_chunks][32 groups][2] (conv epilogue: one record per 32 pixels; standalone
+// statistics pass: one per block).  Grid (slices, B): every warp reads whole 256-byte records (coalesced), the block
+// folds its 8 warps in warp order into slice sums (double), and the last block of an image folds the slices in slice
+// order -> sums[B][32][2] (row tiling: all-reduced by the caller) and / or the per-(image, channel) scale / shift.
+// (Round 2: the conv epilogue stopped combining its four TMEM lane quarters through shared memory, so there are 4x
+// more records; one block per (group, image) reading 8 bytes at a 256-byte stride no longer hides that.)
 __global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float* __restrict__ partial, int n_chunks, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int C,
-                   double count, float eps) {
-  const int g = blockIdx.x, img = blockIdx.y;
-  __shared__ double rs[256], rq[256];
+gn_reduce_kernel(const float* __restrict__ partial, int n_chunks, double* __restrict__ slice_sums,
+                 unsigned int* __restrict__ tickets, double* __restrict__ sums, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int C,
+                 double count, float eps) {
+  const int img = blockIdx.y, S = gridDim.x, sl = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int per = (n_chunks + S - 1) / S;
+  const int c0 = sl * per, c1 = min(n_chunks, c0 + per);
+  __shared__ double rs[8][kGroups], rq[8][kGroups];
+  __shared__ int s_last;
   double s = 0.0, q = 0.0;
-  for (int c = threadIdx.x; c < n_chunks; c += 256) {
-    const float2 pp = *reinterpret_cast<const float2*>(partial + ((long long)img * n_chunks + c) * (kGroups * 2) + g * 2);
+  const float2* rec = reinterpret_cast<const float2*>(partial) + (long long)img * n_chunks * kGroups + lane;
+#pragma unroll 4
+  for (int c = c0 + w; c < c1; c += 8) {
+    const float2 pp = rec[(long long)c * kGroups];
     s += (double)pp.x;
     q += (double)pp.y;
   }
-  rs[threadIdx.x] = s;
-  rq[threadIdx.x] = q;
+  rs[w][lane] = s;
+  rq[w][lane] = q;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
-    __syncthreads();
+  if (w == 0) {
+    for (int k = 1; k < 8; ++k) { s += rs[k][lane]; q += rq[k][lane]; }
+    double* o = slice_sums + (((long long)img * S + sl) * kGroups + lane) * 2;
+    o[0] = s; o[1] = q;
+    __threadfence();
   }
-  const double mean = rs[0] / count;
-  double var = rq[0] / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[img], 1u);
+    s_last = (t == (unsigned int)S - 1u) ? 1 : 0;
+    if (s_last) tickets[img] = 0;                       // ready for the next layer
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (w == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int k = 0; k < S; ++k) {
+      const double* o = slice_sums + (((long long)img * S + k) * kGroups + lane) * 2;
+      ts += __ldcg(o); tq += __ldcg(o + 1);
+    }
+    if (sums != nullptr) { sums[((long long)img * kGroups + lane) * 2] = ts; sums[((long long)img * kGroups + lane) * 2 + 1] = tq; }
+    rs[0][lane] = ts; rq[0][lane] = tq;
+  }
+  __syncthreads();
+  if (scale == nullptr) return;
   const int cpg = C / kGroups;
-  if (threadIdx.x < cpg) {
-    const int c = g * cpg + threadIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const double mean = rs[0][g] / count;
+    double var = rq[0][g] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float a = gamma[c] * rstd;
     scale[(long long)img * C + c] = a;
     shift[(long long)img * C + c] = beta[c] - (float)mean * a;
   }
+}
+static int gn_slices(int n_chunks) {
+  int sl = n_chunks / 32;
+  return sl < 1 ? 1 : (sl > kGnSlices ? kGnSlices : sl);
 }
 
 
@@ -225,7 +265,8 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
 }
 
 size_t gn_scratch_bytes(int B, int C, int max_chunks) {
-  return ((size_t)B * max_chunks * kGroups * 2 + (size_t)2 * B * C + 2) * sizeof(float) + (size_t)B * kGroups * 2 * sizeof(double);
+  return ((size_t)B * max_chunks * kGroups * 2 + (size_t)2 * B * C + 2) * sizeof(float) + (size_t)B * kGroups * 2 * sizeof(double) +
+         (size_t)B * kGnSlices * kGroups * 2 * sizeof(double) + ((size_t)B + 1) * sizeof(unsigned int);
 }
 
 static void gn_chunking(int B, int HW, int C, int max_chunks, int* chunks, int* px_per_block) {
@@ -301,24 +342,6 @@ static void launch_apply(const void* x, void* y, const float* scale, const float
 // Row tiling: the statistics of a (image, group) are sums over ALL ranks' rows.  gn_reduce_partials folds this
 // rank's conv-emitted partials into sums[B][32][2] (double, fixed order); the host all-reduces that block (SUM);
 // gn_finalize_sums turns the global sums into per-(image, channel) scale / shift.
-__global__ void __launch_bounds__(256)
-gn_reduce_partials_kernel(const float* __restrict__ partial, int n_chunks, double* __restrict__ sums) {
-  const int g = blockIdx.x, img = blockIdx.y;
-  __shared__ double rs[256], rq[256];
-  double s = 0.0, q = 0.0;
-  for (int c = threadIdx.x; c < n_chunks; c += 256) {
-    const float2 pp = *reinterpret_cast<const float2*>(partial + ((long long)img * n_chunks + c) * (kGroups * 2) + g * 2);
-    s += (double)pp.x;
-    q += (double)pp.y;
-  }
-  rs[threadIdx.x] = s; rq[threadIdx.x] = q;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { sums[((long long)img * kGroups + g) * 2] = rs[0]; sums[((long long)img * kGroups + g) * 2 + 1] = rq[0]; }
-}
 __global__ void gn_finalize_sums_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
                                         int C, double count, float eps) {
@@ -339,12 +362,26 @@ double* gn_sums_ptr(void* scratch, int B, int C, int max_chunks) {
   (void)C;
   return reinterpret_cast<double*>(reinterpret_cast<float*>(scratch) + (size_t)B * max_chunks * kGroups * 2);
 }
+// [partials][sums][slice sums: B*kGnSlices*64 doubles][tickets: B (+1)][scale: B*C][shift: B*C] — nothing in front of
+// the tickets depends on C (a scratch buffer sized for 512 channels serves every layer)
+static double* gn_slice_ptr(void* scratch, int B, int max_chunks) {
+  return gn_sums_ptr(scratch, B, 0, max_chunks) + (size_t)B * kGroups * 2;
+}
+static unsigned int* gn_ticket_ptr(void* scratch, int B, int max_chunks) {
+  return reinterpret_cast<unsigned int*>(gn_slice_ptr(scratch, B, max_chunks) + (size_t)B * kGnSlices * kGroups * 2);
+}
 static float* gn_scale_ptr(void* scratch, int B, int max_chunks) {
-  return reinterpret_cast<float*>(gn_sums_ptr(scratch, B, 0, max_chunks) + (size_t)B * kGroups * 2);
+  return reinterpret_cast<float*>(gn_ticket_ptr(scratch, B, max_chunks) + B + 1);
+}
+// The tickets must be zero before the first GroupNorm that uses a scratch buffer (they reset themselves afterwards).
+int gn_scratch_reset(void* scratch, int B, int max_chunks, cudaStream_t s) {
+  HDRVAE_CUDA_OK(cudaMemsetAsync(gn_ticket_ptr(scratch, B, max_chunks), 0, (size_t)B * sizeof(unsigned int), s));
+  return 0;
 }
 int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n_partials, cudaStream_t s) {
-  gn_reduce_partials_kernel<<<dim3(kGroups, B), 256, 0, s>>>(reinterpret_cast<const float*>(scratch), n_partials,
-                                                             gn_sums_ptr(scratch, B, C, max_chunks));
+  gn_reduce_kernel<<<dim3(gn_slices(n_partials), B), 256, 0, s>>>(reinterpret_cast<const float*>(scratch), n_partials,
+                                                                    gn_slice_ptr(scratch, B, max_chunks), gn_ticket_ptr(scratch, B, max_chunks),
+                                                                    gn_sums_ptr(scratch, B, C, max_chunks), nullptr, nullptr, nullptr, nullptr, C, 1.0, 0.f);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -401,8 +438,9 @@ int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, in
     HDRVAE_CUDA_OK(cudaGetLastError());
     n_partials = chunks;
   }
-  gn_finalize_kernel<<<dim3(kGroups, B), 256, 0, s>>>(partial, n_partials, gamma, beta, scale, shift, C,
-                                       (double)HW * (double)(C / kGroups), 1e-6f);
+  gn_reduce_kernel<<<dim3(gn_slices(n_partials), B), 256, 0, s>>>(partial, n_partials, gn_slice_ptr(scratch, B, max_chunks),
+                                                                    gn_ticket_ptr(scratch, B, max_chunks), nullptr, gamma, beta, scale, shift, C,
+                                                                    (double)HW * (double)(C / kGroups), 1e-6f);
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   if (y_dtype == DT_F32) {
