@@ -20,6 +20,10 @@
 #pragma nv_diag_suppress 128   // "loop is not reachable": the tap-reload loops after the slab branch of an if-constexpr
 #include "ptx.cuh"
 
+#ifndef HDRVAE_SLAB_PITCH
+#define HDRVAE_SLAB_PITCH 10
+#endif
+
 namespace hdrvae {
 
 constexpr int kBlockM = 128;
@@ -28,9 +32,9 @@ constexpr int kABytes = kBlockM * kRowBytes;      // 16 KB
 constexpr int kEpilogueThreads = 256;             // 8 warps: 2 per TMEM lane quarter, each taking half of the columns
 // Warpgroup 0 = warps 0..3: TMA producer, MMA issuer, two idle warps; warpgroups 1 and 2 = the epilogue.  The register
 // file is allotted per 4 warps anyway (a 320-thread CTA got the 168 registers per thread of a 384-thread one), and whole
-// warpgroups let setmaxnreg move registers from the two single-thread roles to the epilogue: 56 + 2 x 224 per thread.
+// warpgroups let setmaxnreg move registers from the two single-thread roles to the epilogue: 64 + 2 x 216 per thread.
 constexpr int kNumThreads = 128 + kEpilogueThreads;
-constexpr int kRegsControl = 56, kRegsEpilogue = 224;   // 128 * 56 + 256 * 224 = 384 * 168
+constexpr int kRegsControl = 64, kRegsEpilogue = 216;   // 128 * 64 + 256 * 216 <= 384 * 168
 
 constexpr int kSmemLimit = 232448;                // 227 KB opt-in shared memory per CTA on sm_100
 constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 256 /*barriers*/ +
@@ -44,17 +48,20 @@ constexpr int kSmemFixed = 8 * 4096 /*epilogue transpose patches*/ + 256 /*barri
 // kSlabStages buffers, the weights go into their own ring in groups of SLAB taps (9, 3 or 1: one 3-D TMA box each),
 // and the 9 taps are shifted UMMA descriptors into the slab.  L2 -> SM operand traffic drops 4x and the MMA time a
 // byte of shared memory keeps in flight doubles, which is what bounds the layers with <= 128 output columns.
-constexpr int kSlabRows = 18, kSlabPitch = 16;
-constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 36 KB
+// Pitch: the 10 pixels a tile row needs (8 + halo), not a power of two: the 128-byte swizzle is a function of the shared
+// memory address bits, which TMA (writing) and the UMMA descriptors (reading, 8-row groups 10 lines apart) both honour,
+// so row groups need not start on 1024-byte boundaries — only the buffers do.
+constexpr int kSlabRows = 18, kSlabPitch = HDRVAE_SLAB_PITCH;
+constexpr int kSlabBytes = kSlabRows * kSlabPitch * kRowBytes;   // 22.5 KB of TMA traffic per slab
+constexpr int kSlabBufBytes = (kSlabBytes + 1023) / 1024 * 1024;
 template <int BLOCK_N, int CG, int KSUB, int SLAB = 0>
 struct TcConfig {
   static constexpr int kATile = kABytes;
   static constexpr int kBBytes = (SLAB ? SLAB : 1) * (BLOCK_N / CG) * kRowBytes;   // one B stage staged by this CTA
   static constexpr int kSubBytes = kATile + kBBytes;               // bytes one CTA loads per k-sub-block (tap-reload form)
   static constexpr int kStageBytes = SLAB ? kBBytes : KSUB * kSubBytes;
-  // narrow tiles have short MMAs (a slab feeds 36 MMAs of 32 cycles): three slabs in flight cover the TMA latency
-  static constexpr int kSlabStages = SLAB ? (BLOCK_N <= 64 ? 3 : 2) : 0;
-  static constexpr int kSlabBuf = kSlabBytes;                        // bytes of one fp16 slab buffer
+  static constexpr int kSlabStages = SLAB ? 3 : 0;                   // three slabs in flight cover the TMA latency
+  static constexpr int kSlabBuf = kSlabBufBytes;                     // bytes of one fp16 slab buffer
   static constexpr int kPitch = kSlabPitch;                          // 128-byte lines per slab row
   static constexpr int kStagesFit = (kSmemLimit - kSmemFixed - kSlabStages * kSlabBuf) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
@@ -233,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
           if (ptx::elect_one()) {
             if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
-            uint8_t* sa = smem_slab + ss * kSlabBytes;
+            uint8_t* sa = smem_slab + ss * Cfg::kSlabBuf;
             // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
             if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
             else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
@@ -257,25 +264,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // blocks (4 MMAs each) stream; through the two-slot slab ring (round-2 first version: a whole 36 KB halo slab per
         // block) the issuer waited for them longer than it computed (nin-fused 128-column conv: 2.32 M cycles against
         // 1.25 M of MMA work).
+        // (128-column tiles: centre tile + weights = 16 + 8 KB share ONE slot, so a tile's 2 to 4 fused blocks are all in
+        // flight while the 3x3 part still computes; 256-column tiles: two consecutive slots)
+        constexpr int kB2Bytes = (BLOCK_N / CG) * kRowBytes;
+        constexpr bool kOneSlot = Cfg::kBBytes >= kABytes + kB2Bytes;
         for (int kb = 0; kb < kb2_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (ptx::elect_one()) {
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * kABytes));
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * (kABytes + (kOneSlot ? kB2Bytes : 0))));
             uint8_t* sa = smem_b + stage * Cfg::kBBytes;
             if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA2, &full_bar[stage], kb * kElemsPerRow, x0, y0 + p.y_pad, img);
             else ptx::tma_load_4d(sa, &tmA2, &full_bar[stage], kb * kElemsPerRow, x0, y0 + p.y_pad, img);
+            if (kOneSlot) {
+              if (CG == 2) ptx::tma_load_2d_pair(sa + kABytes, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+              else ptx::tma_load_2d(sa + kABytes, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (ptx::elect_one()) {
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * (BLOCK_N / CG) * kRowBytes));
-            uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-            if (CG == 2) ptx::tma_load_2d_pair(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
-            else ptx::tma_load_2d(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+          if (!kOneSlot) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (ptx::elect_one()) {
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * kB2Bytes));
+              uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+              if (CG == 2) ptx::tma_load_2d_pair(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+              else ptx::tma_load_2d(sb, &tmB2, &full_bar[stage], kb * kElemsPerRow, n0);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         continue;
       }
@@ -346,7 +363,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
                 // (9 taps of a 3x3 conv, or the 4 taps of one output phase of an upsample conv)
                 const int t = tg * SLAB + tt;
-                const uint32_t a_off = (uint32_t)(((p.tap_dy[t] + 1) * Cfg::kPitch + (p.tap_dx[t] + 1)) * kRowBytes);
+                // (tap table only in the one-tap-per-stage build, whose 128-cycle MMAs hide the lookup; the 3- and 9-tap
+                // groups are 3x3 convs by construction and keep compile-time offsets: the 32-column build is issue-bound)
+                const uint32_t a_off = SLAB == 1 ? (uint32_t)(((p.tap_dy[t] + 1) * Cfg::kPitch + (p.tap_dx[t] + 1)) * kRowBytes)
+                                                 : (uint32_t)(((t / 3) * Cfg::kPitch + (t % 3)) * kRowBytes);
                 const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, Cfg::kPitch * kRowBytes);
                 const uint64_t db = ptx::make_sw128_kmajor_desc(sb + tt * (BLOCK_N / CG) * kRowBytes);
 #pragma unroll
@@ -371,23 +391,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < kb2_blocks; ++kb) {
           // fused 1x1 conv: the second tensor's centre tile (ring slot `sa_stage`) against one tap of its weights (next slot)
+          constexpr bool kOneSlot = Cfg::kBBytes >= kABytes + (BLOCK_N / CG) * kRowBytes;
           if (tim) tq = clock64();
           ptx::mbar_wait(&full_bar[stage], phase);
           const int sa_stage = stage;
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-          ptx::mbar_wait(&full_bar[stage], phase);
+          if (!kOneSlot) {
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            ptx::mbar_wait(&full_bar[stage], phase);
+          }
           if (tim) w_b += clock64() - tq;
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
             const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + sa_stage * Cfg::kBBytes));
-            const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
+            const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * Cfg::kBBytes + (kOneSlot ? kABytes : 0)));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (CG == 2) ptx::umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
               else ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
             }
-            if (CG == 2) { ptx::umma_commit_pair(&empty_bar[sa_stage]); ptx::umma_commit_pair(&empty_bar[stage]); }
-            else { ptx::umma_commit(&empty_bar[sa_stage]); ptx::umma_commit(&empty_bar[stage]); }
+            if (CG == 2) { ptx::umma_commit_pair(&empty_bar[sa_stage]); if (!kOneSlot) ptx::umma_commit_pair(&empty_bar[stage]); }
+            else { ptx::umma_commit(&empty_bar[sa_stage]); if (!kOneSlot) ptx::umma_commit(&empty_bar[stage]); }
             if (kb == kb2_blocks - 1) {
               if (CG == 2) ptx::umma_commit_pair(&tmem_full_bar[acc]); else ptx::umma_commit(&tmem_full_bar[acc]);
             }
@@ -498,6 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       lo[it] = (uint32_t)((long long)yy * p.out_row_stride + (long long)xx * p.out_px_stride) + half * (BLOCK_N / 2) + slot * 4;
       lo2[it] = (uint32_t)((long long)yy * o2_row + (long long)xx * o2_px) + half * (BLOCK_N / 2) + slot * 4;
     }
+    float4 rres_a[8];                       // residual of the chunk in hand
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool tim = (p.dbg & 32) != 0;     // CTA 0, first epilogue warp: cycles waiting for accumulators / draining them
@@ -522,20 +546,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const long long ty_off = (long long)(ty * p.TH * p.sy + p.py), tx_off = (long long)(tx * p.TW * p.sx + p.px);
           const long long org = img_off + ty_off * p.out_row_stride + tx_off * p.out_px_stride;
           const long long org2 = (long long)img * o2_img + n0 + ty_off * o2_row + tx_off * o2_px;
-          float4 rres[8], rres2[8];
-          auto fetch_res = [&](int ci) {
+          float4 rres2[8];
+          auto fetch_res = [&](long long origin, int ci, float4 (&dst)[8]) {
             if constexpr ((EPI & EPI_RES) != 0) {
-              const float* r = resf + org + ci * 32;      // plain loads: the residual may alias the output
+              const float* r = resf + origin + ci * 32;   // plain loads: the residual may alias the output
 #pragma unroll
-              for (int it = 0; it < 8; ++it) rres[it] = *reinterpret_cast<const float4*>(r + lo[it]);
-            }
-            if constexpr ((EPI & EPI_RES2) != 0) {
-              const float* r = p.residual2 + org + ci * 32;
-#pragma unroll
-              for (int it = 0; it < 8; ++it) rres2[it] = *reinterpret_cast<const float4*>(r + lo[it]);
+              for (int it = 0; it < 8; ++it) dst[it] = *reinterpret_cast<const float4*>(r + lo[it]);
             }
           };
-          fetch_res(0);
+          fetch_res(org, 0, rres_a);
           if (tim) tq = clock64();
           ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
           if (tim) { const long long now = clock64(); w_full += now - tq; tq = now; }
@@ -544,9 +563,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tmem_ld_32x32(t_acc, v);
           const float2 alpha2 = make_float2(alpha, alpha), rs2 = make_float2(res_scale, res_scale);
           const float2 s16_2 = make_float2(s16, s16), s2_2 = make_float2(s2, s2);
-#pragma unroll 1
-          for (int ci = 0; ci < kChunksPerWarp; ++ci) {
-            if (ci > 0) fetch_res(ci);                    // issued first: overlaps the TMEM wait and the transpose
+          // one 32 x 32 chunk: accumulator -> transpose patch -> (+ residual rr) -> global, + GroupNorm partials
+          auto do_chunk = [&](const int ci, const float4 (&rr)[8]) {
+            if constexpr ((EPI & EPI_RES2) != 0) {
+              const float* r = p.residual2 + org + ci * 32;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) rres2[it] = *reinterpret_cast<const float4*>(r + lo[it]);
+            }
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cbase + ci * 32 + slot * 4));
             const float2 b01 = make_float2(bias4.x, bias4.y), b23 = make_float2(bias4.z, bias4.w);
@@ -569,8 +592,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float4 a[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + sr;
-              a[it] = patch[rr * 8 + (slot ^ (rr & 7))];
+              const int rw = it * 4 + sr;
+              a[it] = patch[rw * 8 + (slot ^ (rw & 7))];
             }
             float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
             const long long ob = org + ci * 32, ob2 = org2 + ci * 32;
@@ -579,8 +602,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float2 t01 = f2_fma(make_float2(a[it].x, a[it].y), alpha2, b01);
               float2 t23 = f2_fma(make_float2(a[it].z, a[it].w), alpha2, b23);
               if constexpr ((EPI & EPI_RES) != 0) {
-                t01 = f2_fma(make_float2(rres[it].x, rres[it].y), rs2, t01);
-                t23 = f2_fma(make_float2(rres[it].z, rres[it].w), rs2, t23);
+                t01 = f2_fma(make_float2(rr[it].x, rr[it].y), rs2, t01);
+                t23 = f2_fma(make_float2(rr[it].z, rr[it].w), rs2, t23);
               }
               if constexpr ((EPI & EPI_RES2) != 0) {
                 t01 = f2_add(t01, make_float2(rres2[it].x, rres2[it].y));
@@ -624,6 +647,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (gg < 32) *reinterpret_cast<float2*>(stat_rec + gg * 2) = make_float2(s_acc, q_acc);
               }
             }
+          };
+          // (Round 2 also tried requesting the residual a whole chunk — and, across tiles, a whole tile — ahead: double
+          // buffers, 64 more registers.  No change: 1.449 M against 1.432 M cycles for the 128-channel in-place conv, whose
+          // issuer waits for accumulators 28 % of the time.  The fp32 stream's read + write bytes pace that epilogue (4.9 of
+          // the 6.55 TB/s a plain copy reaches), not its latency.)
+#pragma unroll 1
+          for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+            if (ci > 0) fetch_res(org, ci, rres_a);       // issued first: overlaps the TMEM wait and the transpose
+            do_chunk(ci, rres_a);
           }
           if (tim) w_drain += clock64() - tq;
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
