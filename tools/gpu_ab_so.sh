@@ -25,3 +25,6 @@ cp /tmp/libhdrvae_new.so $L; python tools/profile_decode.py 4 128 gpurun_out/ab_
 paste gpurun_out/ab_per_op_base.tsv gpurun_out/ab_per_op_new.tsv | awk -F'\t' '{printf "%-50s %s -> %s\n", $1, $2, $6}' | grep -v groupnorm
 HDRVAE_NO_GRAPH=1 HDRVAE_GEMM_DBG=32 timeout 300 python tools/profile_decode.py 4 128 > gpurun_out/dbg32.log 2>&1
 grep "gemm_tc<" gpurun_out/dbg32.log | tail -150 > gpurun_out/dbg32_last.log
+# the 4x HDR upscaler (narrow 32- / 64-column convs), previous build then new build
+cp tools/ab/libhdrvae_base.so $L; timeout 600 python tools/up_bench.py 1024 1024 23 > gpurun_out/ab_up_base.log 2>&1; tail -1 gpurun_out/ab_up_base.log
+cp /tmp/libhdrvae_new.so $L; timeout 600 python tools/up_bench.py 1024 1024 23 > gpurun_out/ab_up_new.log 2>&1; tail -1 gpurun_out/ab_up_new.log

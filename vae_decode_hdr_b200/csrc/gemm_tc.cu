@@ -350,14 +350,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (tim) tq = clock64();
           ptx::mbar_wait(&slab_full_bar[ss], sphase);
           if (tim) w_slab += clock64() - tq;
-          const uint32_t sa = ptx::smem_u32(smem_slab + ss * Cfg::kSlabBuf);
+          // descriptors are built once per slab / stage; a tap only ADDS its line offset (>> 4) to the 14-bit address field
+          // (all of shared memory fits in it, so no carry leaves the field): two 64-bit uniform adds per MMA instead of a
+          // shift-mask-or chain — the 32- and 64-column builds (16- and 32-cycle MMAs) are issue-bound
+          const uint64_t da_slab = ptx::make_sw128_kmajor_desc_sbo(ptx::smem_u32(smem_slab + ss * Cfg::kSlabBuf), Cfg::kPitch * kRowBytes);
           for (int tg = 0; tg < ntg; ++tg) {
             if (tim) tq = clock64();
             ptx::mbar_wait(&full_bar[stage], phase);
             if (tim) w_b += clock64() - tq;
             ptx::tc_fence_after_sync();
             if (ptx::elect_one()) {
-              const uint32_t sb = ptx::smem_u32(smem_b + stage * Cfg::kBBytes);
+              const uint64_t db_stage = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
               for (int tt = 0; tt < SLAB; ++tt) {
                 // tap (dy,dx): MMA row m = pixel (m>>3, m&7) of the tile reads slab line (m>>3 + 1+dy)*16 + (m&7) + 1+dx
@@ -367,8 +370,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // groups are 3x3 convs by construction and keep compile-time offsets: the 32-column build is issue-bound)
                 const uint32_t a_off = SLAB == 1 ? (uint32_t)(((p.tap_dy[t] + 1) * Cfg::kPitch + (p.tap_dx[t] + 1)) * kRowBytes)
                                                  : (uint32_t)(((t / 3) * Cfg::kPitch + (t % 3)) * kRowBytes);
-                const uint64_t da = ptx::make_sw128_kmajor_desc_sbo(sa + a_off, Cfg::kPitch * kRowBytes);
-                const uint64_t db = ptx::make_sw128_kmajor_desc(sb + tt * (BLOCK_N / CG) * kRowBytes);
+                const uint64_t da = da_slab + (a_off >> 4);
+                const uint64_t db = db_stage + (uint32_t)((tt * (BLOCK_N / CG) * kRowBytes) >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t accum = (kb | t | k) != 0 ? 1u : 0u;
