@@ -399,10 +399,10 @@ def main():
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained",
                 # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 51 gemm_tc launches of one C2 step
-                # (profiles/r02_ncu_dram_traffic_c2_summary.json, captured on this workload with the round-2 build: 31.7 GB
-                # read + 27.4 GB written; round 1: 79.3 GB over 61 launches).  The kernel is tensor bound; the figure shows
-                # there is no re-read waste (GroupNorm: 36.9 GB measured vs 38.1 GB by the kernels' own byte count)
-                "traffic": (59.13e9 if (B, L) == (4, 128) else None), "traffic_unit": "bytes per step, all conv launches (ncu)",
+                # (profiles/r02_step6_ncu_dram_traffic_c2_summary.json, captured on this workload with the final round-2
+                # build: 30.7 GB read + 27.6 GB written; round 1: 79.3 GB over 61 launches).  The kernel is tensor bound; the
+                # figure shows there is no re-read waste (GroupNorm: 36.9 GB measured vs 38.1 GB by the kernels' own byte count)
+                "traffic": (58.25e9 if (B, L) == (4, 128) else None), "traffic_unit": "bytes per step, all conv launches (ncu)",
                 "achieved_executed": executed_tf, "frac_executed": executed_tf / peak_tf,
                 "note": "achieved = algorithmic conv FLOPs (SURVEY 8d) / summed conv launch time of one step; "
                         "achieved_executed discounts the 5/9 of the upsample convs' FLOPs that phase decomposition removes",
