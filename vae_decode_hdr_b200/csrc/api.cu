@@ -229,8 +229,8 @@ bool conv_takes_slab(const PackedConv& pc, const ConvIO& io, int H, int W, int i
   const bool res_ok = io.residual == nullptr || pc.cout_pad > 128 || slab_res != 0;
   if (pc.upsample)    // the decoder's upsample convs (256-column tiles, statistics [+ scaled operand copy] epilogues)
     return slab_on && slab_up && pc.ks == 3 && pc.w_dtype != DT_F32 && pc.kmul == 1 && impl == HDRVAE_CONV_TCGEN05 && H * W >= 128 &&
-           pc.cout_pad >= 256 && pc.cout_pad <= slab_maxn && io.residual == nullptr && io.stats != nullptr && io.y_dtype == DT_F32 &&
-           io.lrelu == 0.f && io.residual2 == nullptr;
+           pc.cout_pad >= 256 && pc.cout_pad <= slab_maxn && io.residual == nullptr && io.stats != nullptr &&
+           (io.y_dtype == DT_F32 || io.y2 == nullptr) && io.lrelu == 0.f && io.residual2 == nullptr;
   return slab_on && pc.ks == 3 && pc.w_dtype != DT_F32 && impl != HDRVAE_CONV_DIRECT && H * W >= 128 &&
          (pc.cout_pad <= 64 || (pc.cout_pad <= slab_maxn && res_ok));
 }
@@ -326,6 +326,8 @@ struct DecState {
   void* gn;        // GroupNorm scratch (partials | scale | shift)
   int gn_chunks;   // capacity of the partial area (chunks per image)
   int pending;     // partial chunks per image currently valid for the tensor about to be normalised
+  int x_dt = DT_F32;      // element type of the residual stream: fp32, or the operand type scaled by x_scale (x_is_16bit)
+  float x_scale = 1.f;
 };
 
 static int run_gn(hdrvae_ctx* ctx, const void* x, int x_dtype, void* y, int B, int HW, const NormW& nw, bool silu,
@@ -357,6 +359,20 @@ static bool nin_is_fused(hdrvae_ctx* ctx, const ResW& rw, int H, int W) {
   return on && rw.has_nin && !ctx->high && rw.nin_x16.w[0] != nullptr && conv_takes_slab(rw.c2, probe, H, W, ctx->conv_impl);
 }
 
+// The residual stream x itself is stored as fp16 scaled by 2^-4 (what the raw-stream convs read anyway): conv2 / proj_out
+// read and write 2 + 2 bytes per element instead of 4 + 4 (+ 2 for the operand copy), norm1 reads 2 instead of 4, the
+// upsample convs and shortcuts read x directly.  The step runs at its power cap, where bytes are what counts: same-box A/B
+// 39.7 -> 36.8 ms.  Cost: one more fp16 rounding per block on the residual path (features 1.9e-3 -> 2.4e-3 rel-L2 against
+// the fp32 oracle; every parity test keeps its 1e-2 bound).  HDRVAE_X16=0 keeps the fp32 stream.  Needs the fused
+// shortcut and fp16 operands; not used by the bf16 and high-precision modes or the validation kernels.
+static bool x_is_16bit(hdrvae_ctx* ctx) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HDRVAE_X16"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  static int nin_on = -1;
+  if (nin_on < 0) { const char* e = getenv("HDRVAE_FUSE_NIN"); nin_on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on && nin_on && !ctx->high && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && h_is_16bit(ctx);
+}
+
 static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
   return ctx->conv_impl == HDRVAE_CONV_TCGEN05 ? reinterpret_cast<float*>(st->gn) : nullptr;
 }
@@ -380,11 +396,13 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
   {
     ConvIO io; io.y = st->hbuf; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
     io.y_dtype = h_dt; io.y_scale = h_scale;
-    HDRVAE_TRY(gn_before_conv(ctx, st->x, rw.n1, rw.c1, &io, st, B, H, W, s));
+    HDRVAE_TRY(gn_before_conv(ctx, st->x, rw.n1, rw.c1, &io, st, B, H, W, s, st->x_dt, 1.f / st->x_scale));
     HDRVAE_TRY(run_conv(ctx, rw.c1, io, B, H, W, impl, s));
   }
+  const bool x16 = st->x_dt != DT_F32;
   ConvIO io; io.stats = stats_ptr(ctx, st); io.stats_chunks = &st->pending;
-  if (rw.dual_out) { io.y2 = st->xa16; io.y2_dtype = ctx->op_dtype; io.y2_scale = kRawOperandScale; }
+  if (x16) { io.y_dtype = st->x_dt; io.y_scale = st->x_scale; }
+  else if (rw.dual_out) { io.y2 = st->xa16; io.y2_dtype = ctx->op_dtype; io.y2_scale = kRawOperandScale; }
   if (rw.has_nin) {
     // norm2 as a separate pass (conv1's output lives in hbuf, which the shortcut is about to overwrite); then the
     // shortcut on the scaled 16-bit copy of x into hbuf, and conv2 accumulates onto it in place
@@ -393,8 +411,16 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
     if (nin_is_fused(ctx, rw, H, W)) {
       // x_new = conv2(t) + nin(x): ONE launch, written over the old x (whose scaled 16-bit copy is what the shortcut reads)
       io.x2 = st->xb16; io.pc2 = &rw.nin_x16; io.bias = rw.bias_c2_nin; io.y = st->x;
+      if (x16) {
+        // the shortcut reads the 16-bit stream itself; Cin != Cout, so the new stream goes to the other buffer
+        io.x2 = st->x; io.y = st->hbuf;
+        HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
+        std::swap(st->x, st->hbuf);
+        return 0;
+      }
       return run_conv(ctx, rw.c2, io, B, H, W, impl, s);
     }
+    HDRVAE_REQUIRE(!x16, "the 16-bit residual stream needs the fused shortcut");
     ConvIO sc; sc.x = st->xb16; sc.y = st->hbuf; sc.alpha = 1.0f / kRawOperandScale;
     HDRVAE_TRY(run_conv(ctx, rw.nin, sc, B, H, W, impl, s));
     io.y = st->hbuf; io.residual = st->hbuf;
@@ -402,6 +428,7 @@ static int run_res(hdrvae_ctx* ctx, const ResW& rw, DecState* st, int B, int H, 
     std::swap(st->x, st->hbuf);
   } else {
     io.y = st->x; io.residual = st->x;                  // x += conv2(t), in place
+    if (x16) { io.res_dtype = st->x_dt; io.res_scale = 1.f / st->x_scale; }
     HDRVAE_TRY(gn_before_conv(ctx, st->hbuf, rw.n2, rw.c2, &io, st, B, H, W, s, h_dt, 1.f / h_scale));
     HDRVAE_TRY(run_conv(ctx, rw.c2, io, B, H, W, impl, s));
   }
@@ -606,6 +633,8 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
   st.gn = ws + pl.off_gn;
   st.gn_chunks = pl.gn_chunks;
   st.pending = 0;
+  const bool x16 = x_is_16bit(ctx);
+  if (x16) { st.x_dt = dt; st.x_scale = kRawOperandScale; }
   HDRVAE_TRY(gn_scratch_reset(st.gn, B, pl.gn_chunks, s));
 
   if (ctx->high) {
@@ -617,6 +646,7 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
   }
   {
     ConvIO io; io.x = lat; io.y = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
+    if (x16) { io.y_dtype = st.x_dt; io.y_scale = st.x_scale; }
     HDRVAE_TRY(run_conv(ctx, ctx->conv_in, io, B, H, W, impl, s));
   }
   HDRVAE_TRY(run_res(ctx, ctx->mid1, &st, B, H, W, s));
@@ -625,7 +655,7 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
     void* qk = ws + pl.off_qk;
     void* vt = ws + pl.off_vt;
     void* o = ws + pl.off_o;
-    HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->attn_norm, false, &st, s));
+    HDRVAE_TRY(run_gn(ctx, st.x, st.x_dt, st.t, B, H * W, ctx->attn_norm, false, &st, s, -1, 1.f / st.x_scale));
     if (ctx->high) {
       ProfScope prof("attention (high precision, GEMM form)", 4.0 * B * (double)pl.T * pl.T * 512 * 3, 0.0, s);
       for (int b = 0; b < B; ++b)
@@ -654,6 +684,7 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
     }
     }
     ConvIO io; io.x = o; io.y = st.x; io.residual = st.x; io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
+    if (x16) { io.y_dtype = st.x_dt; io.y_scale = st.x_scale; io.res_dtype = st.x_dt; io.res_scale = 1.f / st.x_scale; }
     HDRVAE_TRY(run_conv(ctx, ctx->proj_out, io, B, H, W, impl, s));
   }
   HDRVAE_TRY(run_res(ctx, ctx->mid2, &st, B, H, W, s));
@@ -663,7 +694,8 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
       // operand: the scaled 16-bit copy written by the level's last ResBlock; levels 2 and 1 feed a nin_shortcut
       // one block later, so their output gets a scaled copy too
       ConvIO io; io.x = st.xa16; io.y = st.hbuf; io.alpha = 1.0f / kRawOperandScale;
-      if (lvl <= 2) { io.y2 = st.xb16; io.y2_dtype = dt; io.y2_scale = kRawOperandScale; }
+      if (x16) { io.x = st.x; io.y_dtype = st.x_dt; io.y_scale = st.x_scale; }     // the stream is its own operand copy
+      else if (lvl <= 2) { io.y2 = st.xb16; io.y2_dtype = dt; io.y2_scale = kRawOperandScale; }
       io.stats = stats_ptr(ctx, &st); io.stats_chunks = &st.pending;
       HDRVAE_TRY(run_conv(ctx, ctx->upsample[lvl], io, B, H, W, impl, s));
       std::swap(st.x, st.hbuf);
@@ -671,7 +703,7 @@ static int run_decoder(hdrvae_ctx* ctx, const float* latent, const Plan& pl, uin
     }
   }
   // the tensor the reference's hook captures: 16-bit operand of conv_out, or fp32 in the high-precision mode
-  HDRVAE_TRY(run_gn(ctx, st.x, DT_F32, st.t, B, H * W, ctx->norm_out, true, &st, s, ctx->high ? DT_F32 : -1));
+  HDRVAE_TRY(run_gn(ctx, st.x, st.x_dt, st.t, B, H * W, ctx->norm_out, true, &st, s, ctx->high ? DT_F32 : -1, 1.f / st.x_scale));
   *features = st.t;
   return 0;
 }
@@ -834,10 +866,13 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
   int* pending = &st->pending;
   float* x = st->x; float* hb = st->hbuf;
   const ResW* r = &rw;
-  const bool h16 = h_is_16bit(ctx);                    // same storage rule as the single-GPU program (bit-identical results)
+  const bool h16 = h_is_16bit(ctx);                    // same storage rules as the single-GPU program (bit-identical results)
   const int h_dt = h16 ? ctx->op_dtype : DT_F32;
   const float h_scale = h16 ? kRawOperandScale : 1.f;
-  rows_gn(st, x, rw.n1, true, H, W);
+  const bool x16 = x_is_16bit(ctx);
+  const int x_dt = x16 ? ctx->op_dtype : DT_F32;
+  const float x_scale = x16 ? kRawOperandScale : 1.f;
+  rows_gn(st, x, rw.n1, true, H, W, x_dt, 1.f / x_scale);
   rows_compute(st, [=](cudaStream_t s) {
     ConvIO io; io.x = t; io.y = hb; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
     io.y_dtype = h_dt; io.y_scale = h_scale;
@@ -846,8 +881,18 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
   rows_stats_and_halo(st, hb, H, W, rw.c1.cout, nullptr, 0, h16 ? 2 : 4);
   rows_gn(st, hb, rw.n2, true, H, W, h_dt, 1.f / h_scale);
   const bool fused_nin = nin_is_fused(ctx, rw, H, W);
-  float* out = (rw.has_nin && !fused_nin) ? hb : x;
+  float* out = (rw.has_nin && (!fused_nin || x16)) ? hb : x;      // 16-bit stream: the shortcut reads x itself, so not in place
   rows_compute(st, [=](cudaStream_t s) {
+    if (x16) {
+      // the residual stream is the scaled 16-bit tensor (see x_is_16bit): in place with a 16-bit residual, or — with a
+      // shortcut — from x into the other buffer; its border halo rows are conv padding for the raw-stream convs
+      ConvIO io; io.x = t; io.y = out; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
+      io.y_dtype = x_dt; io.y_scale = x_scale;
+      if (fused_nin) { io.x2 = x; io.pc2 = &r->nin_x16; io.bias = r->bias_c2_nin; }
+      else { io.residual = out; io.res_dtype = x_dt; io.res_scale = 1.f / x_scale; }
+      HDRVAE_TRY(run_conv(ctx, r->c2, io, 1, H, W, HDRVAE_CONV_TCGEN05, s));
+      return zero_border_halos(st, out, H, W, r->c2.cout, 2, s);
+    }
     if (fused_nin) {
       ConvIO io; io.x = t; io.y = out; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
       io.x2 = xb; io.pc2 = &r->nin_x16; io.bias = r->bias_c2_nin;
@@ -863,8 +908,9 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
     if (r->dual_out) HDRVAE_TRY(zero_border_halos(st, xa, H, W, r->c2.cout, 2, s));
     return 0;
   });
-  rows_stats_and_halo(st, out, H, W, rw.c2.cout, rw.dual_out ? xa : nullptr, rw.c2.cout);
-  if (rw.has_nin && !fused_nin) std::swap(st->x, st->hbuf);
+  if (x16) rows_stats_and_halo(st, out, H, W, rw.c2.cout, nullptr, 0, 2);
+  else rows_stats_and_halo(st, out, H, W, rw.c2.cout, rw.dual_out ? xa : nullptr, rw.c2.cout);
+  if (rw.has_nin && (!fused_nin || x16)) std::swap(st->x, st->hbuf);
 }
 
 static int build_rows_program(hdrvae_rows* st) {
@@ -883,6 +929,10 @@ static int build_rows_program(hdrvae_rows* st) {
   int H = pl.hl, W = pl.w;
   const int rank = st->rank;
   const float* latent = st->latent;
+  const bool x16 = x_is_16bit(ctx);                    // residual stream stored like the single-GPU program stores it
+  const int x_dt = x16 ? dt : DT_F32;
+  const float x_scale = x16 ? kRawOperandScale : 1.f;
+  const int x_eb = x16 ? 2 : 4;
 
   {
     float* x = st->x;
@@ -891,9 +941,11 @@ static int build_rows_program(hdrvae_rows* st) {
       HDRVAE_TRY(launch_latent_rows_to_nhwc(latent, lat, dt, 16, pl.h, pl.w, rank * pl.hl - 1, pl.hl + 2, 64, s));
       HDRVAE_TRY(gn_scratch_reset(stats, 1, pl.gn_chunks, s));
       ConvIO io; io.x = lat; io.y = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
-      return run_conv(ctx, ctx->conv_in, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
+      if (x16) { io.y_dtype = x_dt; io.y_scale = x_scale; }
+      HDRVAE_TRY(run_conv(ctx, ctx->conv_in, io, 1, H, W, HDRVAE_CONV_TCGEN05, s));
+      return x16 ? zero_border_halos(st, x, H, W, 512, 2, s) : 0;
     });
-    rows_stats_and_halo(st, x, H, W, 512, nullptr, 0);
+    rows_stats_and_halo(st, x, H, W, 512, nullptr, 0, x_eb);
   }
   rows_res(st, ctx->mid1, H, W);
   {
@@ -905,7 +957,7 @@ static int build_rows_program(hdrvae_rows* st) {
     float* x = st->x;
     float* hscr = st->hbuf;                                   // idle across the attention: lends its memory to the key-split partials
     const size_t hscr_bytes = (size_t)(8 * pl.hl + 2) * 8 * pl.w * 256 * 4;
-    rows_gn(st, x, ctx->attn_norm, false, H, W);
+    rows_gn(st, x, ctx->attn_norm, false, H, W, x_dt, 1.f / x_scale);
     rows_compute(st, [=](cudaStream_t s) {
       const uint16_t* tl = reinterpret_cast<const uint16_t*>(t) + (size_t)W * 512;      // interior rows of the slab
       if (pl.Tp != pl.T) {
@@ -929,31 +981,35 @@ static int build_rows_program(hdrvae_rows* st) {
       HDRVAE_TRY(attention_rows(ctx, ws, pl.off_s, pl.off_p, pl.off_inv, pl.off_part, hscr, hscr_bytes, pl.s_rows,
                                 qk + (size_t)rank * pl.Tl * 1024, pl.Tl, qk + 512, vt, pl.T, pl.Tp, o, 1.0f, s));
       ConvIO io; io.x = o; io.y = x; io.residual = x; io.stats = stats; io.stats_chunks = pending; io.x_pad = 0; io.y_pad = 1;
+      if (x16) { io.y_dtype = x_dt; io.y_scale = x_scale; io.res_dtype = x_dt; io.res_scale = 1.f / x_scale; }
       return run_conv(ctx, ctx->proj_out, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
     });
-    rows_stats_and_halo(st, x, H, W, 512, nullptr, 0);
+    rows_stats_and_halo(st, x, H, W, 512, nullptr, 0, x_eb);
   }
   rows_res(st, ctx->mid2, H, W);
   for (int lvl = 3; lvl >= 0; --lvl) {
     for (int i = 0; i < 3; ++i) rows_res(st, ctx->up[lvl][i], H, W);
     if (lvl != 0) {
       float* hb = st->hbuf;
+      float* xs = st->x;
       const PackedConv* up = &ctx->upsample[lvl];
       const int Hc = H, Wc = W;
       rows_compute(st, [=](cudaStream_t s) {
         ConvIO io; io.x = xa; io.y = hb; io.alpha = 1.0f / kRawOperandScale; io.x_pad = io.y_pad = 1;
-        if (lvl <= 2) { io.y2 = xb; io.y2_dtype = dt; io.y2_scale = kRawOperandScale; }
+        if (x16) { io.x = xs; io.y_dtype = x_dt; io.y_scale = x_scale; }
+        else if (lvl <= 2) { io.y2 = xb; io.y2_dtype = dt; io.y2_scale = kRawOperandScale; }
         io.stats = stats; io.stats_chunks = pending;
-        return run_conv(ctx, *up, io, 1, Hc, Wc, HDRVAE_CONV_TCGEN05, s);
+        HDRVAE_TRY(run_conv(ctx, *up, io, 1, Hc, Wc, HDRVAE_CONV_TCGEN05, s));
+        return x16 ? zero_border_halos(st, hb, 2 * Hc, 2 * Wc, up->cout, 2, s) : 0;
       });
       H *= 2; W *= 2;
-      rows_stats_and_halo(st, hb, H, W, up->cout, nullptr, 0);
+      rows_stats_and_halo(st, hb, H, W, up->cout, nullptr, 0, x_eb);
       std::swap(st->x, st->hbuf);
     }
   }
   {
     float* x = st->x;
-    rows_gn(st, x, ctx->norm_out, true, H, W);
+    rows_gn(st, x, ctx->norm_out, true, H, W, x_dt, 1.f / x_scale);
     void* epi = ws + pl.off_epi;
     float* hscratch = st->hbuf;                       // the other fp32 stream buffer is free by now
     rows_compute(st, [=](cudaStream_t s) {

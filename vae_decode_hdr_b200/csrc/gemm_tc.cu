@@ -139,6 +139,7 @@ enum : int {
   EPI_RES2 = 128,    // + second fp32 residual (end of an RRDB: 0.04 acc + 0.2 x2 + x0)
   EPI_ROWMAX = 256,  // attention pass 1: per-row max of the scores, nothing stored (GemmParams::row_mode 1)
   EPI_EXPSUM = 512,  // attention pass 2: exp(score - row max) as the 16-bit output + per-row sums (row_mode 2)
+  EPI_RES16 = 1024,  // + residual stored as a (scaled) 16-bit tensor of type res_dtype: t += res_scale * r
 };
 
 template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0>
@@ -478,7 +479,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool kGen = (EPI & EPI_GENERIC) != 0;
     const bool out_f32 = kGen ? (p.out_dtype == DT_F32) : ((EPI & EPI_OUT16) == 0);
     const bool has_res_f32 = kGen ? (p.residual != nullptr && p.res_dtype == DT_F32) : ((EPI & EPI_RES) != 0);
-    const bool has_res_16 = kGen && p.residual != nullptr && p.res_dtype != DT_F32;
+    const bool has_res_16 = kGen ? (p.residual != nullptr && p.res_dtype != DT_F32) : ((EPI & EPI_RES16) != 0);
+    const bool res_bf = p.res_dtype == DT_BF16;
     const bool has_out2 = kGen ? (p.out2 != nullptr) : ((EPI & EPI_OUT2) != 0);
     const bool has_stats = kGen ? (p.stats != nullptr) : ((EPI & EPI_STATS) != 0);
     const bool row_ops = kGen ? (p.bias_per_row != 0 || p.row_scale != nullptr) : ((EPI & EPI_ROWOPS) != 0);
@@ -550,11 +552,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const long long org = img_off + ty_off * p.out_row_stride + tx_off * p.out_px_stride;
           const long long org2 = (long long)img * o2_img + n0 + ty_off * o2_row + tx_off * o2_px;
           float4 rres2[8];
+          uint2 rres16[8];
           auto fetch_res = [&](long long origin, int ci, float4 (&dst)[8]) {
             if constexpr ((EPI & EPI_RES) != 0) {
               const float* r = resf + origin + ci * 32;   // plain loads: the residual may alias the output
 #pragma unroll
               for (int it = 0; it < 8; ++it) dst[it] = *reinterpret_cast<const float4*>(r + lo[it]);
+            }
+            if constexpr ((EPI & EPI_RES16) != 0) {
+              const uint16_t* r = reinterpret_cast<const uint16_t*>(p.residual) + origin + ci * 32;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) rres16[it] = *reinterpret_cast<const uint2*>(r + lo[it]);
             }
           };
           fetch_res(org, 0, rres_a);
@@ -611,6 +619,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if constexpr ((EPI & EPI_RES2) != 0) {
                 t01 = f2_add(t01, make_float2(rres2[it].x, rres2[it].y));
                 t23 = f2_add(t23, make_float2(rres2[it].z, rres2[it].w));
+              }
+              if constexpr ((EPI & EPI_RES16) != 0) {
+                float2 r01, r23;
+                if (res_bf) {
+                  r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres16[it].x));
+                  r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres16[it].y));
+                } else {
+                  r01 = __half22float2(*reinterpret_cast<const __half2*>(&rres16[it].x));
+                  r23 = __half22float2(*reinterpret_cast<const __half2*>(&rres16[it].y));
+                }
+                t01 = f2_fma(r01, rs2, t01);
+                t23 = f2_fma(r23, rs2, t23);
               }
               if constexpr ((EPI & EPI_LRELU) != 0) {
                 t01.x = t01.x < 0.f ? t01.x * lrelu : t01.x; t01.y = t01.y < 0.f ? t01.y * lrelu : t01.y;
@@ -842,7 +862,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (has_res2) { t.x += rres2[it].x; t.y += rres2[it].y; t.z += rres2[it].z; t.w += rres2[it].w; }
           if (has_res_16 && live) {
-            // 16-bit residual (test entry only); plain load: the residual may alias the output
+            // 16-bit residual (the scaled 16-bit residual stream, or the test entry); plain load: it may alias the output
             const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + poff[it] + col);
             float2 lo, hi;
             if (p.res_dtype == DT_BF16) {
@@ -852,7 +872,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
               hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
             }
-            t.x += lo.x; t.y += lo.y; t.z += hi.x; t.w += hi.y;
+            t.x = fmaf(lo.x, res_scale, t.x); t.y = fmaf(lo.y, res_scale, t.y);
+            t.z = fmaf(hi.x, res_scale, t.z); t.w = fmaf(hi.y, res_scale, t.w);
           }
           if (has_lrelu) {
             t.x = t.x < 0.f ? t.x * lrelu : t.x; t.y = t.y < 0.f ? t.y * lrelu : t.y;
@@ -1132,7 +1153,8 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
     return use_cg == 2 ? launch_tc<64, false, 2, EPI_GENERIC>(p, num_sms, stream)
                        : launch_tc<64, false, 1, EPI_GENERIC>(p, num_sms, stream);
   }
-  if (use_cg == 2 && !tf32 && p.lrelu == 0.f && p.residual2 == nullptr && (p.res_scale == 0.f || p.res_scale == 1.f)) {
+  const bool res16 = p.residual != nullptr && p.res_dtype != DT_F32;
+  if (use_cg == 2 && !tf32 && p.lrelu == 0.f && p.residual2 == nullptr && (p.res_scale == 0.f || p.res_scale == 1.f || res16)) {
     // specialised epilogues for what the decoder launches; anything else takes the generic build
     int epi = 0;
     const bool simple_res = p.residual == nullptr || p.res_dtype == DT_F32;
@@ -1146,6 +1168,8 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       } else {
         epi = -1;
       }
+    } else if (res16 && !p.round_tf32 && p.out_dtype == p.res_dtype && p.out2 == nullptr && !rowops && p.stats != nullptr) {
+      epi = EPI_OUT16 | EPI_RES16 | EPI_STATS;     // the scaled 16-bit residual stream, updated in place
     } else {
       epi = -1;
     }
@@ -1162,6 +1186,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<128, false, 2, EPI_OUT16 | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_STATS)) return launch_tc<128, false, 2, EPI_RES | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_OUT2 | EPI_STATS)) return launch_tc<128, false, 2, EPI_RES | EPI_OUT2 | EPI_STATS, 3>(p, num_sms, stream);
+      if (epi == (EPI_OUT16 | EPI_RES16 | EPI_STATS)) return launch_tc<128, false, 2, EPI_OUT16 | EPI_RES16 | EPI_STATS, 3>(p, num_sms, stream);
       if (epi == 0) return launch_tc<128, false, 2, 0, 3>(p, num_sms, stream);
       if (epi == EPI_RES) return launch_tc<128, false, 2, EPI_RES, 3>(p, num_sms, stream);
     }
@@ -1170,6 +1195,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       // waited for operands 60 % of the time)
       if (epi == (EPI_OUT2 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT2 | EPI_STATS, 1>(p, num_sms, stream);
       if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1>(p, num_sms, stream);
+      if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_STATS, 1>(p, num_sms, stream);
       HDRVAE_REQUIRE(false, "gemm_tc: no slab build for this upsample epilogue (%d)", epi);
     }
     if (p.slab && !n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
@@ -1178,6 +1204,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_STATS, 1>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_STATS, 1>(p, num_sms, stream);
       if (epi == (EPI_RES | EPI_OUT2 | EPI_STATS)) return launch_tc<256, false, 2, EPI_RES | EPI_OUT2 | EPI_STATS, 1>(p, num_sms, stream);
+      if (epi == (EPI_OUT16 | EPI_RES16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_RES16 | EPI_STATS, 1>(p, num_sms, stream);
     }
 #define HDRVAE_EPI_CASE(E)                                                                       \
     case E:                                                                                      \
@@ -1192,6 +1219,7 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       HDRVAE_EPI_CASE(EPI_OUT16)
       HDRVAE_EPI_CASE(EPI_OUT16 | EPI_STATS)
       HDRVAE_EPI_CASE(EPI_OUT16 | EPI_ROWOPS)
+      HDRVAE_EPI_CASE(EPI_OUT16 | EPI_RES16 | EPI_STATS)
       default: break;
     }
 #undef HDRVAE_EPI_CASE
