@@ -157,6 +157,11 @@ int run_conv(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int B, int
     p.tw_log2 = 3; p.TW = 8; p.TH = 16;
     p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16;
   }
+  if (io.xf_scale != nullptr) {
+    HDRVAE_REQUIRE(p.slab && pc.w_dtype == DT_F16 && io.x_channels == 0, "run_conv: the fused GroupNorm needs the slab form and fp16 operands");
+    p.xf_scale = io.xf_scale; p.xf_shift = io.xf_shift; p.xf_in_scale = io.xf_in_scale;
+    p.xf_y_lo = io.xf_y_lo; p.xf_y_hi = io.xf_y_hi < 0 ? H : io.xf_y_hi;
+  }
   if (io.x2 != nullptr) {
     HDRVAE_REQUIRE(p.slab && io.pc2 != nullptr && io.pc2->ks == 1 && io.pc2->w_dtype == pc.w_dtype && io.pc2->kmul == 1 &&
                    io.pc2->cout == pc.cout, "run_conv: the fused 1x1 conv needs the slab form");
@@ -373,6 +378,21 @@ static bool x_is_16bit(hdrvae_ctx* ctx) {
   return on && nin_on && !ctx->high && ctx->op_dtype == DT_F16 && ctx->conv_impl == HDRVAE_CONV_TCGEN05 && h_is_16bit(ctx);
 }
 
+// GroupNorm + SiLU applied inside the consuming conv (GemmParams::xf_*) instead of by the streaming kernel: for the 3x3
+// slab convs whose input is a scaled fp16 tensor (x and h in the default mode).  HDRVAE_FUSE_GN=0 keeps the streaming kernel.
+static bool gn_is_fused(hdrvae_ctx* ctx, const PackedConv& pc, const ConvIO& io, int x_dtype, int H, int W) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("HDRVAE_FUSE_GN");
+    const char* g = getenv("HDRVAE_CTA_GROUP");
+    on = ((e && atoi(e) == 0) || (g && atoi(g) == 1)) ? 0 : 1;      // the fused builds are CTA-pair builds
+  }
+  // (256-column tiles only: a 128-column slab's MMAs are too short to hide the transform behind, gemm_tc.cu)
+  return on && x_is_16bit(ctx) && x_dtype == DT_F16 && pc.w_dtype == DT_F16 && pc.kmul == 1 && !pc.upsample && pc.ks == 3 &&
+         pc.cout_pad >= 256 && pc.cin_pad % 64 == 0 && ctx->cta_group != 1 && io.x2 == nullptr && io.y_dtype == DT_F16 &&
+         io.stats != nullptr && conv_takes_slab(pc, io, H, W, ctx->conv_impl);
+}
+
 static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
   return ctx->conv_impl == HDRVAE_CONV_TCGEN05 ? reinterpret_cast<float*>(st->gn) : nullptr;
 }
@@ -382,7 +402,19 @@ static float* stats_ptr(hdrvae_ctx* ctx, DecState* st) {
 // DESIGN.md §8 — removed in round 2; last present in commit 93846d6.)
 static int gn_before_conv(hdrvae_ctx* ctx, const void* x, const NormW& nw, const PackedConv& pc, ConvIO* io, DecState* st,
                           int B, int H, int W, cudaStream_t s, int x_dtype = DT_F32, float x_scale = 1.f) {
-  (void)pc;
+  if (gn_is_fused(ctx, pc, *io, x_dtype, H, W)) {
+    // only the reduction of the producer's partials runs as a kernel (-> per-(image, channel) scale / shift); the conv's
+    // transform warps normalise the scaled fp16 tensor as it lands in shared memory: no normalised copy in HBM
+    char pname[64];
+    snprintf(pname, sizeof pname, "groupnorm statistics C=%d @%dx%d", nw.C, B, H * W);
+    ProfScope prof(pname, 0.0, 0.0, s);
+    const int partials = st->pending;
+    st->pending = 0;
+    const float* scale = nullptr; const float* shift = nullptr;
+    HDRVAE_TRY(launch_gn_scale_shift(B, H * W, nw.C, nw.gamma, nw.beta, st->gn, st->gn_chunks, partials, s, &scale, &shift));
+    io->x = x; io->xf_scale = scale; io->xf_shift = shift; io->xf_in_scale = x_scale;
+    return 0;
+  }
   HDRVAE_TRY(run_gn(ctx, x, x_dtype, st->t, B, H * W, nw, true, st, s, -1, x_scale));
   io->x = st->t;
   return 0;
@@ -872,16 +904,31 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
   const bool x16 = x_is_16bit(ctx);
   const int x_dt = x16 ? ctx->op_dtype : DT_F32;
   const float x_scale = x16 ? kRawOperandScale : 1.f;
-  rows_gn(st, x, rw.n1, true, H, W, x_dt, 1.f / x_scale);
+  // GroupNorm applied inside the conv (same rule as the single-GPU program): the conv reads the scaled fp16 slab itself,
+  // halo rows included; a border rank's outer halo row is padding, not an image row
+  void* gn = st->ws + st->pl.off_gn;
+  const int gn_chunks = st->pl.gn_chunks;
+  const int y_lo = st->rank == 0 ? 0 : -1, y_hi = st->rank == st->pl.world - 1 ? H : H + 1;
+  const double world_rows = (double)H * st->pl.world;
+  ConvIO probe1; probe1.y = hb; probe1.y_dtype = h_dt; probe1.stats = stats;
+  const bool f1 = gn_is_fused(ctx, rw.c1, probe1, x_dt, H, W);
+  if (!f1) rows_gn(st, x, rw.n1, true, H, W, x_dt, 1.f / x_scale);
   rows_compute(st, [=](cudaStream_t s) {
     ConvIO io; io.x = t; io.y = hb; io.stats = stats; io.stats_chunks = pending; io.x_pad = io.y_pad = 1;
     io.y_dtype = h_dt; io.y_scale = h_scale;
+    if (f1) {
+      HDRVAE_TRY(launch_gn_scale_shift_from_sums(1, r->n1.C, r->n1.gamma, r->n1.beta, gn, gn_chunks,
+                                                 world_rows * (double)W * (double)(r->n1.C / 32), s, &io.xf_scale, &io.xf_shift));
+      io.x = x; io.xf_in_scale = 1.f / x_scale; io.xf_y_lo = y_lo; io.xf_y_hi = y_hi;
+    }
     return run_conv(ctx, r->c1, io, 1, H, W, HDRVAE_CONV_TCGEN05, s);
   });
   rows_stats_and_halo(st, hb, H, W, rw.c1.cout, nullptr, 0, h16 ? 2 : 4);
-  rows_gn(st, hb, rw.n2, true, H, W, h_dt, 1.f / h_scale);
   const bool fused_nin = nin_is_fused(ctx, rw, H, W);
   float* out = (rw.has_nin && (!fused_nin || x16)) ? hb : x;      // 16-bit stream: the shortcut reads x itself, so not in place
+  ConvIO probe2; probe2.y = out; probe2.residual = rw.has_nin ? nullptr : out; probe2.y_dtype = x_dt; probe2.stats = stats;
+  const bool f2 = !rw.has_nin && gn_is_fused(ctx, rw.c2, probe2, h_dt, H, W);     // (a shortcut block writes over h: not fused)
+  if (!f2) rows_gn(st, hb, rw.n2, true, H, W, h_dt, 1.f / h_scale);
   rows_compute(st, [=](cudaStream_t s) {
     if (x16) {
       // the residual stream is the scaled 16-bit tensor (see x_is_16bit): in place with a 16-bit residual, or — with a
@@ -890,6 +937,11 @@ static void rows_res(hdrvae_rows* st, const ResW& rw, int H, int W) {
       io.y_dtype = x_dt; io.y_scale = x_scale;
       if (fused_nin) { io.x2 = x; io.pc2 = &r->nin_x16; io.bias = r->bias_c2_nin; }
       else { io.residual = out; io.res_dtype = x_dt; io.res_scale = 1.f / x_scale; }
+      if (f2) {
+        HDRVAE_TRY(launch_gn_scale_shift_from_sums(1, r->n2.C, r->n2.gamma, r->n2.beta, gn, gn_chunks,
+                                                   world_rows * (double)W * (double)(r->n2.C / 32), s, &io.xf_scale, &io.xf_shift));
+        io.x = hb; io.xf_in_scale = 1.f / h_scale; io.xf_y_lo = y_lo; io.xf_y_hi = y_hi;
+      }
       HDRVAE_TRY(run_conv(ctx, r->c2, io, 1, H, W, HDRVAE_CONV_TCGEN05, s));
       return zero_border_halos(st, out, H, W, r->c2.cout, 2, s);
     }

@@ -120,6 +120,13 @@ struct GemmParams {
   int stats_chunks_per_img, stats_chunk0;
   int slab;          // 3x3 conv with narrow output (<= 64 columns): 8x16-pixel tiles whose 10x18 activation slab is loaded
                      // ONCE per K block and read by the 9 taps as shifted descriptors (gemm_tc.cu "slab" variant)
+  // GroupNorm + SiLU applied to A inside the kernel (slab form, fp16 A): two otherwise idle warps rewrite every landed
+  // slab in place as silu(a * xf_in_scale * xf_scale[img][c] + xf_shift[img][c]) before the MMAs read it; pixels outside
+  // the image (x outside [0, W), y outside [xf_y_lo, xf_y_hi)) become the conv's zero padding.  null: A is used as it is.
+  const float* xf_scale;
+  const float* xf_shift;
+  float xf_in_scale;
+  int xf_y_lo, xf_y_hi;
   int cta_group;     // 0 = library default (CTA pairs), 1 = single CTA, 2 = CTA pair (tcgen05 cta_group::2)
   int dbg;           // diagnostics (env HDRVAE_GEMM_DBG): bit0 = producer skips the TMA loads, bit1 = issuer skips the MMAs
 };

@@ -33,7 +33,11 @@ size_t quantile_scratch_bytes();
 int launch_quantiles(const float* x, long long n, const unsigned long long* ranks_host, int nq, float* out, void* scratch,
                      cudaStream_t s);
 size_t gn_scratch_bytes(int B, int C, int max_chunks);
-int gn_scratch_reset(void* scratch, int B, int max_chunks, cudaStream_t s);   // once before a scratch buffer's first use
+int gn_scratch_reset(void* scratch, int B, int max_chunks, cudaStream_t s);
+int launch_gn_scale_shift_from_sums(int B, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
+                                    double count, cudaStream_t s, const float** scale_out, const float** shift_out);
+int launch_gn_scale_shift(int B, int HW, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
+                          int partial_chunks, cudaStream_t s, const float** scale_out, const float** shift_out);   // once before a scratch buffer's first use
 int launch_groupnorm(const void* x, int x_dtype, void* y, int y_dtype, int B, int HW, int C, const float* gamma,
                      const float* beta, bool silu, void* scratch, int max_chunks, int partial_chunks, cudaStream_t s,
                      float in_scale = 1.f);
@@ -198,6 +202,12 @@ struct ConvIO {
   const void* x2 = nullptr;
   const PackedConv* pc2 = nullptr;
   const float* bias = nullptr;
+  // GroupNorm + SiLU of x applied inside the conv (GemmParams::xf_*): per-(image, channel) scale / shift, the scale of a
+  // scaled 16-bit x, and which rows of x are image rows (row tiling: a border rank's outer halo row is padding)
+  const float* xf_scale = nullptr;
+  const float* xf_shift = nullptr;
+  float xf_in_scale = 1.f;
+  int xf_y_lo = 0, xf_y_hi = -1;  // -1: H
 };
 
 // true when run_conv would take the slab form of the tensor-core kernel (needed by the fused nin_shortcut path)

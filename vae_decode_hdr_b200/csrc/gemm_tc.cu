@@ -142,8 +142,14 @@ enum : int {
   EPI_RES16 = 1024,  // + residual stored as a (scaled) 16-bit tensor of type res_dtype: t += res_scale * r
 };
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// XF builds (GroupNorm + SiLU applied to the activation slabs in place) carry two more warpgroups: 8 transform warps per
+// CTA, two per scheduler (warps 2 and 3 stay idle: with them as transform warps two schedulers carried twice the load).
+constexpr int kXfWarps = 8;
+constexpr int kXfThreads = kNumThreads + kXfWarps * 32;  // 640
+constexpr int kRegsControlXf = 64, kRegsXf = 64, kRegsEpilogueXf = 144;   // 128 x 64 + 256 x 64 + 256 x 144 = 640 x 96 (the launch allocation)
+
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int KSUB, int SLAB = 0, bool XF = false>
+__global__ void __launch_bounds__(XF ? kXfThreads : kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using Cfg = TcConfig<BLOCK_N, CG, KSUB, SLAB>;
@@ -170,7 +176,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint64_t* slab_full_bar = bars + 2 * kStages + 4;   // [3]
   uint64_t* slab_empty_bar = bars + 2 * kStages + 7;  // [3]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 10);
+  uint64_t* slab_ready_bar = bars + 2 * kStages + 10; // [3] fused GroupNorm: the transform warps are done with a slab
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,6 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 3; ++i) {
       ptx::mbar_init(&slab_full_bar[i], 1);
       ptx::mbar_init(&slab_empty_bar[i], 1);
+      ptx::mbar_init(&slab_ready_bar[i], CG * kXfWarps);    // the transform warps of every CTA of the pair
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);
@@ -212,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = p.ntaps * kb_per_tap;
   const int kb2_blocks = SLAB ? p.k2 / kElemsPerRow : 0;      // extra K blocks from the second tensor (fused 1x1 conv)
   const int ntg = SLAB ? p.ntaps / SLAB : 0;                  // slab form: B stages per K block (taps in groups of SLAB)
+  constexpr bool xf = XF && SLAB > 0;                         // GroupNorm + SiLU applied to the slabs in place
 
   // Producer and MMA issuer run as whole (converged) warps with one elected lane issuing: loop state and
   // addresses are then warp-uniform and stay in the uniform datapath that UTMALDG / UTCHMMA read from (a
@@ -221,12 +230,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_groups = (num_kb + KSUB - 1) / KSUB;
   // (each role's code sits INSIDE the branch that changed its register budget: ptxas applies the smaller budget to
   // everything after a join of the two)
-  if (warp < 4) {
-  ptx::reg_dec<kRegsControl>();
+  if (warp < 4 || warp >= 12) {
+  if (!XF) ptx::reg_dec<kRegsControl>();
+  else if (warp < 4) ptx::reg_dec<kRegsControlXf>();
+  else ptx::reg_dec<kRegsXf>();
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0, ss = 0;
     uint32_t phase = 0, sphase = 0;
+    // slab cursor (slab form): (work item, K block) of the next activation slab to request
+    int s_tile = w_first, s_kb = 0;
+    auto issue_next_slab = [&]() {
+      if (s_tile >= num_tiles) return;
+      const int mt = (s_tile / p.n_tiles_n) * CG + (int)rank;
+      const int img = mt / tiles_per_img;                  // == n_img for the empty tile: out of bounds -> zeros
+      const int rem = mt - img * tiles_per_img;
+      const int ty = rem / p.tiles_x;
+      const int tx = rem - ty * p.tiles_x;
+      const int x0 = tx * p.TW, y0 = ty * p.TH;
+      ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
+      if (ptx::elect_one()) {
+        uint8_t* sa = smem_slab + ss * Cfg::kSlabBuf;
+        // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+8 (outside the image: zero fill = the conv padding)
+        if (xf) {
+          // fused GroupNorm: every CTA's own barrier sees its own slab land (its transform warps wait there)
+          ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)kSlabBytes);
+          ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], s_kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+        } else {
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
+          if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], s_kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+          else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], s_kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
+        }
+      }
+      __syncwarp();
+      if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+      if (++s_kb == kb_per_tap) { s_kb = 0; s_tile += w_step; }
+    };
     for (int tile = w_first; tile < num_tiles; tile += w_step) {
       const int nt = tile % p.n_tiles_n;
       const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
@@ -237,17 +276,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / CG);
       const int bk0 = (int)(img * p.b_img_k_stride);       // split-K: this image's K range of B
       if constexpr (SLAB > 0) {
+        if (tile == w_first) issue_next_slab();             // the very first slab; afterwards always one K block ahead
         for (int kb = 0; kb < kb_per_tap; ++kb) {
-          ptx::mbar_wait(&slab_empty_bar[ss], sphase ^ 1);
-          if (ptx::elect_one()) {
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&slab_full_bar[ss], (uint32_t)(CG * kSlabBytes));
-            uint8_t* sa = smem_slab + ss * Cfg::kSlabBuf;
-            // slab: rows y0-1 .. y0+16, pixels x0-1 .. x0+14 (outside the image: zero fill = the conv padding)
-            if (CG == 2) ptx::tma_load_4d_pair(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-            else ptx::tma_load_4d(sa, &tmA, &slab_full_bar[ss], kb * kElemsPerRow, x0 - 1, y0 - 1 + p.y_pad, img);
-          }
-          __syncwarp();
-          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+          // The slab AFTER this K block's is requested before this K block's weights: the weight ring is shorter than a K
+          // block's taps (7 one-tap stages for 9 taps), so in program order a slab could only be requested once the MMAs
+          // of the previous one were under way — no problem while a slab is usable as it lands, but with the GroupNorm
+          // transform between landing and MMAs it made the period 7 150 instead of 4 608 cycles per slab.
+          issue_next_slab();
           for (int tg = 0; tg < ntg; ++tg) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (ptx::elect_one()) {
@@ -349,8 +384,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (SLAB > 0) {
         for (int kb = 0; kb < kb_per_tap; ++kb) {
           if (tim) tq = clock64();
-          ptx::mbar_wait(&slab_full_bar[ss], sphase);
+          ptx::mbar_wait(xf ? &slab_ready_bar[ss] : &slab_full_bar[ss], sphase);
           if (tim) w_slab += clock64() - tq;
+          ptx::tc_fence_after_sync();
           // descriptors are built once per slab / stage; a tap only ADDS its line offset (>> 4) to the 14-bit address field
           // (all of shared memory fits in it, so no carry leaves the field): two 64-bit uniform adds per MMA instead of a
           // shift-mask-or chain — the 32- and 64-column builds (16- and 32-cycle MMAs) are issue-bound
@@ -464,9 +500,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tim && blockIdx.x == 0 && lane == 0)
       printf("gemm_tc<%d,cg%d,epi%d,slab%d> issuer: %lld cycles, %d tiles x %d k-blocks; waited: accumulator %lld, slab %lld, B stage %lld\n",
              BLOCK_N, CG, EPI, SLAB, clock64() - t_begin, (num_tiles - w_first + w_step - 1) / w_step, num_kb, w_acc, w_slab, w_b);
+  } else if (warp >= 12 && xf) {
+    // ------------------------------------------------------------ fused GroupNorm + SiLU (warps 12..19 of every CTA)
+    // A slab is 180 lines of 128 bytes = 64 channels of one halo pixel each, 16-byte chunk j of line L stored at chunk
+    // j ^ (L & 7).  Thread t of the 256 owns logical chunk c = t & 7 (channels 8c .. 8c+7 of the K block: its 16 scale /
+    // shift values stay in registers) of the lines L = (t >> 3) + 32 i, all of which have the same L & 7: one fixed
+    // physical chunk.  Packed fp32 arithmetic (FFMA2 / FMUL2 / FADD2), the same operations in the same order as
+    // gn_apply_kernel + silu_nr (groupnorm.cu), so the operand the MMAs read is bit-identical to the one the streaming
+    // kernel would have written to HBM and the conv read back: 4 bytes per element of traffic less per layer.
+    // Only for 256-column tiles: a slab then feeds 4 608 cycles of MMAs, the transform costs ~3 000 warp instructions;
+    // behind the 1 152 cycles of a 128-column slab it cannot hide (measured with two warps: 5.1 M cycles instead of 1.0 M).
+    if constexpr (xf) {
+      const int tl = (warp - 12) * 32 + lane;                            // 0 .. 255
+      const int c = tl & 7, lg = tl >> 3;                                // lg = 0 .. 31
+      const uint32_t chunk_off = (uint32_t)((c ^ (lg & 7)) << 4);
+      const int C = p.k_per_tap;
+      const int y_hi = p.xf_y_hi;
+      const float2 nlog2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
+      const float2 one2 = make_float2(1.f, 1.f), two2 = make_float2(2.f, 2.f);
+      int ss = 0;
+      uint32_t sphase = 0;
+      const bool tim = (p.dbg & 32) != 0;                          // CTA 0, first transform warp: waiting for slabs / transforming
+      long long w_land = 0, w_work = 0, tq = 0;
+      for (int tile = w_first; tile < num_tiles; tile += w_step) {
+        const int mt = (tile / p.n_tiles_n) * CG + (int)rank;
+        const int img = mt / tiles_per_img;
+        const int rem = mt - img * tiles_per_img;
+        const int ty = rem / p.tiles_x;
+        const int tx = rem - ty * p.tiles_x;
+        const int x0 = tx * p.TW - 1, y0 = ty * p.TH - 1;          // image coordinates of slab line 0
+        const bool img_ok = img < p.n_img;
+        for (int kb = 0; kb < kb_per_tap; ++kb) {
+          float2 a2[4], b2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int ch = kb * kElemsPerRow + c * 8 + 2 * e;
+            const bool ok = img_ok && ch + 1 < C;
+            a2[e].x = ok ? __ldg(p.xf_scale + (long long)img * C + ch) * p.xf_in_scale : 0.f;
+            a2[e].y = ok ? __ldg(p.xf_scale + (long long)img * C + ch + 1) * p.xf_in_scale : 0.f;
+            b2[e].x = ok ? __ldg(p.xf_shift + (long long)img * C + ch) : 0.f;
+            b2[e].y = ok ? __ldg(p.xf_shift + (long long)img * C + ch + 1) : 0.f;
+          }
+          if (tim) tq = clock64();
+          ptx::mbar_wait(&slab_full_bar[ss], sphase);
+          if (tim) { const long long now = clock64(); w_land += now - tq; tq = now; }
+          uint8_t* base = smem_slab + ss * Cfg::kSlabBuf + chunk_off;
+          int r = lg / kSlabPitch, px = lg - r * kSlabPitch;       // slab row / pixel of line L = lg + 32 i
+#pragma unroll 2
+          for (int L = lg; L < kSlabRows * kSlabPitch; L += 32) {
+            uint4* q = reinterpret_cast<uint4*>(base + L * kRowBytes);
+            const int x = x0 + px, y = y0 + r;
+            const bool inside = x >= 0 && x < p.W && y >= p.xf_y_lo && y < y_hi;
+            uint4 v = *q;
+            __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = f2_fma(__half22float2(h[e]), a2[e], b2[e]);
+              float2 m = f2_mul(t, nlog2e);
+              float2 ex;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(fminf(m.x, 80.f)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(fminf(m.y, 80.f)));
+              const float2 d = f2_add(one2, ex);
+              const float2 nd = make_float2(-d.x, -d.y);
+              float2 rr = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(d.x)), __int_as_float(0x7EF311C7 - __float_as_int(d.y)));
+              rr = f2_mul(rr, f2_fma(nd, rr, two2));
+              rr = f2_mul(rr, f2_fma(nd, rr, two2));
+              const float2 o = f2_mul(t, rr);
+              h[e] = __floats2half2_rn(o.x, o.y);
+            }
+            if (!inside) v = make_uint4(0u, 0u, 0u, 0u);
+            *q = v;
+            px += 32 - 3 * kSlabPitch;                             // 32 lines on = 3 rows + 2 pixels
+            r += 3;
+            if (px >= kSlabPitch) { px -= kSlabPitch; ++r; }
+          }
+          ptx::fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core's reads
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) ptx::mbar_arrive_cluster_release(&slab_ready_bar[ss], 0);
+            else ptx::mbar_arrive(&slab_ready_bar[ss]);
+          }
+          if (tim) w_work += clock64() - tq;
+          if (++ss == Cfg::kSlabStages) { ss = 0; sphase ^= 1; }
+        }
+      }
+      if (tim && blockIdx.x == 0 && warp == 12 && lane == 0)
+        printf("gemm_tc<%d,cg%d,epi%d,slab%d> transform warp 0: waited for slabs to land %lld cycles, transformed them in %lld\n",
+               BLOCK_N, CG, EPI, SLAB, w_land, w_work);
+    }
   }
   } else {
-  ptx::reg_inc<kRegsEpilogue>();
+  if (XF) ptx::reg_inc<kRegsEpilogueXf>(); else ptx::reg_inc<kRegsEpilogue>();
   if ((warp - 4) < kActiveEpiWarps) {
     // ------------------------------------------------------------ epilogue (8 warps; 128 TMEM lanes x 2 column halves)
     // TMEM hands every thread one accumulator ROW (pixel).  Writing rows straight to global memory makes each
@@ -1050,7 +1174,7 @@ void choose_tile(int H, int W, GemmParams* p) {
   p->tiles_y = (H + p->TH - 1) / p->TH;
 }
 
-template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0>
+template <int BLOCK_N, bool kTf32, int CG, int EPI, int SLAB = 0, bool XF = false>
 static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   // two k-sub-blocks per pipeline stage for the 128-column tiles (their MMAs are short: 64 cycles each)
   constexpr int KSUB = SLAB ? 1 : (BLOCK_N <= 128) ? 2 : 1;
@@ -1066,7 +1190,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   HDRVAE_TRY(make_maps(p, BLOCK_N / CG, &maps, SLAB));  // a CTA of a pair stages half of the B rows
   static PerDeviceOnce attr_once;
   if (attr_once.first())
-    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HDRVAE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
   const long long m_tiles = (long long)p.n_img * p.tiles_x * p.tiles_y;
   const long long work = ((m_tiles + CG - 1) / CG) * p.n_tiles_n;
@@ -1075,7 +1199,7 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(XF ? kXfThreads : kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1086,7 +1210,10 @@ static int launch_tc(const GemmParams& p_in, int num_sms, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   HDRVAE_REQUIRE(p.k2 == 0 || (SLAB > 0 && Cfg::kFusedTensorFits), "gemm_tc: a fused second tensor needs the slab form with >= 16 KB ring slots");
-  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB>, maps.a, maps.b, maps.a2, maps.b2, p));
+  HDRVAE_REQUIRE((p.xf_scale != nullptr) == XF, "gemm_tc: fused-GroupNorm parameters and kernel build do not match");
+  HDRVAE_REQUIRE(!XF || (SLAB > 0 && p.ab_dtype == DT_F16 && p.xf_shift != nullptr && p.a_k_valid == 0),
+                 "gemm_tc: the fused GroupNorm needs the slab form and a dense fp16 activation tensor");
+  HDRVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kTf32, CG, EPI, KSUB, SLAB, XF>, maps.a, maps.b, maps.a2, maps.b2, p));
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1197,6 +1324,13 @@ int launch_gemm_tc(const GemmParams& p, int num_sms, cudaStream_t stream) {
       if (epi == EPI_STATS) return launch_tc<256, false, 2, EPI_STATS, 1>(p, num_sms, stream);
       if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_STATS, 1>(p, num_sms, stream);
       HDRVAE_REQUIRE(false, "gemm_tc: no slab build for this upsample epilogue (%d)", epi);
+    }
+    if (p.xf_scale != nullptr) {
+      HDRVAE_REQUIRE(p.slab && !n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0 && p.k2 == 0,
+                     "gemm_tc: the fused GroupNorm exists for the 256-column 3x3 slab convs");
+      if (epi == (EPI_OUT16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_STATS, 1, true>(p, num_sms, stream);
+      if (epi == (EPI_OUT16 | EPI_RES16 | EPI_STATS)) return launch_tc<256, false, 2, EPI_OUT16 | EPI_RES16 | EPI_STATS, 1, true>(p, num_sms, stream);
+      HDRVAE_REQUIRE(false, "gemm_tc: no fused-GroupNorm build for this epilogue (%d)", epi);
     }
     if (p.slab && !n128 && p.ntaps == 9 && p.TW == 8 && p.TH == 16 && p.b_img_k_stride == 0) {
       // 256-column tiles: slab variant with one tap of weights per stage (experiment switch HDRVAE_SLAB_MAXN)

@@ -386,6 +386,17 @@ int launch_gn_reduce_partials(void* scratch, int B, int C, int max_chunks, int n
   HDRVAE_CUDA_OK(cudaGetLastError());
   return 0;
 }
+// Row tiling, normalisation applied inside the consuming conv: only the all-reduced sums -> scale / shift.
+int launch_gn_scale_shift_from_sums(int B, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
+                                    double count, cudaStream_t s, const float** scale_out, const float** shift_out) {
+  float* scale = gn_scale_ptr(scratch, B, max_chunks);
+  float* shift = scale + (size_t)B * C;
+  gn_finalize_sums_kernel<<<B, 256, 0, s>>>(gn_sums_ptr(scratch, B, C, max_chunks), gamma, beta, scale, shift, C, count, 1e-6f);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  *scale_out = scale; *shift_out = shift;
+  return 0;
+}
 // x / y point at the first row to normalise; rows_px = pixels per image to process; count = elements per (image, group)
 // over ALL ranks
 int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride, void* y, int y_dtype, long long y_img_stride,
@@ -409,6 +420,22 @@ int launch_gn_apply_from_sums(const void* x, int x_dtype, long long x_img_stride
   }
   HDRVAE_LAUNCHED();
   HDRVAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Only the reduction: the producer's partials -> per-(image, channel) scale / shift in the scratch buffer (returned), for a
+// conv that applies the normalisation itself (gemm_tc.cu, GemmParams::xf_*).
+int launch_gn_scale_shift(int B, int HW, int C, const float* gamma, const float* beta, void* scratch, int max_chunks,
+                          int partial_chunks, cudaStream_t s, const float** scale_out, const float** shift_out) {
+  HDRVAE_REQUIRE(partial_chunks > 0 && C % 32 == 0, "groupnorm (fused into the conv): needs the producer's statistics");
+  float* scale = gn_scale_ptr(scratch, B, max_chunks);
+  float* shift = scale + (size_t)B * C;
+  gn_reduce_kernel<<<dim3(gn_slices(partial_chunks), B), 256, 0, s>>>(reinterpret_cast<const float*>(scratch), partial_chunks,
+                                                                       gn_slice_ptr(scratch, B, max_chunks), gn_ticket_ptr(scratch, B, max_chunks),
+                                                                       nullptr, gamma, beta, scale, shift, C, (double)HW * (double)(C / kGroups), 1e-6f);
+  HDRVAE_LAUNCHED();
+  HDRVAE_CUDA_OK(cudaGetLastError());
+  *scale_out = scale; *shift_out = shift;
   return 0;
 }
 
