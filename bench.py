@@ -408,11 +408,11 @@ def main():
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained",
                 # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 51 gemm_tc launches of one C2 step
-                # (profiles/r02_step7_ncu_dram_traffic_c2_summary.json, captured on this workload with the final round-2
+                # (profiles/r02_step8_ncu_dram_traffic_c2_summary.json, captured on this workload with the final round-2
                 # build: 26.1 GB read + 14.3 GB written; 58.3 GB before the 16-bit residual stream, round 1: 79.3 GB over 61
-                # launches).  The kernel is tensor bound; the figure shows there is no re-read waste (GroupNorm: 28.0 GB
-                # measured vs 29.4 GB by the kernels' own byte count)
-                "traffic": (40.42e9 if (B, L) == (4, 128) else None), "traffic_unit": "bytes per step, all conv launches (ncu)",
+                # launches).  The kernel is tensor bound; the figure shows there is no re-read waste (the remaining
+                # GroupNorm launches: 18.0 GB measured vs 18.4 GB by the kernels' own byte count; whole step 60.4 GB)
+                "traffic": (40.36e9 if (B, L) == (4, 128) else None), "traffic_unit": "bytes per step, all conv launches (ncu)",
                 "achieved_executed": executed_tf, "frac_executed": executed_tf / peak_tf,
                 # The sustained figure is cuBLAS running back to back at the power cap; in this step the convs alternate with
                 # HBM-bound kernels that draw less, so the cap lets them clock higher and the fractions above can pass 1.
