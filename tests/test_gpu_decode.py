@@ -248,3 +248,57 @@ def test_large_2048_decode_vs_gpu_oracle_and_row_tiling(setup):
         dec.to("cpu")
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
     assert st["pre_max"] == pytest.approx(rst["pre_max"], rel=5e-3)
+
+
+_SWITCH_CHILD = r"""
+import sys, torch
+sys.path.insert(0, ".")
+from oracle.flux_decoder import build_decoder, make_latent
+from vae_decode_hdr_b200.engine import HdrVaeEngine
+eng = HdrVaeEngine(build_decoder(0).state_dict(), "cuda:0")
+z = make_latent(2, 16, 24, seed=5).to("cuda:0")
+img, _ = eng.decode(z, "moderate")
+feat = eng.decode_features(z).float()
+torch.save({"img": img.cpu(), "feat": feat.cpu()}, sys.argv[1])
+"""
+
+
+def _decode_in_child(tmp_path, name, env_extra):
+    """The numeric-plan switches are read once per process, so the other setting runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    out = tmp_path / name
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sys.executable, "-c", _SWITCH_CHILD, str(out)], env=env, capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stderr[-2000:]
+    return torch.load(out)
+
+
+@pytest.mark.gpu
+def test_groupnorm_inside_the_conv_is_bit_identical_to_the_streaming_kernel(tmp_path):
+    """The transform warps of the 256-column convs (gemm_tc.cu, XF builds) perform gn_apply_kernel's operations in its
+    order on the slab in shared memory: features and image of a decode must not change by one bit when HDRVAE_FUSE_GN=0
+    sends every GroupNorm through the streaming kernel instead."""
+    fused = _decode_in_child(tmp_path, "fused.pt", {})
+    streamed = _decode_in_child(tmp_path, "streamed.pt", {"HDRVAE_FUSE_GN": "0"})
+    assert torch.equal(fused["feat"], streamed["feat"])
+    assert torch.equal(fused["img"], streamed["img"])
+
+
+@pytest.mark.gpu
+def test_fp16_residual_stream_against_the_fp32_stream_and_the_oracle(tmp_path):
+    """Default numeric plan (residual stream stored as scaled fp16) vs HDRVAE_X16=0 (fp32 stream) vs the fp32 oracle: both
+    within the 1e-2 image bound, and the cost of the 16-bit stream on the features stays below 1e-3 rel-L2."""
+    dec = build_decoder(0)
+    z = make_latent(2, 16, 24, seed=5)
+    with torch.no_grad():
+        ref, _, _ = ho.simple_hdr_decode(dec, z, "moderate", 1.0)
+        fref = dec.features(z).permute(0, 2, 3, 1)
+    x16 = _decode_in_child(tmp_path, "x16.pt", {})
+    x32 = _decode_in_child(tmp_path, "x32.pt", {"HDRVAE_X16": "0"})
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    e16, e32 = rel(x16["feat"], fref), rel(x32["feat"], fref)
+    assert e32 < 3e-3 and e16 < 4e-3 and e16 - e32 < 1e-3, (e16, e32)
+    assert rel(x16["img"], ref) < 1e-2 and rel(x32["img"], ref) < 1e-2
