@@ -151,6 +151,40 @@ __device__ __forceinline__ float silu_f(float v) {
 }
 // the same with exp on the special-function unit (ex2 + rcp): fewer instructions, two XU operations per element
 __device__ __forceinline__ float silu_mufu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot per two lanes of arithmetic.
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+// silu_nr on a pair: the same operations in the same order (so the results are bit-identical), FFMA2 / FMUL2 / FADD2 where
+// a packed form exists.  Used by the GroupNorm + SiLU streaming kernel and by the conv kernel's in-place slab transform.
+__device__ __forceinline__ float2 silu_nr2(float2 v) {
+  const float2 m = f2_mul(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(fminf(m.x, 80.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(fminf(m.y, 80.f)));
+  const float2 d = f2_add(make_float2(1.f, 1.f), e);
+  const float2 nd = make_float2(-d.x, -d.y);
+  const float2 two = make_float2(2.f, 2.f);
+  float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(d.x)), __int_as_float(0x7EF311C7 - __float_as_int(d.y)));
+  r = f2_mul(r, f2_fma(nd, r, two));
+  r = f2_mul(r, f2_fma(nd, r, two));
+  return f2_mul(v, r);
+}
 // ONE XU operation per element: ex2 on the special-function unit, the reciprocal of d = 1 + e^-v (d >= 1) by two Newton
 // steps on the FMA pipe from the integer-subtraction first guess (relative error 7.6e-6: far below the 16-bit output
 // rounding).  ncu on the streaming GroupNorm kernel: XU pipe 53 % busy, DRAM 57 %, issue 40 % with ex2 + rcp — neither

@@ -80,25 +80,6 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot per two lanes of epilogue arithmetic.
-__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
 __device__ __forceinline__ float round_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -516,8 +497,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t chunk_off = (uint32_t)((c ^ (lg & 7)) << 4);
       const int C = p.k_per_tap;
       const int y_hi = p.xf_y_hi;
-      const float2 nlog2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
-      const float2 one2 = make_float2(1.f, 1.f), two2 = make_float2(2.f, 2.f);
       int ss = 0;
       uint32_t sphase = 0;
       const bool tim = (p.dbg & 32) != 0;                          // CTA 0, first transform warp: waiting for slabs / transforming
@@ -555,17 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __half2* h = reinterpret_cast<__half2*>(&v);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 t = f2_fma(__half22float2(h[e]), a2[e], b2[e]);
-              float2 m = f2_mul(t, nlog2e);
-              float2 ex;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(fminf(m.x, 80.f)));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(fminf(m.y, 80.f)));
-              const float2 d = f2_add(one2, ex);
-              const float2 nd = make_float2(-d.x, -d.y);
-              float2 rr = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(d.x)), __int_as_float(0x7EF311C7 - __float_as_int(d.y)));
-              rr = f2_mul(rr, f2_fma(nd, rr, two2));
-              rr = f2_mul(rr, f2_fma(nd, rr, two2));
-              const float2 o = f2_mul(t, rr);
+              const float2 o = silu_nr2(f2_fma(__half22float2(h[e]), a2[e], b2[e]));
               h[e] = __floats2half2_rn(o.x, o.y);
             }
             if (!inside) v = make_uint4(0u, 0u, 0u, 0u);

@@ -210,6 +210,23 @@ template <int kExp> __device__ __forceinline__ float silu_sel(float v) {
   return kExp == 1 ? silu_mufu(v) : kExp == 2 ? silu_nr(v) : silu_f(v);
 }
 
+// v[j] = [silu](v[j] * a[j] + b[j]) for 8 channels of one pixel, in packed fp32 pairs (FFMA2 / FMUL2 / FADD2): the same
+// operations in the same order as the scalar form, bit for bit, and the SAME helper (silu_nr2) the conv kernel's in-place
+// slab transform uses, which is what keeps the two roads identical.  A third fewer instructions; measured neutral on the
+// kernel's time (0.484 vs 0.488 ms for the 128-channel layers at 4 x 1024^2): it waits on its latency chain, not on issue.
+template <bool kSilu, int kExp>
+__device__ __forceinline__ void norm_act8(float (&v)[8], const float (&a)[8], const float (&b)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    float2 t = f2_fma(make_float2(v[j], v[j + 1]), make_float2(a[j], a[j + 1]), make_float2(b[j], b[j + 1]));
+    if (kSilu) {
+      if (kExp == 2) t = silu_nr2(t);
+      else t = make_float2(silu_sel<kExp>(t.x), silu_sel<kExp>(t.y));
+    }
+    v[j] = t.x; v[j + 1] = t.y;
+  }
+}
+
 template <typename TIn, typename TOut, bool kSilu, int kMufu = 0>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __restrict__ scale,
@@ -244,22 +261,14 @@ gn_apply_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, const float* __
     for (int u = 0; u < U; ++u) Ld8<TIn>::ld(xin + ((long long)(p + u * p_step) * vpp + vi) * 8, v[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[u][j] = fmaf(v[u][j], a[j], b[j]);
-        if (kSilu) v[u][j] = silu_sel<kMufu>(v[u][j]);
-      }
+      norm_act8<kSilu, kMufu>(v[u], a, b);
       store8<TOut>(yout, (long long)(p + u * p_step), vpp, vi, v[u]);
     }
   }
   for (; p < p1; p += p_step) {
     float v[8];
     Ld8<TIn>::ld(xin + ((long long)p * vpp + vi) * 8, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = fmaf(v[j], a[j], b[j]);
-      if (kSilu) v[j] = silu_sel<kMufu>(v[j]);
-    }
+    norm_act8<kSilu, kMufu>(v, a, b);
     store8<TOut>(yout, (long long)p, vpp, vi, v);
   }
 }
