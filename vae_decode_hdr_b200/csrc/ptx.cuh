@@ -203,7 +203,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // same with release semantics at cluster scope: orders this thread's earlier shared-memory writes (made visible to the
-// async proxy by fence.proxy.async) before the arrival is observed by the waiting thread of the other CTA
+// async proxy by fence.proxy.async) before the arrival is observed by the waiting thread of the other CTA.
+// NOT for per-tile use: ptxas implements the cluster-scope release as MEMBAR.ALL.GPU (thousands of cycles; measured in the
+// conv kernel's slab transform, gemm_tc.cu).  Kept for one-off hand-overs only; nothing on a hot path calls it.
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
