@@ -7,5 +7,3 @@ echo "pytest rc=$?"; tail -3 gpurun_out/last_pytest.log | cut -c1-300
 echo "smoke rc=$?"; tail -2 gpurun_out/last_smoke.log | cut -c1-300
 ( timeout 900 python bench.py ) > gpurun_out/last_bench.json 2> gpurun_out/last_bench.err
 echo "bench rc=$?"; cut -c1-260 gpurun_out/last_bench.json
-( timeout 600 python bench.py --impl reference --steps 1 --warmup 0 ) > gpurun_out/last_bench_ref.json 2> gpurun_out/last_bench_ref.err
-echo "reference arm rc=$?"; cut -c1-300 gpurun_out/last_bench_ref.json
